@@ -1,0 +1,239 @@
+/*
+ * scade_b200 -- C ABI of the B200-native (sm_100a) SCADE per-ray renderer.
+ *
+ * The reference (mikacuy/scade @ 23139b1) has no FFI: its hot path is a set of Python callables
+ * (SURVEY.md §8(b)).  This header is the boundary a binding of that path would target: every
+ * entry point names the reference function it replaces (RS = run_scade_scannet.py,
+ * H = model/run_nerf_helpers.py).  The Python mirror in scade_b200/ binds these with ctypes
+ * (see INTEGRATION.md); nothing here depends on torch.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer to contiguous row-major fp32 unless the comment says HOST;
+ *   - the caller allocates all outputs and workspaces; no function allocates or frees device memory;
+ *   - `stream` is a cudaStream_t passed as void*; calls only enqueue work on it (no host sync);
+ *   - return value 0 = ok, otherwise a scade_status; scade_last_error_string() describes the last
+ *     failure on the calling thread.  No C++ exceptions cross the boundary.
+ */
+#ifndef SCADE_B200_H
+#define SCADE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SCADE_B200_VERSION 100
+
+typedef enum {
+  SCADE_OK = 0,
+  SCADE_ERR_INVALID_ARGUMENT = 1,
+  SCADE_ERR_UNSUPPORTED = 2,      /* shape outside what the selected kernel family handles */
+  SCADE_ERR_WORKSPACE = 3,        /* workspace too small */
+  SCADE_ERR_CUDA = 4              /* a CUDA runtime call / launch failed */
+} scade_status;
+
+/* Arithmetic used for the MLP's wide layers. */
+typedef enum {
+  SCADE_PREC_FP32 = 0,   /* fp32 FFMA GEMMs: the reference's own arithmetic (cuBLAS SGEMM / MKL) */
+  SCADE_PREC_TC_F16 = 1  /* tcgen05 tensor cores, fp16 operands, fp32 accumulate in TMEM */
+} scade_precision;
+
+int scade_version(void);
+const char* scade_last_error_string(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Field network: NeRF(D, W, input_ch, input_ch_views, skips=[skip], use_viewdirs=True)  (H:193-247)
+ * --------------------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t D;               /* number of pts_linears (reference default 8) */
+  int32_t W;               /* layer width (256) */
+  int32_t multires;        /* positional-encoding octaves for points (9 -> input_ch = 57), H:174-189 */
+  int32_t multires_views;  /* octaves for view directions (0 -> 3 channels, identity) */
+  int32_t skip;            /* i such that input_pts is re-concatenated after layer i (4); -1 = none, H:229-230 */
+} scade_net_desc;
+
+/* Number of parameter tensors = 2*D + 8, in the reference's state_dict order (H:206-219):
+ *   pts_linears.0.weight, pts_linears.0.bias, ..., pts_linears.{D-1}.weight, .bias,
+ *   views_linears.0.weight, .bias, feature_linear.weight, .bias, alpha_linear.weight, .bias,
+ *   rgb_linear.weight, .bias.   Weights are (out, in) row-major exactly as nn.Linear stores them. */
+#define SCADE_MAX_PARAM_TENSORS 40
+
+typedef struct {
+  scade_net_desc desc;
+  const float* params[SCADE_MAX_PARAM_TENSORS]; /* HOST array of DEVICE pointers (fp32 master weights) */
+  const void* packed_f16;                       /* DEVICE buffer written by scade_mlp_pack_f16, or NULL */
+} scade_net;
+
+/* Bytes of the fp16 tile image used by SCADE_PREC_TC_F16 (0 if the shape is unsupported there). */
+size_t scade_mlp_packed_bytes(const scade_net_desc* desc);
+/* Re-pack fp32 master weights into the swizzled fp16 K-major tile stream the tcgen05 kernel
+ * bulk-copies (call after every optimizer step).  Replaces nothing in the reference: torch keeps
+ * fp32 weights and cuBLAS reads them directly (H:131, H:227). */
+int scade_mlp_pack_f16(const scade_net* net, void* packed_out, void* stream);
+
+/* Workspace bytes for scade_mlp_forward* on P points; save_for_backward adds the activation stash. */
+size_t scade_mlp_workspace_bytes(const scade_net_desc* desc, int64_t P, int precision, int save_for_backward);
+
+/* run_network (RS:48-63) fused with the sampling of points along rays (RS:657):
+ *   pts = o + d*z ; x = (pts - bb_center)*bb_scale ; embed (H:142-172) ; NeRF.forward (H:223-247).
+ * rays: [N, ray_stride] with o at 0..2, d at 3..5, viewdirs at 8..10 (RS:628-632); z: [N,S];
+ * raw_out: [N,S,4] = (rgb_raw3, softplus_beta10(alpha)).  bb_center: HOST float[3]. */
+int scade_mlp_forward_rays(const scade_net* net, int precision, const float* rays, int ray_stride,
+                           const float* z_vals, int64_t N, int S, const float* bb_center_host,
+                           float bb_scale, float* raw_out, void* workspace, size_t workspace_bytes,
+                           int save_for_backward, void* stream);
+
+/* NeRF.forward (H:223-247) on an already embedded input x [P, input_ch + input_ch_views]. */
+int scade_mlp_forward_embedded(const scade_net* net, int precision, const float* x, int64_t P,
+                               float* out, void* workspace, size_t workspace_bytes,
+                               int save_for_backward, void* stream);
+
+/* Backward of either forward above (autograd of H:223-247, RS:985): d_out [P,4] -> gradients of all
+ * parameter tensors, ACCUMULATED into grads[i] (HOST array of DEVICE pointers, same order/shape as
+ * params).  Uses the stash a forward call with save_for_backward=1 left in `workspace`.
+ * No gradient w.r.t. the inputs is produced (z samples are detached, RS:711). */
+int scade_mlp_backward(const scade_net* net, int precision, const float* d_out, int64_t P,
+                       float* const* grads_host, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Embedder.embed (H:171-172): x [P,3] -> [P, 3 + 6*multires]. */
+int scade_embed(const float* x, int64_t P, int multires, float* out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Rays and sample placement
+ * --------------------------------------------------------------------------------------------- */
+/* get_rays (H:285-305) for the pixel rectangle rows [0,H) x cols [col0, col0+ncols) (the with_5_9
+ * crop of RS:109-116 is a column window).  intrinsic: HOST (fx,fy,cx,cy); c2w: HOST 3x4 row-major.
+ * rays_o / rays_d: [H, ncols, 3]. */
+int scade_get_rays(int H, int W, const float* intrinsic_host, const float* c2w_host, int col0, int ncols,
+                   float* rays_o, float* rays_d, void* stream);
+
+/* render()'s batch assembly (RS:123-141): [N,11] = (o, d, near, far, d/|d|). */
+int scade_make_ray_batch(const float* rays_o, const float* rays_d, int64_t N, float near, float far,
+                         float* ray_batch, void* stream);
+
+/* get_rays + batch assembly in one pass for pixels [pix0, pix0+N) of the (cropped) image, row-major. */
+int scade_camera_ray_batch(int H, int W, const float* intrinsic_host, const float* c2w_host, int col0,
+                           int ncols, int64_t pix0, int64_t N, float near, float far, float* ray_batch,
+                           void* stream);
+
+/* Coarse sample placement (RS:640-655): t = linspace(0,1,Nc); z = near(1-t)+far*t (or lindisp, RS:651);
+ * if t_rand != NULL apply perturb_z_vals (RS:564-579) with those uniforms [N,Nc]. */
+int scade_coarse_z_vals(const float* rays, int ray_stride, int64_t N, int Nc, int lindisp,
+                        const float* t_rand, float* z_vals, void* stream);
+
+/* perturb_z_vals (RS:564-579) on given z [N,S] with explicit t_rand [N,S]. */
+int scade_perturb_z_vals(const float* z_in, const float* t_rand, int64_t N, int S, float* z_out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Alpha compositing: compute_weights + raw2outputs (RS:511-562)
+ * --------------------------------------------------------------------------------------------- */
+/* rays_d: [N, d_stride] (first 3 floats of each row used).  noise: [N,S] sigma noise already scaled by
+ * raw_noise_std, or NULL (RS:544-552).  Any output pointer may be NULL. */
+int scade_raw2outputs(const float* raw, const float* z_vals, const float* rays_d, int d_stride,
+                      const float* noise, int64_t N, int S, float* rgb_map, float* disp_map,
+                      float* acc_map, float* weights, float* depth_map, void* stream);
+
+/* Autograd of raw2outputs w.r.t. raw.  Any d_* input may be NULL (= zero).  d_raw: [N,S,4]. */
+int scade_raw2outputs_backward(const float* raw, const float* z_vals, const float* rays_d, int d_stride,
+                               const float* noise, int64_t N, int S, const float* d_rgb_map,
+                               const float* d_disp_map, const float* d_acc_map, const float* d_weights,
+                               const float* d_depth_map, float* d_raw, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Hierarchical resampling: sample_pdf family (H:337-538) and the sort-merge of RS:713
+ * --------------------------------------------------------------------------------------------- */
+/* sample_pdf / sample_pdf_return_u / *_joint*: bins [N,B], weights [N,B-1], samples_out [N,n_samples].
+ * u: explicit uniforms [N,n_samples] (load_u, H:393), or [n_samples] when u_is_joint (one row shared
+ * by all rays, H:452-453), or NULL for det=True -> linspace(0,1,n_samples) (H:347).
+ * u_out (nullable): the [N,n_samples] uniforms actually used (the `u` return of H:436). */
+int scade_sample_pdf(const float* bins, const float* weights, int64_t N, int B, int n_samples,
+                     const float* u, int u_is_joint, float* samples_out, float* u_out, void* stream);
+
+/* Autograd of sample_pdf w.r.t. weights (bins carry no gradient on the reference path, RS:711).
+ * u: [N,n_samples] as returned in u_out.  d_weights: [N,B-1]. */
+int scade_sample_pdf_backward(const float* bins, const float* weights, const float* u, int64_t N, int B,
+                              int n_samples, const float* d_samples, float* d_weights, void* stream);
+
+/* The render_rays form (RS:702-713 / RS:723-726): bins are the mid-points of z_vals [N,S] and the
+ * weights are weights[:,1:-1], both formed on the fly.  If z_merged != NULL also writes
+ * sort(cat(z_vals, samples)) [N, S+n_samples] (RS:713).  z_std (nullable) [N]: std of the samples
+ * (RS:744, unbiased=False). */
+int scade_resample_from_z(const float* z_vals, const float* weights_full, int64_t N, int S, int n_samples,
+                          const float* u, int u_is_joint, float* samples_out, float* u_out,
+                          float* z_merged, float* z_std, void* stream);
+
+/* Backward of the above w.r.t. weights_full [N,S] (zero on the first and last column). */
+int scade_resample_from_z_backward(const float* z_vals, const float* weights_full, const float* u, int64_t N,
+                                   int S, int n_samples, const float* d_samples, float* d_weights_full,
+                                   int accumulate, void* stream);
+
+/* torch.sort(torch.cat([a, b], -1), -1) values (RS:713): a [N,Na], b [N,Nb] -> out [N,Na+Nb]. */
+int scade_sort_merge(const float* a, int Na, const float* b, int Nb, int64_t N, float* out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Losses: compute_space_carving_loss (H:93-128) and img2mse (H:11)
+ * --------------------------------------------------------------------------------------------- */
+/* pred [N,P]; hyp [K,N,1] (hyp_full=0) or [K,N,P] (hyp_full=1); mask [N] or NULL; loss_out: 1 float.
+ * d_pred / d_hyp (nullable, same shapes as pred / hyp) receive the gradient of grad_scale * loss.
+ * workspace: scade_space_carving_workspace_bytes(K,N,P) bytes. */
+size_t scade_space_carving_workspace_bytes(int K, int64_t N, int P);
+int scade_space_carving_loss(const float* pred, const float* hyp, int hyp_full, const float* mask, int K,
+                             int64_t N, int P, int is_joint, float threshold, float grad_scale,
+                             float* loss_out, float* d_pred, float* d_hyp, void* workspace,
+                             size_t workspace_bytes, void* stream);
+
+/* img2mse (H:11): loss_out = mean((x-y)^2) over n elements; d_x (nullable) = grad_scale * d loss/d x.
+ * `denominator` overrides n in the mean when > 0 (ray-sharded training divides by the GLOBAL count). */
+int scade_img2mse(const float* x, const float* y, int64_t n, int64_t denominator, float grad_scale,
+                  float* loss_out, float* d_x, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * render_rays (RS:581-751), N_importance > 0 branch, forward only, one call, one stream
+ * --------------------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t N_samples;      /* coarse samples per ray (RS:585) */
+  int32_t N_importance;   /* importance samples per ray (RS:591), must be > 0 */
+  int32_t lindisp;        /* RS:589 */
+  int32_t precision;      /* scade_precision */
+  int32_t is_joint;       /* RS:596: u rows shared by all rays */
+  int32_t ray_stride;     /* floats per ray_batch row (11, or 14 with depth_range, RS:633) */
+  float bb_center[3];     /* RS:52 */
+  float bb_scale;
+} scade_render_cfg;
+
+typedef struct {          /* RS:733-744; any pointer may be NULL to skip that output */
+  float* rgb_map;   /* [N,3] */
+  float* disp_map;  /* [N] */
+  float* acc_map;   /* [N] */
+  float* depth_map; /* [N] */
+  float* z_vals;    /* [N,Nc+Nf] */
+  float* weights;   /* [N,Nc+Nf] */
+  float* pred_hyp;  /* [N,Nf] */
+  float* u;         /* [N,Nf] */
+  float* raw;       /* [N,Nc+Nf,4] (retraw) */
+  float* rgb0;      /* [N,3] */
+  float* disp0;     /* [N] */
+  float* acc0;      /* [N] */
+  float* depth0;    /* [N] */
+  float* z_vals0;   /* [N,Nc] */
+  float* weights0;  /* [N,Nc] */
+  float* z_std;     /* [N] */
+} scade_render_out;
+
+size_t scade_render_rays_workspace_bytes(const scade_render_cfg* cfg, const scade_net_desc* coarse,
+                                         const scade_net_desc* fine, int64_t N);
+
+/* t_rand [N,Nc] (NULL = no perturbation, i.e. perturb == 0 -> det=True in both sample_pdf calls,
+ * RS:705,726); u_coarse / u_fine [N,Nf] or [Nf] if is_joint (required iff t_rand != NULL; u_fine is
+ * the reference's cached_u, RS:597). */
+int scade_render_rays_forward(const scade_render_cfg* cfg, const float* ray_batch, int64_t N,
+                              const scade_net* coarse, const scade_net* fine, const float* t_rand,
+                              const float* u_coarse, const float* u_fine, const scade_render_out* out,
+                              void* workspace, size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SCADE_B200_H */

@@ -1,0 +1,239 @@
+// Losses of the SCADE train step.
+//   compute_space_carving_loss   model/run_nerf_helpers.py:93-128  (forward + backward in one pass)
+//   img2mse                      model/run_nerf_helpers.py:11
+//
+// Space carving, default branch (H:122-126): loss = mean_n mean_p min_k m_n |pred[n,p] - hyp[k,n]|.
+// One warp per ray: lanes walk the P samples, the K hypotheses of the ray sit in shared memory, the
+// min over K runs in registers, the sum over p is a shuffle reduction and the per-block partial goes to
+// one atomicAdd.  The gradient is written in the same pass (sign of the arg-min term; first k on ties,
+// zero at exact equality, like torch.min(dim)/abs).  The reference materialises [K,N,P] distances
+// (10.5 MB at 20x4096x128); here traffic is 4*(P + K) B/ray in, 4*(P + K) out.
+// Joint branch (H:115-119): mean over rays first -> needs a [K,P] reduction across rays (atomics into
+// the workspace), then min over k per p, then a second pass for the gradient.
+#include "common.cuh"
+
+namespace scade {
+
+constexpr int SC_WARPS = 4;
+
+__device__ __forceinline__ float sc_dist(float pred, float h, float m, float thr, float& sgn) {
+  float diff = pred - h;
+  float d = fabsf(diff) * m;                            // H:106, H:110
+  sgn = (diff > 0.f ? 1.f : (diff < 0.f ? -1.f : 0.f)) * m;
+  if (thr > 0.f && d < thr) { d = 0.f; sgn = 0.f; }     // H:112-113
+  return d;
+}
+
+__global__ void __launch_bounds__(SC_WARPS * 32)
+space_carving_ray_kernel(const float* __restrict__ pred, const float* __restrict__ hyp, int hyp_full,
+                         const float* __restrict__ mask, int K, int64_t N, int P, float thr, float gscale,
+                         float* __restrict__ loss_out, float* __restrict__ d_pred, float* __restrict__ d_hyp) {
+  extern __shared__ float smem[];   // per warp: K hypotheses + K*32 lane-private gradient accumulators
+  __shared__ float s_part[SC_WARPS];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int64_t r = (int64_t)blockIdx.x * SC_WARPS + wid;
+  float ray_sum = 0.f;
+  if (r < N) {
+    float* s_h = smem + (size_t)wid * (K + K * 32);
+    float* s_g = s_h + K;
+    const float m = mask ? mask[r] : 1.0f;
+    const bool want_dh = d_hyp != nullptr;
+    if (!hyp_full) for (int k = lane; k < K; k += 32) s_h[k] = hyp[(int64_t)k * N + r];
+    if (want_dh && !hyp_full) for (int i = lane; i < K * 32; i += 32) s_g[i] = 0.f;
+    __syncwarp();
+    const float gval = gscale / ((float)N * (float)P);
+    for (int p = lane; p < P; p += 32) {
+      float pr = pred[r * P + p];
+      float best = 0.f, bsgn = 0.f;
+      int bk = 0;
+      for (int k = 0; k < K; ++k) {
+        float h = hyp_full ? hyp[((int64_t)k * N + r) * P + p] : s_h[k];
+        float sg;
+        float d = sc_dist(pr, h, m, thr, sg);
+        if (k == 0 || d < best) { best = d; bsgn = sg; bk = k; }   // H:124 (first arg-min)
+      }
+      ray_sum += best;
+      float g = bsgn * gval;
+      if (d_pred) d_pred[r * P + p] = g;
+      if (want_dh) {
+        if (hyp_full) {
+          for (int k = 0; k < K; ++k) d_hyp[((int64_t)k * N + r) * P + p] = (k == bk) ? -g : 0.f;
+        } else {
+          s_g[bk * 32 + lane] -= g;
+        }
+      }
+    }
+    if (want_dh && !hyp_full) {
+      __syncwarp();
+      for (int k = 0; k < K; ++k) {
+        float v = warp_sum(s_g[k * 32 + lane]);
+        if (lane == 0) d_hyp[(int64_t)k * N + r] = v;
+      }
+    }
+    ray_sum = warp_sum(ray_sum) / (float)P;              // H:125
+  }
+  if (lane == 0) s_part[wid] = ray_sum;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+    for (int w = 0; w < SC_WARPS; ++w) s += s_part[w];
+    atomicAdd(loss_out, s / (float)N);                   // H:126
+  }
+}
+
+// ---- joint branch -------------------------------------------------------------------------------
+__global__ void sc_joint_accumulate_kernel(const float* __restrict__ pred, const float* __restrict__ hyp, int hyp_full,
+                                           const float* __restrict__ mask, int K, int64_t N, int P, float thr,
+                                           int64_t rays_per_block, float* __restrict__ qsum /*[K,P]*/) {
+  // block handles a slab of rays; thread handles (k, p) pairs -> one atomicAdd per pair per block
+  const int64_t r0 = (int64_t)blockIdx.x * rays_per_block;
+  const int64_t r1 = min(N, r0 + rays_per_block);
+  for (int kp = threadIdx.x; kp < K * P; kp += blockDim.x) {
+    int k = kp / P, p = kp % P;
+    float acc = 0.f;
+    for (int64_t r = r0; r < r1; ++r) {
+      float h = hyp_full ? hyp[((int64_t)k * N + r) * P + p] : hyp[(int64_t)k * N + r];
+      float sg;
+      acc += sc_dist(pred[r * P + p], h, mask ? mask[r] : 1.0f, thr, sg);
+    }
+    atomicAdd(&qsum[kp], acc);
+  }
+}
+
+__global__ void sc_joint_select_kernel(const float* __restrict__ qsum, int K, int64_t N, int P, int* __restrict__ kstar,
+                                       float* __restrict__ loss_out) {
+  // single block; per p: min over k of qsum/N (H:117-118), then mean over p (H:119)
+  __shared__ float s_red[32];
+  float part = 0.f;
+  for (int p = threadIdx.x; p < P; p += blockDim.x) {
+    float best = 0.f;
+    int bk = 0;
+    for (int k = 0; k < K; ++k) {
+      float v = qsum[k * P + p] / (float)N;
+      if (k == 0 || v < best) { best = v; bk = k; }
+    }
+    kstar[p] = bk;
+    part += best;
+  }
+  part = warp_sum(part);
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = part;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+    for (int w = 0; w < (blockDim.x + 31) / 32; ++w) s += s_red[w];
+    *loss_out = s / (float)P;
+  }
+}
+
+__global__ void sc_joint_grad_kernel(const float* __restrict__ pred, const float* __restrict__ hyp, int hyp_full,
+                                     const float* __restrict__ mask, const int* __restrict__ kstar, int K, int64_t N,
+                                     int P, float thr, float gscale, float* __restrict__ d_pred,
+                                     float* __restrict__ d_hyp) {
+  // one warp per ray (d_hyp [K,N,1] needs a reduction over p)
+  const int lane = threadIdx.x & 31;
+  const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= N) return;
+  const float m = mask ? mask[r] : 1.0f;
+  const float gval = gscale / ((float)N * (float)P);
+  if (d_hyp && hyp_full)
+    for (int k = 0; k < K; ++k)
+      for (int p = lane; p < P; p += 32) d_hyp[((int64_t)k * N + r) * P + p] = 0.f;
+  if (d_hyp && !hyp_full)
+    for (int k = lane; k < K; k += 32) d_hyp[(int64_t)k * N + r] = 0.f;
+  __syncwarp();
+  for (int p0 = 0; p0 < P; p0 += 32) {
+    int p = p0 + lane;
+    float g = 0.f;
+    int k = 0;
+    if (p < P) {
+      k = kstar[p];
+      float h = hyp_full ? hyp[((int64_t)k * N + r) * P + p] : hyp[(int64_t)k * N + r];
+      float sg;
+      sc_dist(pred[r * P + p], h, m, thr, sg);
+      g = sg * gval;
+      if (d_pred) d_pred[r * P + p] = g;
+      if (d_hyp && hyp_full) d_hyp[((int64_t)k * N + r) * P + p] = -g;
+    }
+    if (d_hyp && !hyp_full && p < P) atomicAdd(&d_hyp[(int64_t)k * N + r], -g);
+  }
+}
+
+// ---- img2mse ------------------------------------------------------------------------------------
+__global__ void mse_kernel(const float* __restrict__ x, const float* __restrict__ y, int64_t n, float inv_den,
+                           float gscale, float* __restrict__ loss_out, float* __restrict__ d_x) {
+  __shared__ float s_red[32];
+  float part = 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float d = x[i] - y[i];
+    part += d * d;
+    if (d_x) d_x[i] = 2.0f * d * inv_den * gscale;
+  }
+  part = warp_sum(part);
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = part;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+    for (int w = 0; w < (blockDim.x + 31) / 32; ++w) s += s_red[w];
+    atomicAdd(loss_out, s * inv_den);
+  }
+}
+
+}  // namespace scade
+
+using namespace scade;
+
+extern "C" size_t scade_space_carving_workspace_bytes(int K, int64_t N, int P) {
+  (void)N;
+  return align_up((size_t)K * P * sizeof(float)) + align_up((size_t)P * sizeof(int));
+}
+
+extern "C" int scade_space_carving_loss(const float* pred, const float* hyp, int hyp_full, const float* mask, int K,
+                                        int64_t N, int P, int is_joint, float threshold, float grad_scale,
+                                        float* loss_out, float* d_pred, float* d_hyp, void* workspace,
+                                        size_t workspace_bytes, void* stream) {
+  SCADE_CHECK_ARG(pred && hyp && loss_out && K > 0 && N > 0 && P > 0, "space_carving_loss: bad arguments");
+  cudaStream_t st = as_stream(stream);
+  SCADE_CUDA(cudaMemsetAsync(loss_out, 0, sizeof(float), st));
+  if (!is_joint) {
+    size_t smem = (size_t)SC_WARPS * (K + K * 32) * sizeof(float);
+    SCADE_CHECK_ARG(smem <= 160 * 1024, "space_carving_loss: K=%d too large", K);
+    if (smem > 48 * 1024)
+      SCADE_CUDA(cudaFuncSetAttribute(space_carving_ray_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    space_carving_ray_kernel<<<(unsigned)ceil_div<int64_t>(N, SC_WARPS), SC_WARPS * 32, smem, st>>>(
+        pred, hyp, hyp_full, mask, K, N, P, threshold, grad_scale, loss_out, d_pred, d_hyp);
+    SCADE_LAUNCH_CHECK();
+    return SCADE_OK;
+  }
+  size_t need = scade_space_carving_workspace_bytes(K, N, P);
+  if (workspace == nullptr || workspace_bytes < need) {
+    set_error("space_carving_loss(is_joint): workspace %zu < %zu bytes", workspace_bytes, need);
+    return SCADE_ERR_WORKSPACE;
+  }
+  float* qsum = reinterpret_cast<float*>(workspace);
+  int* kstar = reinterpret_cast<int*>(reinterpret_cast<char*>(workspace) + align_up((size_t)K * P * sizeof(float)));
+  SCADE_CUDA(cudaMemsetAsync(qsum, 0, (size_t)K * P * sizeof(float), st));
+  int64_t rays_per_block = 64;
+  sc_joint_accumulate_kernel<<<(unsigned)ceil_div<int64_t>(N, rays_per_block), 256, 0, st>>>(
+      pred, hyp, hyp_full, mask, K, N, P, threshold, rays_per_block, qsum);
+  SCADE_LAUNCH_CHECK();
+  sc_joint_select_kernel<<<1, 256, 0, st>>>(qsum, K, N, P, kstar, loss_out);
+  SCADE_LAUNCH_CHECK();
+  if (d_pred || d_hyp) {
+    sc_joint_grad_kernel<<<(unsigned)ceil_div<int64_t>(N, 4), 128, 0, st>>>(pred, hyp, hyp_full, mask, kstar, K, N, P,
+                                                                           threshold, grad_scale, d_pred, d_hyp);
+    SCADE_LAUNCH_CHECK();
+  }
+  return SCADE_OK;
+}
+
+extern "C" int scade_img2mse(const float* x, const float* y, int64_t n, int64_t denominator, float grad_scale,
+                             float* loss_out, float* d_x, void* stream) {
+  SCADE_CHECK_ARG(x && y && loss_out && n > 0, "img2mse: bad arguments");
+  cudaStream_t st = as_stream(stream);
+  SCADE_CUDA(cudaMemsetAsync(loss_out, 0, sizeof(float), st));
+  float inv_den = 1.0f / (float)(denominator > 0 ? denominator : n);
+  int blocks = (int)std::min<int64_t>(ceil_div<int64_t>(n, 256), 2 * num_sms());
+  mse_kernel<<<blocks, 256, 0, st>>>(x, y, n, inv_den, grad_scale, loss_out, d_x);
+  SCADE_LAUNCH_CHECK();
+  return SCADE_OK;
+}

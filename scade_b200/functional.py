@@ -1,0 +1,426 @@
+"""Tensor-level wrappers over the C ABI (include/scade_b200.h) with autograd support.
+
+Every function here launches hand-written CUDA kernels from libscade_b200.so on the current
+torch stream; torch is used for device memory, streams and the autograd tape only.  There is no
+CPU or eager fallback: CPU tensors raise.
+"""
+from __future__ import annotations
+
+import ctypes
+from ctypes import byref, c_void_p
+
+import torch
+
+from . import _lib
+from ._lib import PREC_FP32, PREC_TC_F16, check, f32, ptr, stream_ptr
+
+PRECISIONS = {"fp32": PREC_FP32, "tc_f16": PREC_TC_F16, PREC_FP32: PREC_FP32, PREC_TC_F16: PREC_TC_F16}
+
+
+def _L():
+    return _lib.load()
+
+
+def _bytes(n, device):
+    return torch.empty(max(int(n), 256), dtype=torch.uint8, device=device)
+
+
+# ----------------------------------------------------------------------------------------------
+# network handle
+# ----------------------------------------------------------------------------------------------
+class NetHandle:
+    """C-side view (scade_net) of a NeRF module's parameters, in the reference state_dict order
+    (model/run_nerf_helpers.py:206-219).  Keeps the fp16 tile image for the tensor-core path in sync
+    with the fp32 master weights (re-packed whenever a parameter's version counter moved, i.e. after
+    optimizer.step() or load_state_dict())."""
+
+    def __init__(self, params, D, W, multires, multires_views, skip):
+        self.params = list(params)
+        if len(self.params) != 2 * D + 8:
+            raise ValueError(f"expected {2 * D + 8} parameter tensors, got {len(self.params)}")
+        self.desc = _lib.NetDesc(D, W, multires, multires_views, skip)
+        self._packed = None
+        self._packed_key = None
+
+    def tc_supported(self):
+        return _L().scade_mlp_packed_bytes(byref(self.desc)) > 0
+
+    def struct(self, precision):
+        net = _lib.Net()
+        net.desc = self.desc
+        for i, p in enumerate(self.params):
+            if not p.is_cuda or p.dtype != torch.float32 or not p.is_contiguous():
+                raise _lib.ScadeError("network parameters must be contiguous fp32 CUDA tensors")
+            net.params[i] = p.data_ptr()
+        net.packed_f16 = None
+        if precision == PREC_TC_F16:
+            net.packed_f16 = self.packed().data_ptr()
+        return net
+
+    def packed(self):
+        key = tuple((p.data_ptr(), p._version) for p in self.params)
+        if self._packed is None or key != self._packed_key:
+            nbytes = _L().scade_mlp_packed_bytes(byref(self.desc))
+            if nbytes == 0:
+                raise _lib.ScadeError("this network shape is not supported by the tensor-core (tc_f16) path")
+            if self._packed is None or self._packed.numel() != nbytes or self._packed.device != self.params[0].device:
+                self._packed = torch.empty(nbytes, dtype=torch.uint8, device=self.params[0].device)
+            net = self.struct(PREC_FP32)
+            check(_L().scade_mlp_pack_f16(byref(net), ptr(self._packed), stream_ptr()), "scade_mlp_pack_f16")
+            self._packed_key = key
+        return self._packed
+
+    def workspace_bytes(self, P, precision, save):
+        return _L().scade_mlp_workspace_bytes(byref(self.desc), int(P), int(precision), int(save))
+
+
+def _mlp_backward(handle, precision, d_out, P, ws, device):
+    grads = [torch.zeros_like(p) for p in handle.params]
+    net = handle.struct(PREC_FP32)
+    arr = (c_void_p * len(grads))(*[g.data_ptr() for g in grads])
+    check(_L().scade_mlp_backward(byref(net), precision, ptr(d_out), P, arr, ptr(ws), ws.numel(), stream_ptr()),
+          "scade_mlp_backward")
+    return grads
+
+
+class _MLPRaysFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, rays, z_vals, handle, precision, bb_center, bb_scale, *params):
+        N, S = z_vals.shape
+        need_grad = any(ctx.needs_input_grad[6:])
+        raw = torch.empty((N, S, 4), dtype=torch.float32, device=z_vals.device)
+        ws = _bytes(handle.workspace_bytes(N * S, precision, need_grad), z_vals.device)
+        net = handle.struct(precision)
+        check(_L().scade_mlp_forward_rays(byref(net), precision, ptr(rays), rays.shape[1], ptr(z_vals), N, S,
+                                          _lib.host_floats(bb_center), float(bb_scale), ptr(raw), ptr(ws), ws.numel(),
+                                          int(need_grad), stream_ptr()), "scade_mlp_forward_rays")
+        ctx.handle, ctx.precision, ctx.P = handle, precision, N * S
+        ctx.ws = ws if need_grad else None
+        return raw
+
+    @staticmethod
+    def backward(ctx, d_raw):
+        if ctx.ws is None:
+            raise _lib.ScadeError("backward through a forward that did not stash activations")
+        grads = _mlp_backward(ctx.handle, ctx.precision, f32(d_raw), ctx.P, ctx.ws, d_raw.device)
+        ctx.ws = None
+        return (None, None, None, None, None, None, *grads)
+
+
+class _MLPEmbeddedFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, handle, precision, *params):
+        P = x.shape[0]
+        need_grad = any(ctx.needs_input_grad[3:])
+        out = torch.empty((P, 4), dtype=torch.float32, device=x.device)
+        ws = _bytes(handle.workspace_bytes(P, precision, need_grad), x.device)
+        net = handle.struct(precision)
+        check(_L().scade_mlp_forward_embedded(byref(net), precision, ptr(x), P, ptr(out), ptr(ws), ws.numel(),
+                                              int(need_grad), stream_ptr()), "scade_mlp_forward_embedded")
+        ctx.handle, ctx.precision, ctx.P = handle, precision, P
+        ctx.ws = ws if need_grad else None
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        if ctx.ws is None:
+            raise _lib.ScadeError("backward through a forward that did not stash activations")
+        grads = _mlp_backward(ctx.handle, ctx.precision, f32(d_out), ctx.P, ctx.ws, d_out.device)
+        ctx.ws = None
+        return (None, None, None, *grads)
+
+
+def mlp_forward_rays(handle, rays, z_vals, bb_center, bb_scale, precision=PREC_FP32):
+    """run_network fused with pts = o + d*z (RS:48-63, 657): rays [N,>=11], z [N,S] -> raw [N,S,4]."""
+    precision = PRECISIONS[precision]
+    rays, z_vals = f32(rays), f32(z_vals)
+    if precision == PREC_TC_F16 and torch.is_grad_enabled() and any(p.requires_grad for p in handle.params):
+        precision = PREC_FP32      # training stashes fp32 activations; tensor-core backward is future work
+    return _MLPRaysFn.apply(rays, z_vals, handle, precision, [float(c) for c in bb_center], float(bb_scale),
+                            *handle.params)
+
+
+def mlp_forward_embedded(handle, x, precision=PREC_FP32):
+    """NeRF.forward (H:223-247) on embedded inputs [..., in_ch + in_views] -> [..., 4]."""
+    precision = PRECISIONS[precision]
+    lead = x.shape[:-1]
+    x2 = f32(x).reshape(-1, x.shape[-1])
+    if precision == PREC_TC_F16 and torch.is_grad_enabled() and any(p.requires_grad for p in handle.params):
+        precision = PREC_FP32
+    return _MLPEmbeddedFn.apply(x2, handle, precision, *handle.params).reshape(*lead, 4)
+
+
+def embed(x, multires):
+    """Embedder.embed (H:171-172)."""
+    lead = x.shape[:-1]
+    x2 = f32(x).reshape(-1, 3)
+    out = torch.empty((x2.shape[0], 3 + 6 * multires), dtype=torch.float32, device=x2.device)
+    check(_L().scade_embed(ptr(x2), x2.shape[0], multires, ptr(out), stream_ptr()), "scade_embed")
+    return out.reshape(*lead, -1)
+
+
+# ----------------------------------------------------------------------------------------------
+# rays
+# ----------------------------------------------------------------------------------------------
+def get_rays(H, W, intrinsic, c2w, col0=0, ncols=None, device=None):
+    """get_rays (H:285-305) -> rays_o, rays_d [H, ncols, 3]."""
+    ncols = W if ncols is None else ncols
+    device = device or (c2w.device if torch.is_tensor(c2w) and c2w.is_cuda else torch.device("cuda"))
+    intr = _lib.host_floats([float(v) for v in intrinsic][:4])
+    pose = _lib.host_floats([float(v) for v in torch.as_tensor(c2w).detach().cpu().reshape(-1)[:12]])
+    rays_o = torch.empty((H, ncols, 3), dtype=torch.float32, device=device)
+    rays_d = torch.empty_like(rays_o)
+    check(_L().scade_get_rays(H, W, intr, pose, col0, ncols, ptr(rays_o), ptr(rays_d), stream_ptr()), "scade_get_rays")
+    return rays_o, rays_d
+
+
+def make_ray_batch(rays_o, rays_d, near, far):
+    """render()'s batch assembly (RS:123-141): [N,11] = (o, d, near, far, d/|d|)."""
+    rays_o, rays_d = f32(rays_o).reshape(-1, 3), f32(rays_d).reshape(-1, 3)
+    out = torch.empty((rays_o.shape[0], 11), dtype=torch.float32, device=rays_o.device)
+    check(_L().scade_make_ray_batch(ptr(rays_o), ptr(rays_d), rays_o.shape[0], float(near), float(far), ptr(out),
+                                    stream_ptr()), "scade_make_ray_batch")
+    return out
+
+
+def camera_ray_batch(H, W, intrinsic, c2w, near, far, pix0=0, n=None, col0=0, ncols=None, device=None):
+    ncols = W if ncols is None else ncols
+    n = H * ncols - pix0 if n is None else n
+    device = device or torch.device("cuda")
+    intr = _lib.host_floats([float(v) for v in intrinsic][:4])
+    pose = _lib.host_floats([float(v) for v in torch.as_tensor(c2w).detach().cpu().reshape(-1)[:12]])
+    out = torch.empty((n, 11), dtype=torch.float32, device=device)
+    check(_L().scade_camera_ray_batch(H, W, intr, pose, col0, ncols, pix0, n, float(near), float(far), ptr(out),
+                                      stream_ptr()), "scade_camera_ray_batch")
+    return out
+
+
+def coarse_z_vals(ray_batch, n_samples, lindisp=False, t_rand=None):
+    ray_batch = f32(ray_batch)
+    N = ray_batch.shape[0]
+    z = torch.empty((N, n_samples), dtype=torch.float32, device=ray_batch.device)
+    t_rand = None if t_rand is None else f32(t_rand)
+    check(_L().scade_coarse_z_vals(ptr(ray_batch), ray_batch.shape[1], N, n_samples, int(bool(lindisp)), ptr(t_rand),
+                                   ptr(z), stream_ptr()), "scade_coarse_z_vals")
+    return z
+
+
+def perturb_z_vals(z_vals, t_rand):
+    z_vals, t_rand = f32(z_vals), f32(t_rand)
+    out = torch.empty_like(z_vals)
+    check(_L().scade_perturb_z_vals(ptr(z_vals), ptr(t_rand), z_vals.shape[0], z_vals.shape[1], ptr(out), stream_ptr()),
+          "scade_perturb_z_vals")
+    return out
+
+
+# ----------------------------------------------------------------------------------------------
+# compositing
+# ----------------------------------------------------------------------------------------------
+class _Raw2OutputsFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, raw, z_vals, rays_d, noise):
+        N, S = z_vals.shape
+        dev = raw.device
+        rgb = torch.empty((N, 3), dtype=torch.float32, device=dev)
+        disp = torch.empty((N,), dtype=torch.float32, device=dev)
+        acc = torch.empty_like(disp)
+        depth = torch.empty_like(disp)
+        w = torch.empty((N, S), dtype=torch.float32, device=dev)
+        check(_L().scade_raw2outputs(ptr(raw), ptr(z_vals), ptr(rays_d), rays_d.shape[1], ptr(noise), N, S, ptr(rgb),
+                                     ptr(disp), ptr(acc), ptr(w), ptr(depth), stream_ptr()), "scade_raw2outputs")
+        ctx.save_for_backward(raw, z_vals, rays_d, noise if noise is not None else torch.empty(0, device=dev))
+        ctx.has_noise = noise is not None
+        return rgb, disp, acc, w, depth
+
+    @staticmethod
+    def backward(ctx, d_rgb, d_disp, d_acc, d_w, d_depth):
+        raw, z_vals, rays_d, noise = ctx.saved_tensors
+        N, S = z_vals.shape
+        d_raw = torch.empty_like(raw)
+        g = [None if t is None else f32(t) for t in (d_rgb, d_disp, d_acc, d_w, d_depth)]
+        check(_L().scade_raw2outputs_backward(ptr(raw), ptr(z_vals), ptr(rays_d), rays_d.shape[1],
+                                              ptr(noise) if ctx.has_noise else None, N, S, ptr(g[0]), ptr(g[1]),
+                                              ptr(g[2]), ptr(g[3]), ptr(g[4]), ptr(d_raw), stream_ptr()),
+              "scade_raw2outputs_backward")
+        return d_raw, None, None, None
+
+
+def raw2outputs(raw, z_vals, rays_d, noise=None):
+    """compute_weights + raw2outputs (RS:511-562) -> (rgb_map, disp_map, acc_map, weights, depth_map)."""
+    return _Raw2OutputsFn.apply(f32(raw), f32(z_vals), f32(rays_d), None if noise is None else f32(noise))
+
+
+# ----------------------------------------------------------------------------------------------
+# hierarchical sampling
+# ----------------------------------------------------------------------------------------------
+class _SamplePdfFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, bins, weights, u, n_samples, joint):
+        N, B = bins.shape
+        samples = torch.empty((N, n_samples), dtype=torch.float32, device=bins.device)
+        u_out = torch.empty_like(samples)
+        check(_L().scade_sample_pdf(ptr(bins), ptr(weights), N, B, n_samples, ptr(u), int(joint), ptr(samples),
+                                    ptr(u_out), stream_ptr()), "scade_sample_pdf")
+        ctx.save_for_backward(bins, weights, u_out)
+        ctx.mark_non_differentiable(u_out)
+        return samples, u_out
+
+    @staticmethod
+    def backward(ctx, d_samples, _d_u):
+        bins, weights, u = ctx.saved_tensors
+        N, B = bins.shape
+        d_w = torch.empty_like(weights)
+        check(_L().scade_sample_pdf_backward(ptr(bins), ptr(weights), ptr(u), N, B, u.shape[1], ptr(f32(d_samples)),
+                                             ptr(d_w), stream_ptr()), "scade_sample_pdf_backward")
+        return None, d_w, None, None, None
+
+
+def sample_pdf(bins, weights, n_samples, u=None, joint=False):
+    """sample_pdf family (H:337-538).  u=None -> det (linspace); returns (samples, u_used)."""
+    bins, weights = f32(bins), f32(weights)
+    lead = bins.shape[:-1]
+    bins2, w2 = bins.reshape(-1, bins.shape[-1]), weights.reshape(-1, weights.shape[-1])
+    if u is not None:
+        u = f32(u, bins.device)
+        if not joint:
+            u = u.reshape(-1, n_samples)
+    s, uo = _SamplePdfFn.apply(bins2, w2, u, n_samples, bool(joint))
+    return s.reshape(*lead, n_samples), uo.reshape(*lead, n_samples)
+
+
+class _ResampleFromZFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, z_vals, weights, u, n_samples, joint, want_merge, want_std):
+        N, S = z_vals.shape
+        dev = z_vals.device
+        samples = torch.empty((N, n_samples), dtype=torch.float32, device=dev)
+        u_out = torch.empty_like(samples)
+        merged = torch.empty((N, S + n_samples), dtype=torch.float32, device=dev) if want_merge else None
+        std = torch.empty((N,), dtype=torch.float32, device=dev) if want_std else None
+        check(_L().scade_resample_from_z(ptr(z_vals), ptr(weights), N, S, n_samples, ptr(u), int(joint), ptr(samples),
+                                         ptr(u_out), ptr(merged), ptr(std), stream_ptr()), "scade_resample_from_z")
+        ctx.save_for_backward(z_vals, weights, u_out)
+        outs = (samples, u_out, merged if want_merge else torch.empty(0, device=dev),
+                std if want_std else torch.empty(0, device=dev))
+        ctx.mark_non_differentiable(*outs[1:])
+        return outs
+
+    @staticmethod
+    def backward(ctx, d_samples, *_):
+        z_vals, weights, u = ctx.saved_tensors
+        N, S = z_vals.shape
+        d_w = torch.empty_like(weights)
+        check(_L().scade_resample_from_z_backward(ptr(z_vals), ptr(weights), ptr(u), N, S, u.shape[1],
+                                                  ptr(f32(d_samples)), ptr(d_w), 0, stream_ptr()),
+              "scade_resample_from_z_backward")
+        return None, d_w, None, None, None, None, None
+
+
+def resample_from_z(z_vals, weights, n_samples, u=None, joint=False, merge=False, std=False):
+    """RS:702-713 / RS:723-726: mid-point bins + weights[:,1:-1] formed on the fly.
+    Returns (samples, u_used, z_merged or None, z_std or None)."""
+    z_vals, weights = f32(z_vals), f32(weights)
+    if u is not None:
+        u = f32(u, z_vals.device)
+    s, uo, m, sd = _ResampleFromZFn.apply(z_vals, weights, u, n_samples, bool(joint), bool(merge), bool(std))
+    return s, uo, (m if merge else None), (sd if std else None)
+
+
+def sort_merge(a, b):
+    """torch.sort(torch.cat([a, b], -1), -1).values (RS:713)."""
+    a, b = f32(a), f32(b)
+    out = torch.empty((a.shape[0], a.shape[1] + b.shape[1]), dtype=torch.float32, device=a.device)
+    check(_L().scade_sort_merge(ptr(a), a.shape[1], ptr(b), b.shape[1], a.shape[0], ptr(out), stream_ptr()),
+          "scade_sort_merge")
+    return out
+
+
+# ----------------------------------------------------------------------------------------------
+# losses
+# ----------------------------------------------------------------------------------------------
+class _SpaceCarvingFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pred, hyp, mask, is_joint, threshold):
+        N, P = pred.shape
+        K = hyp.shape[0]
+        full = hyp.shape[-1] != 1
+        dev = pred.device
+        loss = torch.empty((1,), dtype=torch.float32, device=dev)
+        want = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
+        d_pred = torch.empty_like(pred) if want else None
+        d_hyp = torch.empty_like(hyp) if want else None
+        ws = _bytes(_L().scade_space_carving_workspace_bytes(K, N, P), dev)
+        check(_L().scade_space_carving_loss(ptr(pred), ptr(hyp), int(full), ptr(mask), K, N, P, int(is_joint),
+                                            float(threshold), 1.0, ptr(loss), ptr(d_pred), ptr(d_hyp), ptr(ws),
+                                            ws.numel(), stream_ptr()), "scade_space_carving_loss")
+        if want:
+            ctx.save_for_backward(d_pred, d_hyp)
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        d_pred, d_hyp = ctx.saved_tensors
+        return d_pred * g, d_hyp * g, None, None, None
+
+
+def space_carving_loss(pred, hyp, is_joint=False, mask=None, threshold=0.0):
+    """compute_space_carving_loss (H:93-128)."""
+    pred, hyp = f32(pred), f32(hyp)
+    mask = None if mask is None else f32(mask)
+    return _SpaceCarvingFn.apply(pred, hyp, mask, bool(is_joint), float(threshold))
+
+
+class _MseFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, y, denominator):
+        loss = torch.empty((1,), dtype=torch.float32, device=x.device)
+        want = ctx.needs_input_grad[0]
+        d_x = torch.empty_like(x) if want else None
+        check(_L().scade_img2mse(ptr(x), ptr(y), x.numel(), int(denominator), 1.0, ptr(loss), ptr(d_x), stream_ptr()),
+              "scade_img2mse")
+        if want:
+            ctx.save_for_backward(d_x)
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        (d_x,) = ctx.saved_tensors
+        return d_x * g, None, None
+
+
+def img2mse(x, y, denominator=0):
+    """img2mse (H:11).  denominator > 0 replaces numel() in the mean (ray-sharded training)."""
+    return _MseFn.apply(f32(x), f32(y).expand_as(x).contiguous(), denominator)
+
+
+# ----------------------------------------------------------------------------------------------
+# fused render_rays forward (no autograd): one C call, one stream
+# ----------------------------------------------------------------------------------------------
+def render_rays_forward(ray_batch, coarse, fine, n_samples, n_importance, bb_center, bb_scale, precision=PREC_FP32,
+                        lindisp=False, is_joint=False, t_rand=None, u_coarse=None, u_fine=None, retraw=False):
+    precision = PRECISIONS[precision]
+    ray_batch = f32(ray_batch)
+    N = ray_batch.shape[0]
+    dev = ray_batch.device
+    fine = fine or coarse
+    cfg = _lib.RenderCfg(n_samples, n_importance, int(bool(lindisp)), precision, int(bool(is_joint)), ray_batch.shape[1],
+                         (ctypes.c_float * 3)(*[float(c) for c in bb_center]), float(bb_scale))
+    S = n_samples + n_importance
+    shapes = {"rgb_map": (N, 3), "disp_map": (N,), "acc_map": (N,), "depth_map": (N,), "z_vals": (N, S),
+              "weights": (N, S), "pred_hyp": (N, n_importance), "u": (N, n_importance), "rgb0": (N, 3), "disp0": (N,),
+              "acc0": (N,), "depth0": (N,), "z_vals0": (N, n_samples), "weights0": (N, n_samples), "z_std": (N,)}
+    if retraw:
+        shapes["raw"] = (N, S, 4)
+    ret = {k: torch.empty(s, dtype=torch.float32, device=dev) for k, s in shapes.items()}
+    out = _lib.RenderOut()
+    for k in _lib.RENDER_OUT_FIELDS:
+        setattr(out, k, ret[k].data_ptr() if k in ret else None)
+    nc, nf = coarse.struct(precision), fine.struct(precision)
+    ws = _bytes(_L().scade_render_rays_workspace_bytes(byref(cfg), byref(coarse.desc), byref(fine.desc), N), dev)
+    t_rand = None if t_rand is None else f32(t_rand, dev)
+    u_coarse = None if u_coarse is None else f32(u_coarse, dev)
+    u_fine = None if u_fine is None else f32(u_fine, dev)
+    check(_L().scade_render_rays_forward(byref(cfg), ptr(ray_batch), N, byref(nc), byref(nf), ptr(t_rand), ptr(u_coarse),
+                                         ptr(u_fine), byref(out), ptr(ws), ws.numel(), stream_ptr()),
+          "scade_render_rays_forward")
+    return ret

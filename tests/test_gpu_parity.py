@@ -1,0 +1,533 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (ctypes wrappers in scade_b200), against the
+CPU oracle on the same seeded inputs and against the reference-generated golden fixtures.
+
+fp32 kernels: tolerances are a few fp32 ulps of the quantity's scale (summation order differs between
+warp-shuffle scans / tiled FFMA GEMMs and numpy).  Tensor-core (fp16 operand) mode: tolerances are written
+next to each check and explained by oracle.nerf_forward_f16 (the same operand rounding emulated on CPU).
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import scade_oracle as O
+from scade_b200 import synthetic as syn
+from tests.golden.generate_goldens import RENDER_CASES, net_pair
+from tests.util import RENDER_FP32_TOL, mean_close
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    from scade_b200 import _lib
+    _lib.load()
+    return torch.device("cuda:0")
+
+
+def T(a, dev):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+
+
+def npy(t):
+    return t.detach().cpu().numpy()
+
+
+def close(a, b, rtol=2e-5, atol=2e-6):
+    np.testing.assert_allclose(np.asarray(a, np.float64), np.asarray(b, np.float64), rtol=rtol, atol=atol)
+
+
+def build_net(params, D, W, dev, precision="fp32", requires_grad=False):
+    from scade_b200.nerf_helpers import NeRF
+    net = NeRF(D=D, W=W, input_ch=57, input_ch_views=3, output_ch=5, skips=[4], use_viewdirs=True, precision=precision)
+    net.load_state_dict({k: torch.from_numpy(v) for k, v in params.items()})
+    net = net.to(dev)
+    for p in net.parameters():
+        p.requires_grad_(requires_grad)
+    return net
+
+
+# ------------------------------------------------------------------------------------------------
+# rays and sample placement
+# ------------------------------------------------------------------------------------------------
+def test_get_rays_and_batch(dev, golden):
+    from scade_b200 import functional as F_
+    g = golden("get_rays")
+    ro, rd = F_.get_rays(6, 8, (10.0, 11.0, 4.0, 3.0), torch.from_numpy(g["c2w"]), device=dev)
+    close(npy(rd), g["rays_d"], rtol=1e-6, atol=1e-7)
+    close(npy(ro), g["rays_o"], rtol=0, atol=0)
+    o_ro, o_rd = O.get_rays(480, 640, syn.CAM_INTRINSIC, g["c2w"])
+    ro, rd = F_.get_rays(480, 640, syn.CAM_INTRINSIC, torch.from_numpy(g["c2w"]), device=dev)
+    np.testing.assert_array_equal(npy(rd), o_rd)         # explicit-rounding kernel: bit exact
+    rb = F_.make_ray_batch(ro, rd, 0.1, 5.0)
+    close(npy(rb), O.make_ray_batch(o_ro, o_rd, 0.1, 5.0), rtol=3e-7, atol=0)
+    # with_5_9 crop (RS:109-116) = column window; fused camera->batch kernel agrees with the two-step path
+    ro_c, rd_c = F_.get_rays(480, 640, syn.CAM_INTRINSIC, torch.from_numpy(g["c2w"]), col0=178, ncols=284, device=dev)
+    np.testing.assert_array_equal(npy(rd_c), o_rd[:, 178:178 + 284])
+    cb = F_.camera_ray_batch(480, 640, syn.CAM_INTRINSIC, torch.from_numpy(g["c2w"]), 0.1, 5.0, pix0=284 * 7, n=1000,
+                             col0=178, ncols=284, device=dev)
+    np.testing.assert_array_equal(npy(cb), npy(F_.make_ray_batch(ro_c, rd_c, 0.1, 5.0))[284 * 7:284 * 7 + 1000])
+
+
+@pytest.mark.parametrize("lindisp", [False, True])
+def test_coarse_z_and_perturb(dev, golden, lindisp):
+    from scade_b200 import functional as F_
+    rb = syn.make_ray_batch(300, seed=3)
+    rb[:, 6] = np.random.default_rng(0).uniform(0.05, 0.5, 300).astype(np.float32)
+    rb[:, 7] = np.random.default_rng(1).uniform(3.0, 6.0, 300).astype(np.float32)
+    t_rand = np.random.default_rng(2).random((300, 67), dtype=np.float32)
+    z = F_.coarse_z_vals(T(rb, dev), 67, lindisp=lindisp)
+    oz = O.coarse_z_vals(rb[:, 6], rb[:, 7], 67, lindisp)
+    np.testing.assert_array_equal(npy(z), oz)
+    zp = F_.coarse_z_vals(T(rb, dev), 67, lindisp=lindisp, t_rand=T(t_rand, dev))
+    np.testing.assert_array_equal(npy(zp), O.perturb_z_vals(oz, t_rand))
+    np.testing.assert_array_equal(npy(F_.perturb_z_vals(z, T(t_rand, dev))), O.perturb_z_vals(oz, t_rand))
+    g = golden("perturb")
+    close(npy(F_.perturb_z_vals(T(g["z"], dev), T(g["t_rand"], dev))), g["out"], rtol=1e-6)
+
+
+def test_embed(dev, golden):
+    from scade_b200 import nerf_helpers as NH
+    g = golden("embed")
+    fn, dim = NH.get_embedder(9, 0)
+    assert dim == 57
+    # sin/cos of arguments up to pi*2^8: CUDA sinf/cosf (<= 2 ulp) vs the reference's libm
+    close(npy(fn(T(g["x"], dev))), g["emb9"], rtol=0, atol=2e-6)
+    fn0, dim0 = NH.get_embedder(0, 0)
+    assert dim0 == 3
+    np.testing.assert_array_equal(npy(fn0(T(g["x"], dev))), g["emb0"])
+    x = np.random.default_rng(5).uniform(-1, 1, (4097, 3)).astype(np.float32)
+    close(npy(fn(T(x, dev))), O.embed(x, 9), rtol=0, atol=2e-6)
+
+
+# ------------------------------------------------------------------------------------------------
+# field network
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("tag,D,W", [("d8w256", 8, 256), ("d4w128", 4, 128)])
+def test_nerf_forward_fp32(dev, golden, tag, D, W):
+    g = golden("nerf_forward")
+    params = syn.make_nerf_params(seed=3, D=D, W=W, bias_scale=0.1, alpha_bias=0.3)
+    net = build_net(params, D, W, dev)
+    with torch.no_grad():
+        out = net(T(g[f"{tag}_x"], dev))
+    close(npy(out), g[f"{tag}_out"], rtol=1e-4, atol=2e-5)          # vs the reference itself
+    x = np.random.default_rng(6).uniform(-1, 1, (1000, 60)).astype(np.float32)     # ragged (not a tile multiple)
+    with torch.no_grad():
+        out = net(T(x, dev))
+    close(npy(out), O.nerf_forward(params, x, dtype=np.float64), rtol=1e-4, atol=2e-5)
+    with torch.no_grad():
+        assert net(T(x[:0], dev)).shape == (0, 4)                    # empty input
+
+
+def test_run_network_fused_fp32(dev, golden):
+    from scade_b200 import functional as F_
+    g = golden("run_network")
+    bb_center, bb_scale = syn.bounding_box()
+    rb = syn.make_ray_batch(32, seed=5)
+    params = syn.make_nerf_params(seed=3, D=8, W=256, bias_scale=0.1, alpha_bias=0.3)
+    net = build_net(params, 8, 256, dev)
+    with torch.no_grad():
+        raw = F_.mlp_forward_rays(net.handle(), T(rb, dev), T(g["z"], dev), bb_center, bb_scale, "fp32")
+    close(npy(raw), g["raw"], rtol=2e-4, atol=5e-5)
+
+
+def test_nerf_forward_tensor_core(dev):
+    """tcgen05 path: fp16 operands, fp32 accumulate.  (1) against the same rounding emulated on the CPU
+    (oracle.nerf_forward_f16): agreement to accumulation-order noise, which pins the kernel's data movement
+    (swizzles, descriptors, chunk order, skip / view concat); (2) against the fp32 oracle: the stated
+    tensor-core tolerance (~4e-3 .. 3e-2 abs on raw outputs for these weight scales)."""
+    params = syn.make_nerf_params(seed=3, D=8, W=256, bias_scale=0.1, alpha_bias=0.3)
+    net = build_net(params, 8, 256, dev, precision="tc_f16")
+    x = np.random.default_rng(7).uniform(-1, 1, (1000, 60)).astype(np.float32)
+    with torch.no_grad():
+        out = npy(net(T(x, dev)))
+    emu = O.nerf_forward_f16(params, x)
+    ref = O.nerf_forward(params, x, dtype=np.float64)
+    assert np.abs(out - emu).max() < 2e-3, np.abs(out - emu).max()
+    assert np.abs(out - emu).mean() < 1e-4
+    assert np.abs(out - ref).max() < 3e-2, np.abs(out - ref).max()
+    assert np.abs(out - ref).mean() < 3e-3
+
+
+def test_run_network_fused_tensor_core(dev):
+    from scade_b200 import functional as F_
+    bb_center, bb_scale = syn.bounding_box()
+    rb = syn.make_ray_batch(77, seed=5)
+    z = np.sort(np.random.default_rng(8).uniform(0.1, 5.0, (77, 45)).astype(np.float32), -1)
+    pc, pf = net_pair(8, 256)
+    net = build_net(pf, 8, 256, dev, precision="tc_f16")
+    with torch.no_grad():
+        raw = npy(F_.mlp_forward_rays(net.handle(), T(rb, dev), T(z, dev), bb_center, bb_scale, "tc_f16"))
+    pts = rb[:, None, 0:3] + rb[:, None, 3:6] * z[:, :, None]
+    x = O.network_inputs(pts, rb[:, 8:11], bb_center, bb_scale)
+    emu = O.nerf_forward_f16(pf, x).reshape(77, 45, 4)
+    ref = O.run_network(pts, rb[:, 8:11], pf, bb_center, bb_scale, dtype=np.float64)
+    assert np.abs(raw - emu).max() < 5e-3, np.abs(raw - emu).max()
+    assert np.abs(raw - ref).mean() < 5e-3 and np.abs(raw - ref).max() < 8e-2
+
+
+@pytest.mark.parametrize("D,W", [(4, 64), (8, 256)])
+def test_nerf_backward_fp32(dev, D, W):
+    """Teacher-forced backward: same x and d_out into the CUDA backward and the oracle's analytic one."""
+    params = syn.make_nerf_params(seed=12, D=D, W=W, bias_scale=0.1, alpha_bias=0.3)
+    net = build_net(params, D, W, dev, requires_grad=True)
+    rng = np.random.default_rng(13)
+    x = rng.uniform(-1, 1, (700, 60)).astype(np.float32)
+    d_out = rng.standard_normal((700, 4)).astype(np.float32)
+    out = net(T(x, dev))
+    out.backward(T(d_out, dev))
+    ref = O.nerf_backward(params, x, d_out, dtype=np.float64)
+    for name, p in net.named_parameters():
+        r = ref[name]
+        err = np.abs(npy(p.grad) - r).max() / (np.abs(r).max() + 1e-12)
+        assert err < 2e-4, (name, err)
+
+
+# ------------------------------------------------------------------------------------------------
+# compositing
+# ------------------------------------------------------------------------------------------------
+def test_raw2outputs(dev, golden):
+    from scade_b200 import render as R_
+    g = golden("raw2outputs")
+    rb = syn.make_ray_batch(64, seed=6)
+    rgb, disp, acc, w, depth = [npy(t) for t in R_.raw2outputs(T(g["raw"], dev), T(g["z"], dev), T(rb[:, 3:6], dev))]
+    close(w, g["weights"]); close(rgb, g["rgb_map"]); close(acc, g["acc_map"]); close(depth, g["depth_map"])
+    assert np.isnan(disp[5]) and np.isnan(g["disp_map"][5])          # acc == 0 -> nan like the reference (RS:559)
+    ok = ~np.isnan(g["disp_map"])
+    close(disp[ok], g["disp_map"][ok])
+    from scade_b200 import functional as F_
+    rgb, _, _, w, depth = [npy(t) for t in F_.raw2outputs(T(g["raw"], dev), T(g["z"], dev), T(rb[:, 3:6], dev),
+                                                         T(g["noise"], dev))]
+    close(w, g["n_weights"]); close(rgb, g["n_rgb_map"]); close(depth, g["n_depth_map"])
+    # ragged sample counts (S not a multiple of the warp) against the oracle
+    rng = np.random.default_rng(9)
+    for S in (1, 5, 33, 192, 257):
+        raw = rng.standard_normal((37, S, 4)).astype(np.float32)
+        raw[..., 3] = np.abs(raw[..., 3]) * 2
+        z = np.sort(rng.uniform(0.1, 5.0, (37, S)).astype(np.float32), -1)
+        d = rng.standard_normal((37, 3)).astype(np.float32)
+        got = [npy(t) for t in F_.raw2outputs(T(raw, dev), T(z, dev), T(d, dev))]
+        want = O.raw2outputs(raw, z, d)
+        for a, b in zip(got, want):
+            close(a, b, rtol=2e-5, atol=2e-6)
+
+
+def test_raw2outputs_backward(dev, golden):
+    from scade_b200 import functional as F_
+    g = golden("raw2outputs")
+    rb = syn.make_ray_batch(64, seed=6)
+    raw = T(g["raw"][:16, :24].copy(), dev).requires_grad_(True)
+    outs = F_.raw2outputs(raw, T(g["z"][:16, :24].copy(), dev), T(rb[:16, 3:6], dev))
+    gs = [g["bwd_g_rgb"], g["bwd_g_disp"], g["bwd_g_acc"], g["bwd_g_w"], g["bwd_g_depth"]]
+    torch.autograd.backward(outs, [T(x, dev) for x in gs])
+    ref = g["bwd_d_raw"]
+    assert np.abs(npy(raw.grad) - ref).max() < 5e-5 * np.abs(ref).max()
+    rng = np.random.default_rng(10)
+    S = 70
+    rw = rng.standard_normal((21, S, 4)).astype(np.float32)
+    rw[..., 3] = np.abs(rw[..., 3])
+    z = np.sort(rng.uniform(0.1, 5.0, (21, S)).astype(np.float32), -1)
+    d = rng.standard_normal((21, 3)).astype(np.float32)
+    g5 = [rng.standard_normal(s).astype(np.float32) for s in [(21, 3), (21,), (21,), (21, S), (21,)]]
+    raw = T(rw, dev).requires_grad_(True)
+    torch.autograd.backward(F_.raw2outputs(raw, T(z, dev), T(d, dev)), [T(x, dev) for x in g5])
+    want = O.raw2outputs_bwd(rw, z, d, *g5, dtype=np.float64)
+    assert np.abs(npy(raw.grad) - want).max() < 5e-5 * np.abs(want).max()
+
+
+# ------------------------------------------------------------------------------------------------
+# hierarchical sampling
+# ------------------------------------------------------------------------------------------------
+def flips_ok(a, b, bins, rtol=1e-5, atol=1e-5, max_frac=0.005):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    bad = np.abs(a - b) > atol + rtol * np.abs(b)
+    assert bad.mean() <= max_frac, bad.mean()
+    width = np.diff(np.asarray(bins, np.float64), axis=-1).max(-1, keepdims=True)
+    assert (np.abs(a - b) <= width + atol)[bad].all()
+
+
+def test_sample_pdf(dev, golden):
+    from scade_b200 import nerf_helpers as NH
+    g = golden("sample_pdf")
+    bins, w = T(g["bins"], dev), T(g["w"], dev)
+    flips_ok(npy(NH.sample_pdf(bins, w, 48, det=True)), g["det"], g["bins"])
+    s, u = NH.sample_pdf_return_u(bins, w, 48, load_u=T(g["u"], dev))
+    flips_ok(npy(s), g["with_u"], g["bins"])
+    np.testing.assert_array_equal(npy(u), g["u"])
+    s, u = NH.sample_pdf_return_u(bins, w, 33, det=True)
+    flips_ok(npy(s), g["det33"], g["bins"])
+    close(npy(u), g["u_det33"], rtol=0, atol=6e-8)
+    np.testing.assert_array_equal(npy(u)[0], O.linspace(0.0, 1.0, 33))
+    s, _ = NH.sample_pdf_joint_return_u(bins, w, 48, load_u=T(np.broadcast_to(g["u_joint"], (40, 48)).copy(), dev))
+    flips_ok(npy(s), g["joint"], g["bins"])
+    from scade_b200 import functional as F_
+    s, _ = F_.sample_pdf(bins, w, 48, u=T(g["u_joint"], dev), joint=True)
+    flips_ok(npy(s), g["joint"], g["bins"])
+    kb, kw = T(np.linspace(0, 1, 5, dtype=np.float32)[None], dev), T(np.array([[1, 2, 1, 0]], np.float32), dev)
+    close(npy(NH.sample_pdf(kb, kw, 6, det=True)), g["kat_det"], atol=1e-6)
+    close(npy(NH.sample_pdf_return_u(kb, kw, 4, load_u=T(np.array([[.1, .9, .5, .25]], np.float32), dev))[0]),
+          g["kat_u"], atol=1e-6)
+    # pytest=True reproduces the reference's numpy seed-0 stream (H:352-361)
+    s = NH.sample_pdf(bins, w, 48, det=False, pytest=True)
+    np.random.seed(0)
+    want, _ = O.sample_pdf(g["bins"], g["w"], 48, u=np.random.rand(40, 48).astype(np.float32))
+    flips_ok(npy(s), want, g["bins"])
+
+
+def test_sample_pdf_backward(dev, golden):
+    from scade_b200 import nerf_helpers as NH
+    g = golden("sample_pdf")
+    w = T(g["w"], dev).requires_grad_(True)
+    s, _ = NH.sample_pdf_return_u(T(g["bins"], dev), w, 48, load_u=T(g["u"], dev))
+    s.backward(T(g["bwd_g"], dev))
+    ref = g["bwd_d_w"].astype(np.float64)
+    err = np.abs(npy(w.grad) - ref).max(-1) / (np.abs(ref).max(-1) + 1e-12)
+    assert np.median(err) < 1e-4 and (err < 2e-2).mean() > 0.9, err
+
+
+def test_resample_from_z_and_merge(dev):
+    from scade_b200 import functional as F_
+    rng = np.random.default_rng(11)
+    for N, S, n in [(50, 64, 128), (9, 128, 128), (33, 17, 5), (3, 256, 128)]:
+        z = np.sort(rng.uniform(0.1, 5.0, (N, S)).astype(np.float32), -1)
+        w = (rng.random((N, S), dtype=np.float32) ** 3).astype(np.float32)
+        u = rng.random((N, n), dtype=np.float32)
+        mid = 0.5 * (z[:, 1:] + z[:, :-1])
+        for uu in (None, u):
+            s, uo, merged, std = F_.resample_from_z(T(z, dev), T(w, dev), n, u=None if uu is None else T(uu, dev),
+                                                    merge=True, std=True)
+            want, wu = O.sample_pdf(mid, w[:, 1:-1], n, det=uu is None, u=uu)
+            flips_ok(npy(s), want, mid, max_frac=0.01)
+            close(npy(uo), wu, rtol=0, atol=6e-8)
+            np.testing.assert_array_equal(npy(merged), np.sort(np.concatenate([z, npy(s)], -1), -1))   # RS:713
+            close(npy(std), np.std(npy(s), -1), rtol=1e-4, atol=1e-6)                                  # RS:744
+        a, b = rng.standard_normal((N, S)).astype(np.float32), rng.standard_normal((N, n)).astype(np.float32)
+        np.testing.assert_array_equal(npy(F_.sort_merge(T(a, dev), T(b, dev))), np.sort(np.concatenate([a, b], -1), -1))
+        # backward w.r.t. the full weights row
+        wt = T(w, dev).requires_grad_(True)
+        s, _, _, _ = F_.resample_from_z(T(z, dev), wt, n, u=T(u, dev))
+        gs = rng.standard_normal((N, n)).astype(np.float32)
+        s.backward(T(gs, dev))
+        ref = np.zeros((N, S))
+        ref[:, 1:-1] = O.sample_pdf_bwd(mid, w[:, 1:-1], u, gs, dtype=np.float64)
+        err = np.abs(npy(wt.grad) - ref).max(-1) / (np.abs(ref).max(-1) + 1e-12)
+        assert np.median(err) < 2e-4 and (err < 2e-2).mean() > 0.9, (N, S, n, err)
+
+
+# ------------------------------------------------------------------------------------------------
+# losses
+# ------------------------------------------------------------------------------------------------
+def test_space_carving(dev, golden):
+    from scade_b200 import nerf_helpers as NH
+    g = golden("space_carving")
+    cases = {"default": {}, "joint": dict(is_joint=True), "thr": dict(threshold=0.6), "mask": dict(mask=g["mask"]),
+             "joint_mask_thr": dict(is_joint=True, mask=g["mask"], threshold=0.3)}
+    for name, kw in cases.items():
+        kw = dict(kw)
+        if "mask" in kw:
+            kw["mask"] = T(kw["mask"], dev)
+        pred = T(g["pred"], dev).requires_grad_(True)
+        hyp = T(g["hyp"], dev).requires_grad_(True)
+        loss = NH.compute_space_carving_loss(pred, hyp, norm_p=2, **kw)
+        loss.backward()
+        close(loss.item(), g[name + "_loss"], rtol=2e-5)
+        close(npy(pred.grad), g[name + "_d_pred"], rtol=1e-5, atol=1e-9)
+        close(npy(hyp.grad), g[name + "_d_hyp"], rtol=1e-4, atol=1e-8)
+    pred = T(g["pred"], dev).requires_grad_(True)
+    hyp = T(g["hyp_full"], dev).requires_grad_(True)
+    loss = NH.compute_space_carving_loss(pred, hyp)
+    loss.backward()
+    close(loss.item(), g["full_loss"], rtol=2e-5)
+    close(npy(pred.grad), g["full_d_pred"], atol=1e-9)
+    close(npy(hyp.grad), g["full_d_hyp"], atol=1e-9)
+    kp = T(np.array([[1, 2], [3, 5]], np.float32), dev)
+    kh = T(np.array([[[1.5], [2.0]], [[0], [4.5]], [[2], [9]]], np.float32), dev)
+    got = [NH.compute_space_carving_loss(kp, kh).item(), NH.compute_space_carving_loss(kp, kh, is_joint=True).item(),
+           NH.compute_space_carving_loss(kp, kh, threshold=0.6).item(),
+           NH.compute_space_carving_loss(kp, kh, mask=T(np.array([1, 0], np.float32), dev)).item()]
+    close(got, [0.5, 1.0, 0.25, 0.125])
+    # BASELINE config 3 size: K=20, 4096 rays x 128 samples, against the oracle
+    rng = np.random.default_rng(14)
+    pred = rng.uniform(0.1, 5.0, (4096, 128)).astype(np.float32)
+    hyp = rng.uniform(0.1, 5.0, (20, 4096, 1)).astype(np.float32)
+    pt, ht = T(pred, dev).requires_grad_(True), T(hyp, dev).requires_grad_(True)
+    loss = NH.compute_space_carving_loss(pt, ht)
+    loss.backward()
+    close(loss.item(), O.space_carving_loss(pred, hyp, dtype=np.float64), rtol=1e-5)
+    d_pred, d_hyp = O.space_carving_loss_bwd(pred, hyp)
+    close(npy(pt.grad), d_pred, rtol=1e-5, atol=1e-12)
+    close(npy(ht.grad), d_hyp, rtol=1e-4, atol=1e-9)
+
+
+def test_img2mse(dev):
+    from scade_b200 import nerf_helpers as NH
+    rng = np.random.default_rng(15)
+    x, y = rng.random((4096, 3), dtype=np.float32), rng.random((4096, 3), dtype=np.float32)
+    xt = T(x, dev).requires_grad_(True)
+    loss = NH.img2mse(xt, T(y, dev))
+    loss.backward()
+    close(loss.item(), O.img2mse(x, y, dtype=np.float64), rtol=1e-5)
+    close(npy(xt.grad), 2 * (x - y) / x.size, rtol=1e-5, atol=1e-10)
+    close(NH.mse2psnr(loss).item(), O.mse2psnr(np.float32(loss.item())), rtol=1e-5)
+
+
+# ------------------------------------------------------------------------------------------------
+# render_rays end to end
+# ------------------------------------------------------------------------------------------------
+def make_render_kwargs(D, W, dev, precision, perturb, Nc, Nf, requires_grad=False):
+    from scade_b200 import nerf_helpers as NH
+    from scade_b200.render import NetworkQuery
+    pc, pf = net_pair(D, W)
+    bb_center, bb_scale = syn.bounding_box()
+    netc = build_net(pc, D, W, dev, precision, requires_grad)
+    netf = build_net(pf, D, W, dev, precision, requires_grad)
+    qf = NetworkQuery(NH.get_embedder(9, 0)[0], NH.get_embedder(0, 0)[0], bb_center, bb_scale, precision=precision)
+    kwargs = dict(network_fn=netc, network_query_fn=qf, N_samples=Nc, embedded_cam=torch.tensor((), device=dev),
+                  retraw=True, perturb=perturb, N_importance=Nf, network_fine=netf, raw_noise_std=0.0)
+    return kwargs, (pc, pf, bb_center, bb_scale)
+
+
+@pytest.mark.parametrize("name", list(RENDER_CASES))
+def test_render_rays_fp32_vs_reference_golden(dev, golden, name):
+    from scade_b200 import render as R_
+    g = golden(name)
+    n, Nc, Nf, D, W, perturb = RENDER_CASES[name]
+    kwargs, _ = make_render_kwargs(D, W, dev, "fp32", perturb, Nc, Nf)
+    rb = syn.make_ray_batch(n, seed=20)
+    t_rand, u_c, u_f = syn.make_uniforms(n, Nc, Nf, seed=21)
+    with torch.no_grad():
+        if perturb > 0:
+            ret = R_.render_rays(T(rb, dev), True, cached_u=T(u_f, dev), t_rand=T(t_rand, dev), u_coarse=T(u_c, dev), **kwargs)
+        else:
+            ret = R_.render_rays(T(rb, dev), True, **kwargs)
+    assert set(g) - {"raw_head"} <= set(ret) and "raw" in ret
+    for k, (mean_tol, max_tol) in RENDER_FP32_TOL.items():
+        mean_close(npy(ret[k]), g[k], mean_tol, max_tol, name=k)
+    close(npy(ret["u"]), g["u"], rtol=0, atol=6e-8)
+
+
+def test_render_rays_fused_equals_composed(dev):
+    """The one-call C orchestration (eval path) and the autograd-composed path launch the same kernels."""
+    from scade_b200 import render as R_
+    kwargs, _ = make_render_kwargs(8, 256, dev, "fp32", 1.0, 64, 128)
+    rb = T(syn.make_ray_batch(200, seed=40), dev)
+    t_rand, u_c, u_f = [T(x, dev) for x in syn.make_uniforms(200, 64, 128, seed=41)]
+    with torch.no_grad():
+        a = R_.render_rays(rb, True, cached_u=u_f, t_rand=t_rand, u_coarse=u_c, **kwargs)
+    for p in kwargs["network_fn"].parameters():
+        p.requires_grad_(True)
+    b = R_.render_rays(rb, True, cached_u=u_f, t_rand=t_rand, u_coarse=u_c, **kwargs)
+    assert b["rgb_map"].requires_grad and b["pred_hyp"].requires_grad and not b["z_vals"].requires_grad
+    for k in a:
+        np.testing.assert_array_equal(npy(a[k]), npy(b[k]), err_msg=k)
+
+
+def psnr(a, b):
+    return -10.0 * np.log10(np.mean((np.asarray(a, np.float64) - np.asarray(b, np.float64)) ** 2) + 1e-20)
+
+
+def test_render_rays_tensor_core_vs_oracle(dev):
+    """Tensor-core mode end to end (BASELINE config 2 shape, fewer rays): PSNR of rgb against the fp32 oracle
+    >= 45 dB and mean abs depth error <= 5e-3 (SURVEY App. D measured 55-62 dB / 2e-3 for fp16 operands)."""
+    from scade_b200 import render as R_
+    kwargs, (pc, pf, bb_center, bb_scale) = make_render_kwargs(8, 256, dev, "tc_f16", 0.0, 64, 128)
+    rbn = syn.make_ray_batch(256, seed=42)
+    with torch.no_grad():
+        ret = R_.render_rays(T(rbn, dev), True, **kwargs)
+    ref = O.render_rays(rbn, pc, pf, bb_center, bb_scale, 64, 128)
+    assert psnr(npy(ret["rgb_map"]), ref["rgb_map"]) > 45.0, psnr(npy(ret["rgb_map"]), ref["rgb_map"])
+    assert psnr(npy(ret["rgb0"]), ref["rgb0"]) > 45.0
+    assert np.abs(npy(ret["depth_map"]) - ref["depth_map"]).mean() < 5e-3
+    assert np.abs(npy(ret["pred_hyp"]) - ref["pred_hyp"]).mean() < 2e-2
+    close(npy(ret["acc_map"]), ref["acc_map"], rtol=0, atol=1e-4)
+    np.testing.assert_array_equal(npy(ret["z_vals0"]), ref["z_vals0"])
+
+
+def test_render_image_and_chunking(dev):
+    """render() with c2w (RS:106-108) and batchify_rays: results do not depend on ``chunk`` (RS:88-89)."""
+    from scade_b200 import render as R_
+    kwargs, _ = make_render_kwargs(8, 256, dev, "tc_f16", 0.0, 64, 128)
+    kwargs.pop("retraw")
+    c2w = torch.from_numpy(syn.spiral_poses(4)[1])
+    with torch.no_grad():
+        rgb, disp, acc, extras = R_.render(24, 32, syn.CAM_INTRINSIC, chunk=4096, c2w=c2w, near=0.1, far=5.0,
+                                           use_viewdirs=True, **kwargs)
+        rgb2, disp2, acc2, extras2 = R_.render(24, 32, syn.CAM_INTRINSIC, chunk=100, c2w=c2w, near=0.1, far=5.0,
+                                               use_viewdirs=True, **kwargs)
+    assert rgb.shape == (24, 32, 3) and disp.shape == (24, 32) and extras["z_vals"].shape == (24, 32, 192)
+    assert extras["pred_hyp"].shape == (24, 32, 128) and extras["rgb0"].shape == (24, 32, 3)
+    np.testing.assert_array_equal(npy(rgb), npy(rgb2))
+    np.testing.assert_array_equal(npy(extras["depth_map"]), npy(extras2["depth_map"]))
+    with torch.no_grad():
+        crop = R_.render(18, 64, syn.CAM_INTRINSIC, c2w=c2w, near=0.1, far=5.0, use_viewdirs=True, with_5_9=True, **kwargs)
+    assert crop[0].shape == (18, 10, 3)          # W' = int(18/9*16/3) = 10 (RS:111-113)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "tc_f16"])
+def test_render_properties_at_baseline_size(dev, precision):
+    """BASELINE metric shape (4096 rays x 128 coarse + 128 importance, 8x256): properties that hold at any size."""
+    from scade_b200 import render as R_
+    kwargs, _ = make_render_kwargs(8, 256, dev, precision, 0.0, 128, 128)
+    kwargs["retraw"] = False
+    rb = T(syn.make_ray_batch(4096, seed=50), dev)
+    with torch.no_grad():
+        ret = R_.render_rays(rb, True, **kwargs)
+    z, w = npy(ret["z_vals"]), npy(ret["weights"])
+    assert z.shape == (4096, 256) and (np.diff(z, axis=-1) >= 0).all()                  # sorted merge (RS:713)
+    assert np.isfinite(npy(ret["rgb_map"])).all() and (w >= 0).all()
+    close(w.sum(-1), npy(ret["acc_map"]), rtol=1e-5, atol=1e-6)                          # RS:560
+    close((w * z).sum(-1), npy(ret["depth_map"]), rtol=1e-4, atol=1e-5)                  # RS:558
+    assert (npy(ret["rgb_map"]) >= 0).all() and (npy(ret["rgb_map"]) <= 1 + 1e-5).all()  # convex mix of sigmoids
+    assert (npy(ret["pred_hyp"]) >= z[:, :1] - 1e-6).all() and (npy(ret["pred_hyp"]) <= z[:, -1:] + 1e-6).all()
+    assert (np.diff(npy(ret["pred_hyp"]), axis=-1) >= -1e-6).all()                       # det u is monotone
+    # the coarse 128 samples are a subset of the merged 256
+    z0 = npy(ret["z_vals0"])
+    assert all(np.isin(z0[r], z[r]).all() for r in range(0, 4096, 512))
+    # ray independence: any sub-batch renders to the same values
+    with torch.no_grad():
+        sub = R_.render_rays(rb[1000:1300], True, **kwargs)
+    np.testing.assert_array_equal(npy(sub["rgb_map"]), npy(ret["rgb_map"])[1000:1300])
+
+
+# ------------------------------------------------------------------------------------------------
+# train step
+# ------------------------------------------------------------------------------------------------
+def test_train_step_matches_oracle(dev):
+    """RS:954-985 on the CUDA path (autograd over the CUDA kernels) vs the oracle's analytic gradients, on a
+    small net where fp32 chaos is mild; the losses also against the reference-generated golden."""
+    from scade_b200 import nerf_helpers as NH
+    from scade_b200 import render as R_
+    n, Nc, Nf, D, W = 48, 32, 64, 4, 64
+    kwargs, (pc, pf, bb_center, bb_scale) = make_render_kwargs(D, W, dev, "fp32", 1.0, Nc, Nf, requires_grad=True)
+    rb = syn.make_ray_batch(n, seed=30)
+    t_rand, u_c, u_f = syn.make_uniforms(n, Nc, Nf, seed=31)
+    target_s, target_h = syn.make_train_targets(n, K=20, seed=32)
+    scale = torch.tensor([1.1], device=dev, requires_grad=True)
+    shift = torch.tensor([-0.05], device=dev, requires_grad=True)
+    th = T(target_h, dev) * scale + shift                                            # RS:954
+    rays = torch.stack([T(rb[:, 0:3], dev), T(rb[:, 3:6], dev)], 0)
+    kwargs.update(near=0.1, far=5.0, use_viewdirs=True)
+    rgb, _, _, extras = R_.render_hyp(480, 640, None, chunk=32768, rays=rays, cached_u=T(u_f, dev), t_rand=T(t_rand, dev),
+                                      u_coarse=T(u_c, dev), **kwargs)                # RS:963
+    img_loss = NH.img2mse(rgb, T(target_s, dev))
+    sc = NH.compute_space_carving_loss(extras["pred_hyp"], th, is_joint=False, norm_p=2, threshold=0.0)
+    img_loss0 = NH.img2mse(extras["rgb0"], T(target_s, dev))
+    loss = img_loss + 0.007 * sc + img_loss0                                         # RS:976,983
+    loss.backward()                                                                  # RS:985
+    losses, gc, gf, d_scale, d_shift, _ = O.train_loss_and_grads(
+        rb, pc, pf, bb_center, bb_scale, Nc, Nf, target_s, target_h, t_rand, u_c, u_f, scale=1.1, shift=-0.05)
+    close(img_loss0.item(), losses["img_loss0"], rtol=1e-5)
+    close(loss.item(), losses["loss"], rtol=2e-3)
+    close(sc.item(), losses["space_carving"], rtol=2e-3)
+    close(scale.grad.item(), d_scale, rtol=5e-2, atol=3e-5)
+    close(shift.grad.item(), d_shift, rtol=5e-2, atol=3e-5)
+    for net, ref, tol in ((kwargs["network_fn"], gc, 1e-3), (kwargs["network_fine"], gf, 0.25)):
+        for name, p in net.named_parameters():
+            r = ref[name]
+            err = np.abs(npy(p.grad) - r).max() / (np.abs(r).max() + 1e-12)
+            assert err < tol, (name, err)
+    # an optimizer step on the reference's parameter containers works unchanged (RS:993)
+    opt = torch.optim.Adam(list(kwargs["network_fn"].parameters()) + list(kwargs["network_fine"].parameters()), lr=5e-4)
+    before = kwargs["network_fine"].alpha_linear.weight.detach().clone()
+    opt.step()
+    assert not torch.equal(before, kwargs["network_fine"].alpha_linear.weight)
