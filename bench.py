@@ -1,0 +1,309 @@
+#!/usr/bin/env python
+"""Headline benchmark: rays/sec of the SCADE render path on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--precision tc_f16|fp32]
+
+Workload (BASELINE.json "metric"): one step = render_rays forward (coarse 8x256 MLP on 128 samples ->
+compositing -> sample_pdf -> sort-merge -> fine 8x256 MLP on 256 samples -> compositing -> second
+sample_pdf) over 4096 synthetic rays per GPU, all reference outputs materialised (RS:733-744, no `raw`).
+Weak scaling: every rank renders its own 4096 rays, no data-path collective (rays are independent).
+
+Prints ONE JSON line (rank 0).  `value` = rays/s with the ray batch already in HBM, timed with CUDA events
+on the launching stream around each step (L2 flushed between steps, untimed); `e2e` = the same metric through
+the public Python API (scade_b200.render.render_rays -> C ABI) with the ray batch in pinned HOST memory and the
+image outputs read back every step.  `roofline` is for the dominant kernel (the fine-pass tcgen05 MLP launch),
+`cpu_baseline` is the torch-op port of the reference's CPU path on this box's host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_RAYS, N_COARSE, N_FINE, NET_D, NET_W = 4096, 128, 128, 8, 256
+FLOP_PER_EVAL = 2 * 587264            # 587,264 MAC per MLP evaluation
+WORKLOAD = f"render_rays fwd, {N_RAYS} rays x ({N_COARSE}c+{N_FINE}f), {NET_D}x{NET_W} MLP x2 nets, det sampling"
+METRIC = "rays/sec (4096 rays x 256 samples, 8x256 MLP)"
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return p.get("bf16_tflops", 1590.0), p.get("bf16_tflops_sustained", 1400.0), p.get("hbm_gbs", 6650.0), "measured"
+    return 1590.0, 1400.0, 6650.0, "fallback"       # B200_PROFILING.md fallback figures
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: torch-op port of the reference's CPU path (oracle/torch_port.py)
+# ------------------------------------------------------------------------------------------------
+def cpu_arm(n_rays_sample, steps, warmup):
+    import torch
+    from oracle import torch_port as TP
+    from scade_b200 import synthetic as syn
+    from tests.golden.generate_goldens import net_pair
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    pc, pf = net_pair(NET_D, NET_W)
+    pc = {k: torch.from_numpy(v) for k, v in pc.items()}
+    pf = {k: torch.from_numpy(v) for k, v in pf.items()}
+    bb_center, bb_scale = syn.bounding_box()
+    rb = torch.from_numpy(syn.make_ray_batch(N_RAYS, seed=50)[:n_rays_sample])
+    bbc = torch.from_numpy(bb_center)
+    times = []
+    with torch.no_grad():
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            TP.render_rays(rb, pc, pf, bbc, float(bb_scale), N_COARSE, N_FINE)
+            dt = time.perf_counter() - t0
+            if i >= warmup:
+                times.append(dt)
+    sec = float(np.mean(times))
+    return {"value": n_rays_sample / sec, "unit": "rays/s", "cores": cores, "kind": "port",
+            "sample": f"{n_rays_sample} of {N_RAYS} rays of the same workload per step, {steps} steps after {warmup} warm-up, "
+                      f"torch {torch.__version__} CPU fp32, {cores} threads (oracle/torch_port.py)",
+            "sec_per_step": sec}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    base = cpu_arm(256, max(1, min(args.steps, 5)), 1)
+    line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": "rays/s", "n_gpus": args.gpus,
+            "steps": max(1, min(args.steps, 5)), "warmup": 1, "ms_per_step": base["sec_per_step"] * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD}, "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": base["value"], "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampler
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.samples, self.proc, self.thread = index, [], None, None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+        except Exception:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._read, daemon=True)
+        self.thread.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for s in self.samples:
+            parts = [p.strip() for p in s.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0])); mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], parts[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    from scade_b200 import _lib, functional as F_, synthetic as syn
+    from scade_b200 import nerf_helpers as NH
+    from scade_b200 import render as R_
+    from tests.golden.generate_goldens import net_pair
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+    prec = args.precision
+
+    pc, pf = net_pair(NET_D, NET_W)
+
+    def mk(params):
+        net = NH.NeRF(D=NET_D, W=NET_W, input_ch=57, input_ch_views=3, output_ch=5, skips=[4], use_viewdirs=True,
+                      precision=prec)
+        net.load_state_dict({k: torch.from_numpy(v) for k, v in params.items()})
+        net = net.to(dev)
+        for p in net.parameters():
+            p.requires_grad_(False)
+        return net
+    netc, netf = mk(pc), mk(pf)
+    bb_center, bb_scale = syn.bounding_box()
+    qf = R_.NetworkQuery(NH.get_embedder(9, 0)[0], NH.get_embedder(0, 0)[0], bb_center, bb_scale, precision=prec)
+    kwargs = dict(network_fn=netc, network_query_fn=qf, N_samples=N_COARSE, embedded_cam=torch.tensor((), device=dev),
+                  retraw=False, perturb=0.0, N_importance=N_FINE, network_fine=netf, raw_noise_std=0.0)
+    rb_host = torch.from_numpy(syn.make_ray_batch(N_RAYS, seed=50 + rank)).pin_memory()
+    rb_dev = rb_host.to(dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident():
+        return F_.render_rays_forward(rb_dev, netc.handle(), netf.handle(), N_COARSE, N_FINE, bb_center, bb_scale,
+                                      precision=prec)
+
+    out_host = {k: torch.empty(s, dtype=torch.float32).pin_memory()
+                for k, s in {"rgb_map": (N_RAYS, 3), "disp_map": (N_RAYS,), "acc_map": (N_RAYS,), "depth_map": (N_RAYS,)}.items()}
+
+    def step_e2e():
+        rb = rb_host.to(dev, non_blocking=True)
+        with torch.no_grad():
+            ret = R_.render_rays(rb, True, **kwargs)
+        for k, buf in out_host.items():
+            buf.copy_(ret[k], non_blocking=True)
+        return ret
+
+    # ---- warm-up ----
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+        step_e2e()
+    sync_all()
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+
+    # ---- timed: device-resident ----
+    launches0 = lib.scade_kernel_launch_count()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    sync_all()
+    wall0 = time.perf_counter()
+    for s, e in ev:
+        flush.zero_()                      # L2 flush between steps (untimed)
+        s.record()
+        step_resident()
+        e.record()
+    sync_all()
+    wall = time.perf_counter() - wall0
+    launches = lib.scade_kernel_launch_count() - launches0
+    dev_ms = sum(s.elapsed_time(e) for s, e in ev)
+
+    # ---- timed: end to end through the public API with host buffers ----
+    sync_all()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_e2e()
+        torch.cuda.current_stream().synchronize()      # the result is on the host when the step ends
+    sync_all()
+    e2e_sec = time.perf_counter() - t0
+
+    # ---- dominant kernel alone: fine-pass MLP launch (4096 x 256 points) ----
+    z_f = step_resident()["z_vals"]
+    mlp_ev = []
+    for i in range(3 + args.steps):
+        flush.zero_()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        F_.mlp_forward_rays(netf.handle(), rb_dev, z_f, bb_center, bb_scale, prec)
+        e.record()
+        if i >= 3:
+            mlp_ev.append((s, e))
+    torch.cuda.synchronize()
+    mlp_ms = float(np.mean([s.elapsed_time(e) for s, e in mlp_ev]))
+    clocks = sampler.stop() if rank == 0 else None
+
+    t = torch.tensor([dev_ms, e2e_sec * 1e3], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms, e2e_ms = float(t[0]), float(t[1])
+
+    if rank == 0:
+        burst, sustained, hbm, src = load_peaks()
+        total_rays = N_RAYS * world * args.steps
+        flop_launch = N_RAYS * (N_COARSE + N_FINE) * FLOP_PER_EVAL
+        achieved = flop_launch / (mlp_ms * 1e-3) / 1e12
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+        if os.path.exists(tpath):
+            with open(tpath) as f:
+                traffic = json.load(f).get("mlp_fine_dram_bytes_per_launch")
+        is_tc = prec == "tc_f16"
+        line = {
+            "metric": METRIC, "value": total_rays / (dev_ms * 1e-3), "unit": "rays/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f16 operands / f32 accumulate (tcgen05)" if is_tc else "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "rays_per_gpu": N_RAYS, "precision": prec, "parallelism": f"rays x{world}",
+                       "l2": "flushed between steps (256 MiB memset, untimed); weights (2.3 MB fp16) are meant to be L2-resident",
+                       "weights": "Xavier-uniform random init (synthetic.make_nerf_params)"},
+            "e2e": {"value": total_rays / (e2e_ms * 1e-3), "unit": "rays/s", "h2d_bytes_per_step": int(rb_host.numel() * 4),
+                    "d2h_bytes_per_step": int(sum(b.numel() * 4 for b in out_host.values())),
+                    "api": "scade_b200.render.render_rays (pinned host ray batch in, rgb/disp/acc/depth maps out)"},
+            "gpu_launches": int(launches),
+            "wall_ms_timed_region": wall * 1e3,
+            "roofline": {"bound": "tensor", "kernel": "nerf_mlp_tc_kernel (fine pass, 4096x256 points)" if is_tc
+                         else "sgemm_kernel chain (fine pass)",
+                         "achieved": achieved, "peak": burst, "unit": "TFLOP/s", "frac": achieved / burst,
+                         "peak_source": f"{src} bf16 dense burst (kernel timed alone)", "traffic": traffic,
+                         "flop_per_launch": flop_launch, "ms_per_launch": mlp_ms,
+                         "step_frac_of_sustained_peak": (N_RAYS * (2 * N_COARSE + N_FINE) * FLOP_PER_EVAL)
+                         / (dev_ms / args.steps * 1e-3) / 1e12 / sustained},
+            "clocks": clocks,
+        }
+        if not args.no_cpu_baseline:
+            base = cpu_arm(256, 2, 1)
+            line["cpu_baseline"] = {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default="tc_f16", choices=["tc_f16", "fp32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -42,6 +42,8 @@ typedef enum {
 
 int scade_version(void);
 const char* scade_last_error_string(void);
+/* Number of CUDA kernels this library has launched in the calling process (diagnostic; bench.py reports it). */
+uint64_t scade_kernel_launch_count(void);
 
 /* ---------------------------------------------------------------------------------------------
  * Field network: NeRF(D, W, input_ch, input_ch_views, skips=[skip], use_viewdirs=True)  (H:193-247)

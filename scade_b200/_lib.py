@@ -47,6 +47,7 @@ _P = c_void_p
 _SIGNATURES = {
     "scade_version": (c_int, []),
     "scade_last_error_string": (c_char_p, []),
+    "scade_kernel_launch_count": (ctypes.c_uint64, []),
     "scade_mlp_packed_bytes": (c_size_t, [POINTER(NetDesc)]),
     "scade_mlp_pack_f16": (c_int, [POINTER(Net), _P, _P]),
     "scade_mlp_workspace_bytes": (c_size_t, [POINTER(NetDesc), c_int64, c_int, c_int]),

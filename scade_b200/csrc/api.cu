@@ -8,6 +8,7 @@
 namespace scade {
 
 static thread_local char g_err[512] = "";
+unsigned long long g_launch_count = 0;
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -49,6 +50,7 @@ using namespace scade;
 
 extern "C" int scade_version(void) { return SCADE_B200_VERSION; }
 extern "C" const char* scade_last_error_string(void) { return g_err; }
+extern "C" uint64_t scade_kernel_launch_count(void) { return g_launch_count; }
 
 extern "C" size_t scade_mlp_packed_bytes(const scade_net_desc* desc) {
   if (!desc || check_desc(*desc) != SCADE_OK || !mlp_tc_supported(*desc)) return 0;
@@ -78,7 +80,8 @@ extern "C" int scade_mlp_forward_rays(const scade_net* net, int precision, const
                                       float bb_scale, float* raw_out, void* workspace, size_t workspace_bytes,
                                       int save_for_backward, void* stream) {
   SCADE_TRY(check_net(net, precision));
-  SCADE_CHECK_ARG(rays && z_vals && bb_center_host && raw_out && N >= 0 && S > 0 && ray_stride >= 11,
+  if (N == 0) return SCADE_OK;
+  SCADE_CHECK_ARG(rays && z_vals && bb_center_host && raw_out && N > 0 && S > 0 && ray_stride >= 11,
                   "mlp_forward_rays: bad arguments");
   SCADE_CHECK_ARG((reinterpret_cast<uintptr_t>(raw_out) & 15) == 0, "mlp_forward_rays: raw_out must be 16-byte aligned");
   if (N == 0) return SCADE_OK;
@@ -93,7 +96,8 @@ extern "C" int scade_mlp_forward_rays(const scade_net* net, int precision, const
 extern "C" int scade_mlp_forward_embedded(const scade_net* net, int precision, const float* x, int64_t P, float* out,
                                           void* workspace, size_t workspace_bytes, int save_for_backward, void* stream) {
   SCADE_TRY(check_net(net, precision));
-  SCADE_CHECK_ARG(x && out && P >= 0, "mlp_forward_embedded: bad arguments");
+  if (P == 0) return SCADE_OK;
+  SCADE_CHECK_ARG(x && out && P > 0, "mlp_forward_embedded: bad arguments");
   SCADE_CHECK_ARG((reinterpret_cast<uintptr_t>(out) & 15) == 0, "mlp_forward_embedded: out must be 16-byte aligned");
   if (P == 0) return SCADE_OK;
   SCADE_CHECK_ARG(workspace != nullptr, "mlp_forward_embedded: null workspace");

@@ -29,7 +29,13 @@ void set_error(const char* fmt, ...);
     }                                                                                        \
   } while (0)
 
-#define SCADE_LAUNCH_CHECK() SCADE_CUDA(cudaGetLastError())
+// every kernel launch of the library goes through this macro; the counter backs bench.py's gpu_launches claim
+extern unsigned long long g_launch_count;
+#define SCADE_LAUNCH_CHECK()            \
+  do {                                  \
+    ++::scade::g_launch_count;          \
+    SCADE_CUDA(cudaGetLastError());     \
+  } while (0)
 
 #define SCADE_TRY(call)          \
   do {                           \

@@ -85,9 +85,8 @@ def _mlp_backward(handle, precision, d_out, P, ws, device):
 
 class _MLPRaysFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, rays, z_vals, handle, precision, bb_center, bb_scale, *params):
+    def forward(ctx, rays, z_vals, handle, precision, bb_center, bb_scale, need_grad, *params):
         N, S = z_vals.shape
-        need_grad = any(ctx.needs_input_grad[6:])
         raw = torch.empty((N, S, 4), dtype=torch.float32, device=z_vals.device)
         ws = _bytes(handle.workspace_bytes(N * S, precision, need_grad), z_vals.device)
         net = handle.struct(precision)
@@ -104,14 +103,13 @@ class _MLPRaysFn(torch.autograd.Function):
             raise _lib.ScadeError("backward through a forward that did not stash activations")
         grads = _mlp_backward(ctx.handle, ctx.precision, f32(d_raw), ctx.P, ctx.ws, d_raw.device)
         ctx.ws = None
-        return (None, None, None, None, None, None, *grads)
+        return (None, None, None, None, None, None, None, *grads)
 
 
 class _MLPEmbeddedFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, handle, precision, *params):
+    def forward(ctx, x, handle, precision, need_grad, *params):
         P = x.shape[0]
-        need_grad = any(ctx.needs_input_grad[3:])
         out = torch.empty((P, 4), dtype=torch.float32, device=x.device)
         ws = _bytes(handle.workspace_bytes(P, precision, need_grad), x.device)
         net = handle.struct(precision)
@@ -127,17 +125,20 @@ class _MLPEmbeddedFn(torch.autograd.Function):
             raise _lib.ScadeError("backward through a forward that did not stash activations")
         grads = _mlp_backward(ctx.handle, ctx.precision, f32(d_out), ctx.P, ctx.ws, d_out.device)
         ctx.ws = None
-        return (None, None, None, *grads)
+        return (None, None, None, None, *grads)
 
 
 def mlp_forward_rays(handle, rays, z_vals, bb_center, bb_scale, precision=PREC_FP32):
     """run_network fused with pts = o + d*z (RS:48-63, 657): rays [N,>=11], z [N,S] -> raw [N,S,4]."""
     precision = PRECISIONS[precision]
     rays, z_vals = f32(rays), f32(z_vals)
-    if precision == PREC_TC_F16 and torch.is_grad_enabled() and any(p.requires_grad for p in handle.params):
+    need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in handle.params)
+    if precision == PREC_TC_F16 and need_grad:
         precision = PREC_FP32      # training stashes fp32 activations; tensor-core backward is future work
+    if rays.shape[0] == 0:
+        return torch.empty((0, z_vals.shape[1], 4), dtype=torch.float32, device=z_vals.device)
     return _MLPRaysFn.apply(rays, z_vals, handle, precision, [float(c) for c in bb_center], float(bb_scale),
-                            *handle.params)
+                            need_grad, *handle.params)
 
 
 def mlp_forward_embedded(handle, x, precision=PREC_FP32):
@@ -145,9 +146,12 @@ def mlp_forward_embedded(handle, x, precision=PREC_FP32):
     precision = PRECISIONS[precision]
     lead = x.shape[:-1]
     x2 = f32(x).reshape(-1, x.shape[-1])
-    if precision == PREC_TC_F16 and torch.is_grad_enabled() and any(p.requires_grad for p in handle.params):
+    need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in handle.params)
+    if precision == PREC_TC_F16 and need_grad:
         precision = PREC_FP32
-    return _MLPEmbeddedFn.apply(x2, handle, precision, *handle.params).reshape(*lead, 4)
+    if x2.shape[0] == 0:
+        return torch.empty((*lead, 4), dtype=torch.float32, device=x2.device)
+    return _MLPEmbeddedFn.apply(x2, handle, precision, need_grad, *handle.params).reshape(*lead, 4)
 
 
 def embed(x, multires):
@@ -340,13 +344,12 @@ def sort_merge(a, b):
 # ----------------------------------------------------------------------------------------------
 class _SpaceCarvingFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, pred, hyp, mask, is_joint, threshold):
+    def forward(ctx, pred, hyp, mask, is_joint, threshold, want):
         N, P = pred.shape
         K = hyp.shape[0]
         full = hyp.shape[-1] != 1
         dev = pred.device
         loss = torch.empty((1,), dtype=torch.float32, device=dev)
-        want = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
         d_pred = torch.empty_like(pred) if want else None
         d_hyp = torch.empty_like(hyp) if want else None
         ws = _bytes(_L().scade_space_carving_workspace_bytes(K, N, P), dev)
@@ -360,21 +363,21 @@ class _SpaceCarvingFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):
         d_pred, d_hyp = ctx.saved_tensors
-        return d_pred * g, d_hyp * g, None, None, None
+        return d_pred * g, d_hyp * g, None, None, None, None
 
 
 def space_carving_loss(pred, hyp, is_joint=False, mask=None, threshold=0.0):
     """compute_space_carving_loss (H:93-128)."""
     pred, hyp = f32(pred), f32(hyp)
     mask = None if mask is None else f32(mask)
-    return _SpaceCarvingFn.apply(pred, hyp, mask, bool(is_joint), float(threshold))
+    want = torch.is_grad_enabled() and (pred.requires_grad or hyp.requires_grad)
+    return _SpaceCarvingFn.apply(pred, hyp, mask, bool(is_joint), float(threshold), want)
 
 
 class _MseFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, y, denominator):
+    def forward(ctx, x, y, denominator, want):
         loss = torch.empty((1,), dtype=torch.float32, device=x.device)
-        want = ctx.needs_input_grad[0]
         d_x = torch.empty_like(x) if want else None
         check(_L().scade_img2mse(ptr(x), ptr(y), x.numel(), int(denominator), 1.0, ptr(loss), ptr(d_x), stream_ptr()),
               "scade_img2mse")
@@ -385,12 +388,13 @@ class _MseFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):
         (d_x,) = ctx.saved_tensors
-        return d_x * g, None, None
+        return d_x * g, None, None, None
 
 
 def img2mse(x, y, denominator=0):
     """img2mse (H:11).  denominator > 0 replaces numel() in the mean (ray-sharded training)."""
-    return _MseFn.apply(f32(x), f32(y).expand_as(x).contiguous(), denominator)
+    x = f32(x)
+    return _MseFn.apply(x, f32(y).expand_as(x).contiguous(), denominator, torch.is_grad_enabled() and x.requires_grad)
 
 
 # ----------------------------------------------------------------------------------------------

@@ -219,3 +219,18 @@ def test_train_step_float64_pins_analytic_backward(golden):
         for k, v in grads.items():
             ref = g[pref + k]
             assert np.abs(v - ref).max() <= 1e-9 * np.abs(ref).max() + 1e-18, pref + k
+
+
+def test_torch_port_matches_oracle():
+    """oracle/torch_port.py (the timed CPU baseline) computes what the numpy oracle computes."""
+    import torch
+    from oracle import torch_port as TP
+    pc, pf = net_pair(8, 256)
+    bb_center, bb_scale = syn.bounding_box()
+    rb = syn.make_ray_batch(40, seed=60)
+    want = O.render_rays(rb, pc, pf, bb_center, bb_scale, 64, 128)
+    tp = lambda d: {k: torch.from_numpy(v) for k, v in d.items()}
+    with torch.no_grad():
+        got = TP.render_rays(torch.from_numpy(rb), tp(pc), tp(pf), torch.from_numpy(bb_center), float(bb_scale), 64, 128)
+    for k, (mean_tol, max_tol) in RENDER_FP32_TOL.items():
+        mean_close(got[k].numpy(), want[k], mean_tol, max_tol, name=k)
