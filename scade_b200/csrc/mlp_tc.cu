@@ -14,14 +14,21 @@
 //     [128 (N) x 64 (K)] fp16 stage, in consumption order, so the producer warp streams them with plain
 //     16 KB cp.async.bulk (TMA) copies through a 4-stage mbarrier ring.  Both row tiles consume every
 //     stage, halving L2->SMEM weight traffic per point.
-//   * warp 0: TMA producer; warp 1: TMEM allocator + single-thread tcgen05.mma issuer;
-//     warps 2..9: prologue/epilogue (thread == point row): positional encoding straight into the
+//   * warp 0: TMA producer; warp 1: TMEM allocator + single-thread tcgen05.mma issuer (warps 2-3 idle; the
+//     control warpgroup hands its registers over with setmaxnreg);
+//     warps 4..11: prologue/epilogue (thread == point row): positional encoding straight into the
 //     swizzled A tile, then per layer TMEM -> registers -> bias + ReLU -> fp16 -> swizzled A tile of the
 //     next layer.  alpha_linear (256->1) and rgb_linear (128->3) are fp32 dot products done in the
 //     epilogues on the un-rounded fp32 activations; softplus(beta=10) is applied before the single
 //     float4 store of (rgb_raw, sigma) per point -- the only HBM write of the kernel.
 //   * skip connection (H:230) and view concat (H:235) are extra K chunks that re-use the encoding chunk;
 //     nothing is concatenated in memory.
+//   * Biases ride on the tensor core: the encoding chunk carries two constant-1 columns (60, 61) and the packed
+//     weights carry fp16 hi/lo halves of the bias in the matching K positions (layers without an encoding K
+//     chunk get one extra K=16 MMA step per tile from a "bias stage"), so the epilogue is LDTM -> cvt.rn.relu.f16x2
+//     -> st.shared only.
+//   * CTAs run as clusters of 2: each CTA bulk-copies half of every weight stage and multicasts it to both, so
+//     L2->SMEM weight traffic per SM is halved again (the v1 kernel was L2-bound at ~6 TB/s during MMA phases).
 #include <cuda_fp16.h>
 
 #include <algorithm>
@@ -43,7 +50,7 @@ constexpr int NUM_STAGES = 4;
 constexpr int MAX_LAYERS = 12;           // D (<= 8) + feature + views
 constexpr int MAX_STAGE_DESCS = 96;
 constexpr int EPI_WARPS = 8;
-constexpr int THREADS = 64 + EPI_WARPS * 32;
+constexpr int THREADS = 128 + EPI_WARPS * 32;   // warpgroup 0: producer, MMA issuer, 2 idle warps; warpgroups 1-2: epilogue
 
 // shared-memory map (relative to a 1024-byte aligned base)
 constexpr int OFF_A = 0;                                 // [TILES][4 chunks]
@@ -60,25 +67,32 @@ struct LayerDesc {
   int n_halves;           // N / 128
   int relu;
   int kind;               // 0 = hidden, 1 = last hidden (also computes alpha), 2 = feature, 3 = views (final)
-  int bias_idx;           // parameter index of the bias
+  int bias_stage;         // 1: an extra stage carries the bias (layer has no encoding K chunk)
 };
 
 struct NetPlan {
   int n_layers;
   int stages_per_pass;
   LayerDesc layers[MAX_LAYERS];
-  const float* bias[MAX_LAYERS];
-  const float* w_alpha; const float* b_alpha;
-  const float* w_rgb; const float* b_rgb;
+};
+
+// small fp32 table behind the stage images in the packed buffer
+struct PackedTail {
+  float4 w_rgb[W / 2];     // (r, g, b, 0) weights of rgb_linear per hidden column
+  float w_alpha[W];
+  float b_alpha, b_rgb[3];
 };
 
 struct StageDesc {
   const float* W; int ld; int col0; int ncols; int dst_col0; int row0; int nrows;
+  const float* bias; int bias_mode;   // 0 none; 1: cols 60/61 <- hi/lo of bias[row0+n]; 2: bias stage (both N halves)
 };
 struct PackPlan {
   int n_stages;
   StageDesc st[MAX_STAGE_DESCS];
+  const float* w_alpha; const float* b_alpha; const float* w_rgb; const float* b_rgb;
 };
+constexpr int ONES_COL = 60;      // encoding-chunk columns 60 and 61 hold 1.0 (bias hi / lo ride on them)
 
 // ---- PTX wrappers -------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -110,6 +124,40 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
                "l"(src), "r"(bytes), "r"(bar)
                : "memory");
 }
+__device__ __forceinline__ void bulk_g2s_mcast(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(dst),
+      "l"(src), "r"(bytes), "r"(bar), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t cluster_id_x() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t num_clusters_x() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%nclusterid.x;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -124,6 +172,11 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
 }
 __device__ __forceinline__ void mma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mma_commit_mcast(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"(mask)
+               : "memory");
 }
 // D[tmem] (+)= A[smem] * B[smem]^T, fp16 operands, fp32 accumulate
 __device__ __forceinline__ void mma_f16_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
@@ -175,6 +228,17 @@ __device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
   __half2 h = __floats2half2_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&h);
 }
+// max(x, 0) -> fp16, two values per instruction
+__device__ __forceinline__ uint32_t pack_relu_f16x2(uint32_t lo_bits, uint32_t hi_bits) {
+  uint32_t d;
+  asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(__uint_as_float(hi_bits)), "f"(__uint_as_float(lo_bits)));
+  return d;
+}
+__device__ __forceinline__ uint32_t pack_plain_f16x2(uint32_t lo_bits, uint32_t hi_bits) {
+  uint32_t d;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(__uint_as_float(hi_bits)), "f"(__uint_as_float(lo_bits)));
+  return d;
+}
 
 // sin/cos of arguments up to ~pi*2^8 for fp16 consumers: two-term Cody-Waite reduction by 2*pi, then the
 // MUFU approximations on [-pi, pi] (abs error ~5e-7, three orders below the fp16 rounding that follows).
@@ -198,12 +262,18 @@ struct FwdArgs {
   int64_t n_pairs;
 };
 
+template <bool kCluster>
 __global__ void __launch_bounds__(THREADS, 1) nerf_mlp_tc_kernel(const __grid_constant__ FwdArgs a,
                                                                  const __grid_constant__ NetPlan plan) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const uint32_t sbase = smem_u32(smem);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t cta_rank = kCluster ? cluster_ctarank() : 0;
+  // work units: a cluster (or a lone CTA) walks `n_steps`; CTA `cta_rank` of the cluster takes pair 2*step + rank
+  const int64_t unit0 = kCluster ? cluster_id_x() : blockIdx.x;
+  const int64_t n_units = kCluster ? num_clusters_x() : gridDim.x;
+  const int64_t n_steps = kCluster ? (a.n_pairs + 1) / 2 : a.n_pairs;
 
   // barriers: full[4], empty[4], acc_full, a_ready, then the TMEM base address slot
   const uint32_t bar_full = sbase + OFF_BAR, bar_empty = bar_full + 8 * NUM_STAGES;
@@ -213,7 +283,7 @@ __global__ void __launch_bounds__(THREADS, 1) nerf_mlp_tc_kernel(const __grid_co
   if (threadIdx.x == 0) {
     for (int s = 0; s < NUM_STAGES; ++s) {
       mbar_init(bar_full + 8 * s, 1);
-      mbar_init(bar_empty + 8 * s, 1);
+      mbar_init(bar_empty + 8 * s, kCluster ? 2 : 1);     // both CTAs' MMA warps release a multicast stage
     }
     mbar_init(bar_acc, 1);
     mbar_init(bar_aready, EPI_WARPS);
@@ -222,77 +292,124 @@ __global__ void __launch_bounds__(THREADS, 1) nerf_mlp_tc_kernel(const __grid_co
   if (warp == 1) tmem_alloc(smem_u32((const void*)tmem_slot), 512);
   tc_fence_before();
   __syncthreads();
+  if (kCluster) cluster_sync_all();        // peers' barriers are initialised before any remote arrive / multicast
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+
+  // register budget: the control warpgroup gives registers to the two epilogue warpgroups.  The pool is what the CTA got
+  // at launch (384 threads x 168 = 64512 registers), so 128*96 + 256*200 = 63488 fits; asking for more blocks forever.
+  if (warp < 4) asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");
+  else asm volatile("setmaxnreg.inc.sync.aligned.u32 200;");
 
   if (warp == 0) {
     // ================= TMA producer: stream the packed weight stages =================
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
-      for (int64_t pair = blockIdx.x; pair < a.n_pairs; pair += gridDim.x) {
+      for (int64_t step = unit0; step < n_steps; step += n_units) {
         const uint8_t* src = a.packed;
         for (int s = 0; s < plan.stages_per_pass; ++s) {
           mbar_wait(bar_empty + 8 * stage, phase ^ 1);
           mbar_expect_tx(bar_full + 8 * stage, STAGE_BYTES);
-          bulk_g2s(sbase + OFF_STAGE + stage * STAGE_BYTES, src, STAGE_BYTES, bar_full + 8 * stage);
+          const uint32_t dst = sbase + OFF_STAGE + stage * STAGE_BYTES;
+          if (kCluster) {
+            const uint32_t half = STAGE_BYTES / 2;
+            bulk_g2s_mcast(dst + cta_rank * half, src + cta_rank * half, half, bar_full + 8 * stage, (uint16_t)3);
+          } else {
+            bulk_g2s(dst, src, STAGE_BYTES, bar_full + 8 * stage);
+          }
           src += STAGE_BYTES;
           if (++stage == NUM_STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    // ================= MMA issuer (one thread) =================
-    if (lane == 0) {
-      uint32_t stage = 0, phase = 0, a_phase = 0;
-      constexpr uint32_t idesc = make_idesc(TILE_M, STAGE_N);
-      for (int64_t pair = blockIdx.x; pair < a.n_pairs; pair += gridDim.x) {
-        for (int l = 0; l < plan.n_layers; ++l) {
-          const LayerDesc& L = plan.layers[l];
-          mbar_wait(bar_aready, a_phase);
-          a_phase ^= 1;
-          tc_fence_after();
-          for (int kc = 0; kc < L.n_k; ++kc) {
-            const int src = L.a_src[kc];
-            for (int nh = 0; nh < L.n_halves; ++nh) {
-              mbar_wait(bar_full + 8 * stage, phase);
-              tc_fence_after();
-              const uint32_t b_addr = sbase + OFF_STAGE + stage * STAGE_BYTES;
+    // ================= MMA issuer =================
+    // The whole warp walks the loops (warp-uniform control flow keeps descriptors in uniform registers);
+    // one elected lane issues the tcgen05 instructions.
+    uint32_t stage = 0, phase = 0, a_phase = 0;
+    constexpr uint32_t idesc = make_idesc(TILE_M, STAGE_N);
+    constexpr uint64_t desc_hi = ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61) | ((uint64_t)1 << 16);
+    for (int64_t step = unit0; step < n_steps; step += n_units) {
+      for (int l = 0; l < plan.n_layers; ++l) {
+        const int n_k = plan.layers[l].n_k, n_halves = plan.layers[l].n_halves, bias_stage = plan.layers[l].bias_stage;
+        int a_src[5];
+#pragma unroll
+        for (int i = 0; i < 5; ++i) a_src[i] = plan.layers[l].a_src[i];
+        mbar_wait(bar_aready, a_phase);
+        a_phase ^= 1;
+        tc_fence_after();
+#pragma unroll 1
+        for (int kc = 0; kc < n_k; ++kc) {
+          int src = a_src[0];
+#pragma unroll
+          for (int i = 1; i < 5; ++i) src = (kc == i) ? a_src[i] : src;
+          const uint32_t a_off = (src == SRC_EMB) ? OFF_EMB : OFF_A + src * CHUNK_BYTES;
+          const uint32_t a_stride = (src == SRC_EMB) ? CHUNK_BYTES : 4 * CHUNK_BYTES;
+#pragma unroll 1
+          for (int nh = 0; nh < n_halves; ++nh) {
+            mbar_wait(bar_full + 8 * stage, phase);
+            tc_fence_after();
+            if (elect_one()) {
+              const uint64_t b_desc = desc_hi | (uint64_t)(((sbase + OFF_STAGE + stage * STAGE_BYTES) & 0x3FFFF) >> 4);
 #pragma unroll
               for (int t = 0; t < TILES; ++t) {
-                const uint32_t a_addr = (src == SRC_EMB) ? sbase + OFF_EMB + t * CHUNK_BYTES
-                                                         : sbase + OFF_A + (t * 4 + src) * CHUNK_BYTES;
+                const uint64_t a_desc = desc_hi | (uint64_t)(((sbase + a_off + t * a_stride) & 0x3FFFF) >> 4);
                 const uint32_t d_addr = tmem_base + t * W + nh * STAGE_N;
 #pragma unroll
-                for (int ks = 0; ks < KCHUNK / 16; ++ks) {
-                  mma_f16_ss(d_addr, make_smem_desc(a_addr + ks * 32), make_smem_desc(b_addr + ks * 32), idesc,
-                             (kc | ks) != 0 ? 1u : 0u);
-                }
+                for (int ks = 0; ks < KCHUNK / 16; ++ks)
+                  mma_f16_ss(d_addr, a_desc + 2 * ks, b_desc + 2 * ks, idesc, (kc | ks) != 0 ? 1u : 0u);
               }
-              mma_commit(bar_empty + 8 * stage);       // frees the weight stage when these MMAs retire
-              if (++stage == NUM_STAGES) { stage = 0; phase ^= 1; }
+              // frees the weight stage (in both CTAs of a cluster) when these MMAs retire
+              if (kCluster) mma_commit_mcast(bar_empty + 8 * stage, (uint16_t)3);
+              else mma_commit(bar_empty + 8 * stage);
             }
+            __syncwarp();
+            if (++stage == NUM_STAGES) { stage = 0; phase ^= 1; }
           }
-          mma_commit(bar_acc);                          // accumulators of this layer complete
         }
+        if (bias_stage) {
+          // bias: A = K-step 3 of the encoding chunk (columns 48..63: zero-weighted encoding + the two 1.0
+          // columns), B = K-step `nh` of the bias stage (hi/lo halves of the bias at positions 12/13)
+          mbar_wait(bar_full + 8 * stage, phase);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint64_t b_desc = desc_hi | (uint64_t)(((sbase + OFF_STAGE + stage * STAGE_BYTES) & 0x3FFFF) >> 4);
+#pragma unroll
+            for (int nh = 0; nh < 2; ++nh)
+#pragma unroll
+              for (int t = 0; t < TILES; ++t) {
+                const uint64_t a_desc = desc_hi | (uint64_t)(((sbase + OFF_EMB + t * CHUNK_BYTES + 3 * 32) & 0x3FFFF) >> 4);
+                mma_f16_ss(tmem_base + t * W + nh * STAGE_N, a_desc, b_desc + 2 * nh, idesc, 1u);
+              }
+            if (kCluster) mma_commit_mcast(bar_empty + 8 * stage, (uint16_t)3);
+            else mma_commit(bar_empty + 8 * stage);
+          }
+          __syncwarp();
+          if (++stage == NUM_STAGES) { stage = 0; phase ^= 1; }
+        }
+        if (elect_one()) mma_commit(bar_acc);           // accumulators of this layer complete
+        __syncwarp();
       }
     }
-  } else {
+  } else if (warp >= 4) {
     // ================= prologue / epilogue warps: thread == point row =================
-    const int ew = warp - 2;
+    const int ew = warp - 4;
     const int tile = ew >> 2;
     const int quarter = warp & 3;                       // TMEM lane quarter this warp may access
     const int row = quarter * 32 + lane;
     uint8_t* a_tile = smem + OFF_A + tile * 4 * CHUNK_BYTES;
     uint8_t* emb_tile = smem + OFF_EMB + tile * CHUNK_BYTES;
     const uint32_t t_lane = tmem_base + ((uint32_t)(quarter * 32) << 16) + tile * W;
+    const PackedTail* tail = reinterpret_cast<const PackedTail*>(a.packed + (size_t)plan.stages_per_pass * STAGE_BYTES);
     uint32_t acc_phase = 0;
 
-    for (int64_t pair = blockIdx.x; pair < a.n_pairs; pair += gridDim.x) {
+    for (int64_t step = unit0; step < n_steps; step += n_units) {
+      const int64_t pair = kCluster ? 2 * step + cta_rank : step;
       const int64_t p_raw = pair * (TILES * TILE_M) + tile * TILE_M + row;
       const bool live = p_raw < a.P;
       const int64_t p = live ? p_raw : a.P - 1;
 
-      // ---- positional encoding -> fp16 encoding chunk (columns: gamma(x), view dir, zeros) ----
+      // ---- positional encoding -> fp16 encoding chunk (columns: gamma(x), view dir, zeros, 1, 1, 0, 0) ----
       {
         float v[64];
 #pragma unroll
@@ -323,9 +440,11 @@ __global__ void __launch_bounds__(THREADS, 1) nerf_mlp_tc_kernel(const __grid_co
         } else {
           const float* x = a.x_embedded + p * a.in_all;
 #pragma unroll
-          for (int i = 0; i < 64; ++i)
+          for (int i = 0; i < ONES_COL; ++i)
             if (i < a.in_all) v[i] = x[i];
         }
+        v[ONES_COL] = 1.0f;
+        v[ONES_COL + 1] = 1.0f;
 #pragma unroll
         for (int piece = 0; piece < 8; ++piece) {
           uint4 q;
@@ -352,36 +471,40 @@ __global__ void __launch_bounds__(THREADS, 1) nerf_mlp_tc_kernel(const __grid_co
 
       float alpha = 0.f;
       for (int l = 0; l < plan.n_layers; ++l) {
-        const LayerDesc& L = plan.layers[l];
+        const int kind = plan.layers[l].kind, relu = plan.layers[l].relu;
         mbar_wait(bar_acc, acc_phase);
         acc_phase ^= 1;
         tc_fence_after();
-        const float* bias = plan.bias[l];
-        if (L.kind != 3) {
-          // hidden / feature layer: 256 columns -> next layer's A chunks
-#pragma unroll 1
+        if (kind != 3) {
+          // hidden / feature layer: 256 accumulator columns (bias already inside) -> next layer's A chunks.
+          // 32-column TMEM loads are double-buffered: the load of chunk c+1 is in flight while chunk c is packed.
+          uint32_t rbuf[2][32];
+          tmem_ld32(t_lane, rbuf[0]);
+#pragma unroll
           for (int c8 = 0; c8 < W / 32; ++c8) {
-            uint32_t r[32];
-            tmem_ld32(t_lane + c8 * 32, r);
+            uint32_t* r = rbuf[c8 & 1];
             tmem_ld_wait();
-            float f[32];
+            if (c8 + 1 < W / 32) tmem_ld32(t_lane + (c8 + 1) * 32, rbuf[(c8 + 1) & 1]);
+            if (kind == 1) {
+              const float* wa = tail->w_alpha + c8 * 32;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              float x = __uint_as_float(r[j]) + __ldg(bias + c8 * 32 + j);
-              f[j] = L.relu ? fmaxf(x, 0.f) : x;
-            }
-            if (L.kind == 1) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) alpha = fmaf(f[j], __ldg(plan.w_alpha + c8 * 32 + j), alpha);   // H:233
+              for (int j = 0; j < 32; ++j) alpha = fmaf(fmaxf(__uint_as_float(r[j]), 0.f), __ldg(wa + j), alpha);   // H:233
             }
             uint8_t* chunk = a_tile + (c8 >> 1) * CHUNK_BYTES;
 #pragma unroll
             for (int pc = 0; pc < 4; ++pc) {
               uint4 q;
-              q.x = pack_f16x2(f[pc * 8 + 0], f[pc * 8 + 1]);
-              q.y = pack_f16x2(f[pc * 8 + 2], f[pc * 8 + 3]);
-              q.z = pack_f16x2(f[pc * 8 + 4], f[pc * 8 + 5]);
-              q.w = pack_f16x2(f[pc * 8 + 6], f[pc * 8 + 7]);
+              if (relu) {
+                q.x = pack_relu_f16x2(r[pc * 8 + 0], r[pc * 8 + 1]);
+                q.y = pack_relu_f16x2(r[pc * 8 + 2], r[pc * 8 + 3]);
+                q.z = pack_relu_f16x2(r[pc * 8 + 4], r[pc * 8 + 5]);
+                q.w = pack_relu_f16x2(r[pc * 8 + 6], r[pc * 8 + 7]);
+              } else {
+                q.x = pack_plain_f16x2(r[pc * 8 + 0], r[pc * 8 + 1]);
+                q.y = pack_plain_f16x2(r[pc * 8 + 2], r[pc * 8 + 3]);
+                q.z = pack_plain_f16x2(r[pc * 8 + 4], r[pc * 8 + 5]);
+                q.w = pack_plain_f16x2(r[pc * 8 + 6], r[pc * 8 + 7]);
+              }
               *reinterpret_cast<uint4*>(chunk + sw128_offset(row, (c8 & 1) * 4 + pc)) = q;
             }
           }
@@ -393,24 +516,25 @@ __global__ void __launch_bounds__(THREADS, 1) nerf_mlp_tc_kernel(const __grid_co
           // views layer (N = 128) + rgb_linear + output                          H:238-242
           float cr = 0.f, cg = 0.f, cb = 0.f;
 #pragma unroll 1
-          for (int c8 = 0; c8 < (W / 2) / 32; ++c8) {
-            uint32_t r[32];
-            tmem_ld32(t_lane + c8 * 32, r);
+          for (int c = 0; c < 2; ++c) {
+            uint32_t r[64];
+            tmem_ld32(t_lane + c * 64, r);
+            tmem_ld32(t_lane + c * 64 + 32, r + 32);
             tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const int col = c8 * 32 + j;
-              float h = fmaxf(__uint_as_float(r[j]) + __ldg(bias + col), 0.f);
-              cr = fmaf(h, __ldg(plan.w_rgb + col), cr);
-              cg = fmaf(h, __ldg(plan.w_rgb + (W / 2) + col), cg);
-              cb = fmaf(h, __ldg(plan.w_rgb + W + col), cb);
+            for (int j = 0; j < 64; ++j) {
+              float h = fmaxf(__uint_as_float(r[j]), 0.f);
+              float4 w = __ldg(tail->w_rgb + c * 64 + j);
+              cr = fmaf(h, w.x, cr);
+              cg = fmaf(h, w.y, cg);
+              cb = fmaf(h, w.z, cb);
             }
           }
           tc_fence_before();
           if (live) {
-            float al = alpha + __ldg(plan.b_alpha);
-            a.out[p_raw] = make_float4(cr + __ldg(plan.b_rgb), cg + __ldg(plan.b_rgb + 1), cb + __ldg(plan.b_rgb + 2),
-                                       softplus_beta10(al));
+            float al = alpha + __ldg(&tail->b_alpha);
+            a.out[p_raw] = make_float4(cr + __ldg(&tail->b_rgb[0]), cg + __ldg(&tail->b_rgb[1]),
+                                       cb + __ldg(&tail->b_rgb[2]), softplus_beta10(al));
           }
         }
       }
@@ -419,6 +543,7 @@ __global__ void __launch_bounds__(THREADS, 1) nerf_mlp_tc_kernel(const __grid_co
 
   tc_fence_before();
   __syncthreads();
+  if (kCluster) cluster_sync_all();        // no CTA leaves while its peer may still multicast into it
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
@@ -426,16 +551,48 @@ __global__ void __launch_bounds__(THREADS, 1) nerf_mlp_tc_kernel(const __grid_co
 }
 
 // ---- weight packing ---------------------------------------------------------------------------------
+__device__ __forceinline__ void split_f16(float b, __half* hi, __half* lo) {
+  *hi = __float2half_rn(b);
+  *lo = __float2half_rn(b - __half2float(*hi));
+}
+
 __global__ void pack_kernel(const __grid_constant__ PackPlan plan, uint8_t* __restrict__ out) {
+  if ((int)blockIdx.x == plan.n_stages) {
+    // fp32 tail: rgb_linear as (r,g,b,0) per hidden column, alpha_linear, head biases
+    PackedTail* tail = reinterpret_cast<PackedTail*>(out + (size_t)plan.n_stages * STAGE_BYTES);
+    for (int k = threadIdx.x; k < W / 2; k += blockDim.x)
+      tail->w_rgb[k] = make_float4(plan.w_rgb[k], plan.w_rgb[W / 2 + k], plan.w_rgb[W + k], 0.f);
+    for (int k = threadIdx.x; k < W; k += blockDim.x) tail->w_alpha[k] = plan.w_alpha[k];
+    if (threadIdx.x == 0) {
+      tail->b_alpha = plan.b_alpha[0];
+      tail->b_rgb[0] = plan.b_rgb[0]; tail->b_rgb[1] = plan.b_rgb[1]; tail->b_rgb[2] = plan.b_rgb[2];
+    }
+    return;
+  }
   const StageDesc& sd = plan.st[blockIdx.x];
   __half* dst = reinterpret_cast<__half*>(out + (size_t)blockIdx.x * STAGE_BYTES);
   for (int idx = threadIdx.x; idx < STAGE_N * KCHUNK; idx += blockDim.x) {
     int n = idx / KCHUNK, k = idx % KCHUNK;
-    float v = 0.f;
-    int sc = k - sd.dst_col0;
-    if (n < sd.nrows && sc >= 0 && sc < sd.ncols) v = sd.W[(int64_t)(sd.row0 + n) * sd.ld + sd.col0 + sc];
+    __half hv = __float2half_rn(0.f);
+    if (sd.bias_mode == 2) {
+      // K-step j (columns 16j..16j+15) feeds N half j; positions 12/13 meet the encoding chunk's 1.0 columns
+      int j = k >> 4, i = k & 15;
+      if (j < 2 && (i == 12 || i == 13)) {
+        __half hi, lo;
+        split_f16(sd.bias[j * STAGE_N + n], &hi, &lo);
+        hv = (i == 12) ? hi : lo;
+      }
+    } else {
+      int sc = k - sd.dst_col0;
+      if (n < sd.nrows && sc >= 0 && sc < sd.ncols) hv = __float2half_rn(sd.W[(int64_t)(sd.row0 + n) * sd.ld + sd.col0 + sc]);
+      if (sd.bias_mode == 1 && n < sd.nrows && (k == ONES_COL || k == ONES_COL + 1)) {
+        __half hi, lo;
+        split_f16(sd.bias[sd.row0 + n], &hi, &lo);
+        hv = (k == ONES_COL) ? hi : lo;
+      }
+    }
     uint32_t off = sw128_offset(n, k >> 3) + (k & 7) * 2;
-    dst[off >> 1] = __float2half_rn(v);
+    dst[off >> 1] = hv;
   }
 }
 
@@ -445,48 +602,51 @@ static void build_plans(const scade_net& net, NetPlan* np, PackPlan* pp) {
   NetDims nd(d);
   NetPlan P{};
   PackPlan Q{};
-  auto add_stage = [&](const float* Wt, int ld, int col0, int ncols, int dst_col0, int row0, int nrows) {
-    StageDesc s{Wt, ld, col0, ncols, dst_col0, row0, nrows};
+  auto add_stage = [&](const float* Wt, int ld, int col0, int ncols, int dst_col0, int row0, int nrows,
+                       const float* bias, int bias_mode) {
+    StageDesc s{Wt, ld, col0, ncols, dst_col0, row0, nrows, bias, bias_mode};
     Q.st[Q.n_stages++] = s;
   };
   auto add_layer = [&](const float* Wt, int fan_in, bool with_emb, int emb_col0, int emb_ncols, int emb_dst, int h_col0,
-                       bool with_h, int n_out, int relu, int kind, int bias_idx) {
+                       bool with_h, int n_out, int relu, int kind, const float* bias) {
     LayerDesc L{};
     L.n_halves = n_out / STAGE_N;
-    L.relu = relu; L.kind = kind; L.bias_idx = bias_idx;
+    L.relu = relu; L.kind = kind;
+    L.bias_stage = with_emb ? 0 : 1;
     int nk = 0;
     if (with_emb) L.a_src[nk++] = SRC_EMB;
     if (with_h) for (int c = 0; c < 4; ++c) L.a_src[nk++] = c;
     L.n_k = nk;
     for (int kc = 0; kc < nk; ++kc)
       for (int nh = 0; nh < L.n_halves; ++nh) {
-        if (L.a_src[kc] == SRC_EMB) add_stage(Wt, fan_in, emb_col0, emb_ncols, emb_dst, nh * STAGE_N, STAGE_N);
-        else add_stage(Wt, fan_in, h_col0 + 64 * L.a_src[kc], 64, 0, nh * STAGE_N, STAGE_N);
+        if (L.a_src[kc] == SRC_EMB) add_stage(Wt, fan_in, emb_col0, emb_ncols, emb_dst, nh * STAGE_N, STAGE_N, bias, 1);
+        else add_stage(Wt, fan_in, h_col0 + 64 * L.a_src[kc], 64, 0, nh * STAGE_N, STAGE_N, nullptr, 0);
       }
-    P.bias[P.n_layers] = net.params[bias_idx];
+    if (L.bias_stage) add_stage(nullptr, 0, 0, 0, 0, 0, 0, bias, 2);
     P.layers[P.n_layers++] = L;
   };
   for (int i = 0; i < d.D; ++i) {
     const float* Wt = net.params[2 * i];
+    const float* b = net.params[2 * i + 1];
     int kind = (i == d.D - 1) ? 1 : 0;
-    if (i == 0) add_layer(Wt, nd.in_ch, true, 0, nd.in_ch, 0, 0, false, W, 1, kind, 1);
-    else if (i - 1 == d.skip) add_layer(Wt, nd.in_ch + W, true, 0, nd.in_ch, 0, nd.in_ch, true, W, 1, kind, 2 * i + 1);
-    else add_layer(Wt, W, false, 0, 0, 0, 0, true, W, 1, kind, 2 * i + 1);
+    if (i == 0) add_layer(Wt, nd.in_ch, true, 0, nd.in_ch, 0, 0, false, W, 1, kind, b);
+    else if (i - 1 == d.skip) add_layer(Wt, nd.in_ch + W, true, 0, nd.in_ch, 0, nd.in_ch, true, W, 1, kind, b);
+    else add_layer(Wt, W, false, 0, 0, 0, 0, true, W, 1, kind, b);
   }
   const int pv = 2 * d.D;
-  add_layer(net.params[pv + 2], W, false, 0, 0, 0, 0, true, W, 0, 2, pv + 3);                          // feature_linear
-  add_layer(net.params[pv], W + nd.in_views, true, W, nd.in_views, nd.in_ch, 0, true, W / 2, 1, 3, pv + 1);   // views
+  add_layer(net.params[pv + 2], W, false, 0, 0, 0, 0, true, W, 0, 2, net.params[pv + 3]);                        // feature_linear
+  add_layer(net.params[pv], W + nd.in_views, true, W, nd.in_views, nd.in_ch, 0, true, W / 2, 1, 3, net.params[pv + 1]);   // views
   P.stages_per_pass = Q.n_stages;
-  P.w_alpha = net.params[pv + 4]; P.b_alpha = net.params[pv + 5];
-  P.w_rgb = net.params[pv + 6]; P.b_rgb = net.params[pv + 7];
+  Q.w_alpha = net.params[pv + 4]; Q.b_alpha = net.params[pv + 5];
+  Q.w_rgb = net.params[pv + 6]; Q.b_rgb = net.params[pv + 7];
   if (np) *np = P;
   if (pp) *pp = Q;
 }
 
 static int count_stages(const scade_net_desc& d) {
-  int n = 2;                                   // layer 0: 1 K chunk x 2 halves
-  for (int i = 1; i < d.D; ++i) n += ((i - 1 == d.skip) ? 5 : 4) * 2;
-  n += 8;                                      // feature
+  int n = 2;                                   // layer 0: 1 K chunk x 2 halves (bias inside)
+  for (int i = 1; i < d.D; ++i) n += (i - 1 == d.skip) ? 10 : 9;     // 4 K chunks x 2 halves + bias stage, or 5 x 2
+  n += 9;                                      // feature + bias stage
   n += 5;                                      // views (N = 128)
   return n;
 }
@@ -495,16 +655,18 @@ static int count_stages(const scade_net_desc& d) {
 
 bool mlp_tc_supported(const scade_net_desc& d) {
   NetDims nd(d);
-  return d.W == tc::W && d.D >= 2 && d.D <= 8 && nd.in_all <= 64 && d.multires <= 9 && d.multires_views == 0 && d.skip != d.D - 1 &&
-         tc::count_stages(d) <= tc::MAX_STAGE_DESCS;
+  return d.W == tc::W && d.D >= 2 && d.D <= 8 && nd.in_all <= tc::ONES_COL && d.multires <= 9 && d.multires_views == 0 &&
+         d.skip != d.D - 1 && tc::count_stages(d) <= tc::MAX_STAGE_DESCS;
 }
 
-size_t mlp_tc_packed_bytes(const scade_net_desc& d) { return (size_t)tc::count_stages(d) * tc::STAGE_BYTES; }
+size_t mlp_tc_packed_bytes(const scade_net_desc& d) {
+  return (size_t)tc::count_stages(d) * tc::STAGE_BYTES + align_up(sizeof(tc::PackedTail));
+}
 
 int mlp_tc_pack(const scade_net& net, void* packed_out, cudaStream_t st) {
   tc::PackPlan pp;
   tc::build_plans(net, nullptr, &pp);
-  tc::pack_kernel<<<pp.n_stages, 256, 0, st>>>(pp, reinterpret_cast<uint8_t*>(packed_out));
+  tc::pack_kernel<<<pp.n_stages + 1, 256, 0, st>>>(pp, reinterpret_cast<uint8_t*>(packed_out));
   SCADE_LAUNCH_CHECK();
   return SCADE_OK;
 }
@@ -519,9 +681,14 @@ int mlp_tc_forward(const scade_net& net, const float* rays, int ray_stride, cons
     set_error("SCADE_PREC_TC_F16 forward does not stash activations for backward in this version");
     return SCADE_ERR_UNSUPPORTED;
   }
+  static const bool use_cluster = []() {
+    const char* e = getenv("SCADE_TC_CLUSTER");
+    return !(e && e[0] == '0');
+  }();
   static bool attr_set = false;
   if (!attr_set) {
-    SCADE_CUDA(cudaFuncSetAttribute(tc::nerf_mlp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
+    SCADE_CUDA(cudaFuncSetAttribute(tc::nerf_mlp_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
+    SCADE_CUDA(cudaFuncSetAttribute(tc::nerf_mlp_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
     attr_set = true;
   }
   tc::NetPlan plan;
@@ -537,8 +704,23 @@ int mlp_tc_forward(const scade_net& net, const float* rays, int ray_stride, cons
   a.multires = net.desc.multires; a.multires_views = net.desc.multires_views;
   a.out = reinterpret_cast<float4*>(raw_out);
   a.n_pairs = ceil_div<int64_t>(a.P, tc::TILES * tc::TILE_M);
-  int grid = (int)std::min<int64_t>(a.n_pairs, num_sms());
-  tc::nerf_mlp_tc_kernel<<<grid, tc::THREADS, tc::SMEM_BYTES, st>>>(a, plan);
+  if (use_cluster) {
+    int64_t n_steps = (a.n_pairs + 1) / 2;
+    int clusters = (int)std::min<int64_t>(n_steps, num_sms() / 2);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(2 * clusters);
+    cfg.blockDim = dim3(tc::THREADS);
+    cfg.dynamicSmemBytes = tc::SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    SCADE_CUDA(cudaLaunchKernelEx(&cfg, tc::nerf_mlp_tc_kernel<true>, a, plan));
+  } else {
+    int grid = (int)std::min<int64_t>(a.n_pairs, num_sms());
+    tc::nerf_mlp_tc_kernel<false><<<grid, tc::THREADS, tc::SMEM_BYTES, st>>>(a, plan);
+  }
   SCADE_LAUNCH_CHECK();
   return SCADE_OK;
 }
