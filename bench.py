@@ -290,6 +290,85 @@ def run_gpu(args):
         dist.destroy_process_group()
 
 
+def run_train(args):
+    """BASELINE config 3: train step on 4096 rays (global), 64 coarse + 128 importance, K=20 hypotheses:
+    forward + losses + backward + ONE NCCL all-reduce of the flat gradient buffer + Adam (RS:954-997).
+    Strong scaling: the 4096 rays of the step are split across ranks."""
+    import torch
+    import torch.distributed as dist
+    from scade_b200 import nerf_helpers as NH, render as R_, synthetic as syn
+    from scade_b200 import _lib
+    from scade_b200.dist import shard_range, sharded_train_step
+    from tests.golden.generate_goldens import net_pair
+    rank, world, local = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+    N, Nc, Nf, K = 4096, 64, 128, 20
+    pc, pf = net_pair(NET_D, NET_W)
+    nets = []
+    for p in (pc, pf):
+        net = NH.NeRF(D=NET_D, W=NET_W, input_ch=57, input_ch_views=3, output_ch=5, skips=[4], use_viewdirs=True, precision="fp32")
+        net.load_state_dict({k: torch.from_numpy(v) for k, v in p.items()})
+        nets.append(net.to(dev))
+    bb_center, bb_scale = syn.bounding_box()
+    qf = R_.NetworkQuery(NH.get_embedder(9, 0)[0], NH.get_embedder(0, 0)[0], bb_center, bb_scale, precision="fp32")
+    kw = dict(network_fn=nets[0], network_query_fn=qf, N_samples=Nc, embedded_cam=torch.tensor((), device=dev), perturb=1.0,
+              N_importance=Nf, network_fine=nets[1], raw_noise_std=0.0)
+    opt = torch.optim.Adam([p for n in nets for p in n.parameters()], lr=5e-4, betas=(0.9, 0.999))
+    scale = torch.ones(1, device=dev, requires_grad=True)
+    shift = torch.zeros(1, device=dev, requires_grad=True)
+    opt_ss = torch.optim.Adam([scale, shift], lr=1e-6)
+    lo, hi = shard_range(N, rank, world)
+    to = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    rb = to(syn.make_ray_batch(N, seed=80)[lo:hi])
+    target_s, target_h = syn.make_train_targets(N, K=K, seed=82)
+    target_s, target_h = to(target_s[lo:hi]), to(target_h[:, lo:hi])
+
+    def step():
+        opt.zero_grad(set_to_none=False)
+        opt_ss.zero_grad()
+        losses = sharded_train_step(rb, target_s, target_h, scale, shift, kw, n_global=N)
+        opt.step()
+        opt_ss.step()
+        return losses
+    for _ in range(max(args.warmup, 3)):
+        step()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    l0 = lib.scade_kernel_launch_count()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(args.steps):
+        losses = step()
+    e.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = torch.tensor([s.elapsed_time(e)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        flop_step = N * (Nc + Nc + Nf) * 3464448          # SURVEY §8(d): fwd + dgrad + wgrad per evaluation
+        burst, sustained, _, src = load_peaks()
+        sec = float(ms) * 1e-3 / args.steps
+        print(json.dumps({
+            "metric": "train rays/sec (4096 rays, 64c+128f, K=20, fwd+loss+bwd+allreduce+Adam)", "value": N / sec, "unit": "rays/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": sec * 1e3, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "BASELINE config 3 train step", "global_rays": N, "precision": "fp32 FFMA GEMMs (fwd+bwd)",
+                       "collective": "1 NCCL all-reduce / step, flat fp32 buffer 4.72 MB"},
+            "gpu_launches": int(lib.scade_kernel_launch_count() - l0), "loss": float(losses["loss"]),
+            "roofline": {"bound": "tensor", "achieved": flop_step / sec / 1e12, "peak": sustained, "unit": "TFLOP/s",
+                         "frac": flop_step / sec / 1e12 / sustained, "peak_source": f"{src} bf16 sustained", "traffic": None}}), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -298,9 +377,13 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default="tc_f16", choices=["tc_f16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="render", choices=["render", "train"],
+                    help="render = BASELINE metric (default); train = config 3 (4096 rays, 64c+128f, K=20, fwd+loss+bwd+allreduce+Adam)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "train":
+        run_train(args)
     else:
         run_gpu(args)
 

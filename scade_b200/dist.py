@@ -1,0 +1,139 @@
+"""Ray-sharded multi-GPU execution: one process per GPU, torch.distributed for the plumbing.
+
+The reference scales with nn.DataParallel (RS:438,455): one process, weights re-broadcast and activations
+scattered/gathered through GPU 0 on every forward.  Rays are independent, so here every rank
+keeps resident weights and renders / differentiates its own contiguous slice of the ray list:
+
+  * render: no data-path collective; one all_gather of the finished per-ray outputs (<= 32 B/ray) at the end;
+  * train : local losses are normalised by the GLOBAL ray count, so the sum over ranks of the local gradients
+            equals the single-GPU gradient; ONE all-reduce per step over a flat fp32 buffer holding the gradients
+            of both networks, d_scale, d_shift and the three loss partial sums (4.72 MB for 8x256 nets).
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+
+def shard_range(n: int, rank: int, world: int):
+    """Contiguous, balanced slice [lo, hi) of n items for `rank` of `world` (first n % world ranks get one more)."""
+    if world <= 0 or not (0 <= rank < world):
+        raise ValueError(f"bad rank/world {rank}/{world}")
+    base, rem = divmod(n, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def _world(group=None):
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(group), dist.get_world_size(group)
+    return 0, 1
+
+
+class FlatAllReduce:
+    """Packs tensors into one flat fp32 buffer, all-reduces it once (sum) and copies the results back.
+    Tensors may be None (skipped).  Works with any backend (nccl on GPUs, gloo in the CPU tests)."""
+
+    def __init__(self, tensors):
+        self.tensors = [t for t in tensors if t is not None]
+        self.numel = sum(t.numel() for t in self.tensors)
+        ref = self.tensors[0]
+        self.flat = torch.empty(self.numel, dtype=torch.float32, device=ref.device)
+
+    def pack(self):
+        off = 0
+        for t in self.tensors:
+            n = t.numel()
+            self.flat[off:off + n].copy_(t.reshape(-1))
+            off += n
+        return self.flat
+
+    def unpack(self):
+        off = 0
+        for t in self.tensors:
+            n = t.numel()
+            t.copy_(self.flat[off:off + n].view_as(t))
+            off += n
+
+    def all_reduce(self, group=None):
+        self.pack()
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
+        self.unpack()
+        return self.flat
+
+
+def sharded_train_step(ray_batch, target_s, target_h, scale, shift, render_kwargs, n_global=None,
+                       space_carving_weight=0.007, threshold=0.0, mask=None, t_rand=None, u_coarse=None, u_fine=None,
+                       group=None):
+    """One SCADE training step (RS:954-985) on this rank's ray shard, followed by the single gradient all-reduce.
+
+    ray_batch [n_local,11], target_s [n_local,3], target_h [K,n_local,1] are this rank's slices of the step's
+    N_rand rays (all from one image, same scale/shift on every rank, RS:945-952).  After the call every rank holds
+    the global gradient in ``.grad`` of the network parameters / scale / shift, exactly as after ``loss.backward()``
+    on one GPU.  Returns a dict of GLOBAL losses (tensors)."""
+    from . import nerf_helpers as NH
+    from . import render as R_
+    rank, world = _world(group)
+    n_local = ray_batch.shape[0]
+    n_global = int(n_global if n_global is not None else n_local * world)
+    th = target_h * scale + shift                                                       # RS:954
+    ret = R_.render_rays(ray_batch, True, cached_u=u_fine, t_rand=t_rand, u_coarse=u_coarse, retraw=False, **render_kwargs)
+    # local sums divided by the global count: sum over ranks == the single-GPU mean (H:11, H:125-126)
+    img_loss = F_img2mse(ret["rgb_map"], target_s, n_global * 3)
+    img_loss0 = F_img2mse(ret["rgb0"], target_s, n_global * 3)
+    sc = NH.compute_space_carving_loss(ret["pred_hyp"], th, is_joint=False, mask=mask, threshold=threshold) \
+        * (float(n_local) / float(n_global))
+    loss = img_loss + space_carving_weight * sc + img_loss0                             # RS:976,983
+    loss.backward()                                                                     # RS:985
+    nets = [R_._unwrap(render_kwargs["network_fn"]), R_._unwrap(render_kwargs["network_fine"] or render_kwargs["network_fn"])]
+    params = [p for net in dict.fromkeys(nets) for p in net.parameters() if p.requires_grad]
+    for p in params:
+        if p.grad is None:
+            p.grad = torch.zeros_like(p)
+    extras = [t.grad for t in (scale, shift) if torch.is_tensor(t) and t.requires_grad and t.grad is not None]
+    losses = torch.stack([img_loss.detach(), sc.detach(), img_loss0.detach()])
+    FlatAllReduce([p.grad for p in params] + extras + [losses]).all_reduce(group)
+    return {"img_loss": losses[0], "space_carving": losses[1], "img_loss0": losses[2],
+            "loss": losses[0] + space_carving_weight * losses[1] + losses[2]}
+
+
+def F_img2mse(x, y, denominator):
+    from . import functional as F_
+    return F_.img2mse(x, y, denominator)
+
+
+def render_image_sharded(H, W, intrinsic, c2w, near, far, render_kwargs, chunk=1024 * 16, keys=("rgb_map", "depth_map", "acc_map"),
+                         group=None, gather=True, device=None):
+    """Full-image render (RS:106-108,147) with the pixel list split across ranks.  Every rank builds the rays of its
+    own pixel range on the device (no full-image get_rays + scatter), renders them in `chunk`-ray pieces and, if
+    `gather`, all ranks end with the [H,W,...] maps."""
+    from . import functional as F_
+    from . import render as R_
+    rank, world = _world(group)
+    device = device or torch.device("cuda", torch.cuda.current_device())
+    n = H * W
+    lo, hi = shard_range(n, rank, world)
+    rays = F_.camera_ray_batch(H, W, intrinsic, c2w, near, far, pix0=lo, n=hi - lo, device=device)
+    kw = {k: v for k, v in render_kwargs.items() if k not in ("near", "far", "ndc", "use_viewdirs")}
+    with torch.no_grad():
+        ret = R_.batchify_rays(rays, chunk, True, **kw)
+    out = {}
+    for k in keys:
+        local = ret[k].reshape(hi - lo, -1)
+        if world > 1 and gather:
+            width = local.shape[1]
+            per = (n + world - 1) // world
+            pad = torch.zeros((per, width), dtype=local.dtype, device=local.device)
+            pad[:hi - lo] = local
+            full = torch.empty((world * per, width), dtype=local.dtype, device=local.device)
+            dist.all_gather_into_tensor(full, pad, group=group)
+            pieces = []
+            for r in range(world):
+                a, b = shard_range(n, r, world)
+                pieces.append(full[r * per:r * per + (b - a)])
+            local = torch.cat(pieces, 0)
+            out[k] = local.reshape(H, W, -1).squeeze(-1)
+        else:
+            out[k] = local.squeeze(-1)
+    return out
