@@ -67,7 +67,8 @@ struct LayerDesc {
   int n_halves;           // N / 128
   int relu;
   int kind;               // 0 = hidden, 1 = last hidden (also computes alpha), 2 = feature, 3 = views (final)
-  int bias_stage;         // 1: an extra stage carries the bias (layer has no encoding K chunk)
+  int bias_stage;         // 1: extra stages carry the bias (layer has no encoding K chunk)
+  int n_out;              // output width (256, or 128 for the views layer)
 };
 
 struct NetPlan {
@@ -148,6 +149,51 @@ __device__ __forceinline__ uint32_t num_clusters_x() {
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t local_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// wait with cluster-scope acquire (the barrier receives arrivals from the peer CTA)
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAITC_LOOP:\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra WAITC_DONE;\n\t"
+      "bra WAITC_LOOP;\n\t"
+      "WAITC_DONE:\n\t"
+      "}" ::"r"(bar), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// arrives on the barrier at the same offset in every CTA of `mask` once all prior MMAs of this thread retired
+__device__ __forceinline__ void mma_commit_pair(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"(mask)
+               : "memory");
+}
+// M=256 over the SM pair: each CTA contributes its 128 rows of A and its half (N/2 rows) of B
+__device__ __forceinline__ void mma_f16_ss_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                                uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
   asm volatile(
@@ -159,6 +205,7 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -262,37 +309,47 @@ struct FwdArgs {
   int64_t n_pairs;
 };
 
-template <bool kCluster>
+// kPair == false: every CTA is independent (cta_group::1, M=128 MMAs, both N halves of every weight block).
+// kPair == true : clusters of 2 CTAs on an SM pair; the leader issues tcgen05.mma.cta_group::2 (M=256 = 128 rows of each
+//                 CTA, N=256); each CTA streams only ITS half (128 N rows) of every weight block, so the B operand read
+//                 per SM and the weight bytes per SM are halved (the single-CTA form is shared-memory-bandwidth bound:
+//                 4 KB of A + 4 KB of B per 64-cycle instruction = 128 B/cycle).
+template <bool kPair>
 __global__ void __launch_bounds__(THREADS, 1) nerf_mlp_tc_kernel(const __grid_constant__ FwdArgs a,
                                                                  const __grid_constant__ NetPlan plan) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const uint32_t sbase = smem_u32(smem);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t cta_rank = kCluster ? cluster_ctarank() : 0;
+  const uint32_t cta_rank = kPair ? cluster_ctarank() : 0;
   // work units: a cluster (or a lone CTA) walks `n_steps`; CTA `cta_rank` of the cluster takes pair 2*step + rank
-  const int64_t unit0 = kCluster ? cluster_id_x() : blockIdx.x;
-  const int64_t n_units = kCluster ? num_clusters_x() : gridDim.x;
-  const int64_t n_steps = kCluster ? (a.n_pairs + 1) / 2 : a.n_pairs;
+  const int64_t unit0 = kPair ? cluster_id_x() : blockIdx.x;
+  const int64_t n_units = kPair ? num_clusters_x() : gridDim.x;
+  const int64_t n_steps = kPair ? (a.n_pairs + 1) / 2 : a.n_pairs;
 
-  // barriers: full[4], empty[4], acc_full, a_ready, then the TMEM base address slot
+  // barriers: full[4], empty[4], acc_full, a_ready, peer_full[4] (leader: the peer's stage has landed), TMEM base slot
   const uint32_t bar_full = sbase + OFF_BAR, bar_empty = bar_full + 8 * NUM_STAGES;
   const uint32_t bar_acc = bar_empty + 8 * NUM_STAGES, bar_aready = bar_acc + 8;
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + OFF_BAR + 8 * (2 * NUM_STAGES + 2));
+  const uint32_t bar_peer_full = bar_aready + 8;
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + OFF_BAR + 8 * (3 * NUM_STAGES + 2));
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < NUM_STAGES; ++s) {
       mbar_init(bar_full + 8 * s, 1);
-      mbar_init(bar_empty + 8 * s, kCluster ? 2 : 1);     // both CTAs' MMA warps release a multicast stage
+      mbar_init(bar_empty + 8 * s, 1);
+      mbar_init(bar_peer_full + 8 * s, 1);
     }
     mbar_init(bar_acc, 1);
-    mbar_init(bar_aready, EPI_WARPS);
+    mbar_init(bar_aready, kPair ? 2 * EPI_WARPS : EPI_WARPS);     // pair: the peer's epilogue warps arrive remotely
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(smem_u32((const void*)tmem_slot), 512);
+  if (warp == 1) {
+    if (kPair) tmem_alloc_pair(smem_u32((const void*)tmem_slot), 512);
+    else tmem_alloc(smem_u32((const void*)tmem_slot), 512);
+  }
   tc_fence_before();
   __syncthreads();
-  if (kCluster) cluster_sync_all();        // peers' barriers are initialised before any remote arrive / multicast
+  if (kPair) cluster_sync_all();           // peers' barriers are initialised before any remote arrive / multicast commit
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -303,21 +360,28 @@ __global__ void __launch_bounds__(THREADS, 1) nerf_mlp_tc_kernel(const __grid_co
 
   if (warp == 0) {
     // ================= TMA producer: stream the packed weight stages =================
+    // pair mode: stages alternate (CTA 0's half, CTA 1's half); each CTA fetches only its own
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
+      const int s0 = kPair ? (int)cta_rank : 0, ds = kPair ? 2 : 1;
       for (int64_t step = unit0; step < n_steps; step += n_units) {
-        const uint8_t* src = a.packed;
-        for (int s = 0; s < plan.stages_per_pass; ++s) {
+        for (int s = s0; s < plan.stages_per_pass; s += ds) {
           mbar_wait(bar_empty + 8 * stage, phase ^ 1);
           mbar_expect_tx(bar_full + 8 * stage, STAGE_BYTES);
-          const uint32_t dst = sbase + OFF_STAGE + stage * STAGE_BYTES;
-          if (kCluster) {
-            const uint32_t half = STAGE_BYTES / 2;
-            bulk_g2s_mcast(dst + cta_rank * half, src + cta_rank * half, half, bar_full + 8 * stage, (uint16_t)3);
-          } else {
-            bulk_g2s(dst, src, STAGE_BYTES, bar_full + 8 * stage);
-          }
-          src += STAGE_BYTES;
+          bulk_g2s(sbase + OFF_STAGE + stage * STAGE_BYTES, a.packed + (size_t)s * STAGE_BYTES, STAGE_BYTES, bar_full + 8 * stage);
+          if (++stage == NUM_STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 2) {
+    // ================= relay (pair mode, non-leader CTA): tell the leader that this CTA's stage has landed =========
+    if (kPair && cta_rank != 0 && lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      const uint32_t leader_peer_full = map_to_cta(bar_peer_full, 0);
+      for (int64_t step = unit0; step < n_steps; step += n_units) {
+        for (int s = 1; s < plan.stages_per_pass; s += 2) {
+          mbar_wait(bar_full + 8 * stage, phase);
+          mbar_arrive_remote(leader_peer_full + 8 * stage);
           if (++stage == NUM_STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -325,70 +389,96 @@ __global__ void __launch_bounds__(THREADS, 1) nerf_mlp_tc_kernel(const __grid_co
   } else if (warp == 1) {
     // ================= MMA issuer =================
     // The whole warp walks the loops (warp-uniform control flow keeps descriptors in uniform registers);
-    // one elected lane issues the tcgen05 instructions.
+    // one elected lane issues the tcgen05 instructions.  In pair mode only the leader CTA issues.
     uint32_t stage = 0, phase = 0, a_phase = 0;
-    constexpr uint32_t idesc = make_idesc(TILE_M, STAGE_N);
     constexpr uint64_t desc_hi = ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61) | ((uint64_t)1 << 16);
-    for (int64_t step = unit0; step < n_steps; step += n_units) {
-      for (int l = 0; l < plan.n_layers; ++l) {
-        const int n_k = plan.layers[l].n_k, n_halves = plan.layers[l].n_halves, bias_stage = plan.layers[l].bias_stage;
-        int a_src[5];
+    if (!kPair || cta_rank == 0) {
+      for (int64_t step = unit0; step < n_steps; step += n_units) {
+        for (int l = 0; l < plan.n_layers; ++l) {
+          const int n_k = plan.layers[l].n_k, n_halves = plan.layers[l].n_halves, bias_stage = plan.layers[l].bias_stage;
+          const uint32_t idesc = kPair ? make_idesc(2 * TILE_M, plan.layers[l].n_out) : make_idesc(TILE_M, STAGE_N);
+          int a_src[5];
 #pragma unroll
-        for (int i = 0; i < 5; ++i) a_src[i] = plan.layers[l].a_src[i];
-        mbar_wait(bar_aready, a_phase);
-        a_phase ^= 1;
-        tc_fence_after();
-#pragma unroll 1
-        for (int kc = 0; kc < n_k; ++kc) {
-          int src = a_src[0];
-#pragma unroll
-          for (int i = 1; i < 5; ++i) src = (kc == i) ? a_src[i] : src;
-          const uint32_t a_off = (src == SRC_EMB) ? OFF_EMB : OFF_A + src * CHUNK_BYTES;
-          const uint32_t a_stride = (src == SRC_EMB) ? CHUNK_BYTES : 4 * CHUNK_BYTES;
-#pragma unroll 1
-          for (int nh = 0; nh < n_halves; ++nh) {
-            mbar_wait(bar_full + 8 * stage, phase);
-            tc_fence_after();
-            if (elect_one()) {
-              const uint64_t b_desc = desc_hi | (uint64_t)(((sbase + OFF_STAGE + stage * STAGE_BYTES) & 0x3FFFF) >> 4);
-#pragma unroll
-              for (int t = 0; t < TILES; ++t) {
-                const uint64_t a_desc = desc_hi | (uint64_t)(((sbase + a_off + t * a_stride) & 0x3FFFF) >> 4);
-                const uint32_t d_addr = tmem_base + t * W + nh * STAGE_N;
-#pragma unroll
-                for (int ks = 0; ks < KCHUNK / 16; ++ks)
-                  mma_f16_ss(d_addr, a_desc + 2 * ks, b_desc + 2 * ks, idesc, (kc | ks) != 0 ? 1u : 0u);
-              }
-              // frees the weight stage (in both CTAs of a cluster) when these MMAs retire
-              if (kCluster) mma_commit_mcast(bar_empty + 8 * stage, (uint16_t)3);
-              else mma_commit(bar_empty + 8 * stage);
-            }
-            __syncwarp();
-            if (++stage == NUM_STAGES) { stage = 0; phase ^= 1; }
-          }
-        }
-        if (bias_stage) {
-          // bias: A = K-step 3 of the encoding chunk (columns 48..63: zero-weighted encoding + the two 1.0
-          // columns), B = K-step `nh` of the bias stage (hi/lo halves of the bias at positions 12/13)
-          mbar_wait(bar_full + 8 * stage, phase);
+          for (int i = 0; i < 5; ++i) a_src[i] = plan.layers[l].a_src[i];
+          if (kPair) mbar_wait_cluster(bar_aready, a_phase); else mbar_wait(bar_aready, a_phase);
+          a_phase ^= 1;
           tc_fence_after();
-          if (elect_one()) {
-            const uint64_t b_desc = desc_hi | (uint64_t)(((sbase + OFF_STAGE + stage * STAGE_BYTES) & 0x3FFFF) >> 4);
+#pragma unroll 1
+          for (int kc = 0; kc < n_k; ++kc) {
+            int src = a_src[0];
 #pragma unroll
-            for (int nh = 0; nh < 2; ++nh)
+            for (int i = 1; i < 5; ++i) src = (kc == i) ? a_src[i] : src;
+            const uint32_t a_off = (src == SRC_EMB) ? OFF_EMB : OFF_A + src * CHUNK_BYTES;
+            const uint32_t a_stride = (src == SRC_EMB) ? CHUNK_BYTES : 4 * CHUNK_BYTES;
+            if (kPair) {
+              mbar_wait(bar_full + 8 * stage, phase);
+              mbar_wait_cluster(bar_peer_full + 8 * stage, phase);
+              tc_fence_after();
+              if (elect_one()) {
+                const uint64_t b_desc = desc_hi | (uint64_t)(((sbase + OFF_STAGE + stage * STAGE_BYTES) & 0x3FFFF) >> 4);
 #pragma unroll
-              for (int t = 0; t < TILES; ++t) {
-                const uint64_t a_desc = desc_hi | (uint64_t)(((sbase + OFF_EMB + t * CHUNK_BYTES + 3 * 32) & 0x3FFFF) >> 4);
-                mma_f16_ss(tmem_base + t * W + nh * STAGE_N, a_desc, b_desc + 2 * nh, idesc, 1u);
+                for (int t = 0; t < TILES; ++t) {
+                  const uint64_t a_desc = desc_hi | (uint64_t)(((sbase + a_off + t * a_stride) & 0x3FFFF) >> 4);
+#pragma unroll
+                  for (int ks = 0; ks < KCHUNK / 16; ++ks)
+                    mma_f16_ss_pair(tmem_base + t * W, a_desc + 2 * ks, b_desc + 2 * ks, idesc, (kc | ks) != 0 ? 1u : 0u);
+                }
+                mma_commit_pair(bar_empty + 8 * stage, (uint16_t)3);     // frees this slot in both CTAs
               }
-            if (kCluster) mma_commit_mcast(bar_empty + 8 * stage, (uint16_t)3);
-            else mma_commit(bar_empty + 8 * stage);
+              __syncwarp();
+              if (++stage == NUM_STAGES) { stage = 0; phase ^= 1; }
+            } else {
+#pragma unroll 1
+              for (int nh = 0; nh < n_halves; ++nh) {
+                mbar_wait(bar_full + 8 * stage, phase);
+                tc_fence_after();
+                if (elect_one()) {
+                  const uint64_t b_desc = desc_hi | (uint64_t)(((sbase + OFF_STAGE + stage * STAGE_BYTES) & 0x3FFFF) >> 4);
+#pragma unroll
+                  for (int t = 0; t < TILES; ++t) {
+                    const uint64_t a_desc = desc_hi | (uint64_t)(((sbase + a_off + t * a_stride) & 0x3FFFF) >> 4);
+                    const uint32_t d_addr = tmem_base + t * W + nh * STAGE_N;
+#pragma unroll
+                    for (int ks = 0; ks < KCHUNK / 16; ++ks)
+                      mma_f16_ss(d_addr, a_desc + 2 * ks, b_desc + 2 * ks, idesc, (kc | ks) != 0 ? 1u : 0u);
+                  }
+                  mma_commit(bar_empty + 8 * stage);                     // frees the weight stage when these MMAs retire
+                }
+                __syncwarp();
+                if (++stage == NUM_STAGES) { stage = 0; phase ^= 1; }
+              }
+            }
+          }
+          if (bias_stage) {
+            // bias: A = K-step 3 of the encoding chunk (columns 48..63: zero-weighted encoding + the two 1.0 columns),
+            // B = K-step 0 of a bias stage (hi/lo fp16 halves of the bias at K positions 12/13); one stage per N half
+            const int n_b = kPair ? 1 : 2;
+#pragma unroll 1
+            for (int nh = 0; nh < n_b; ++nh) {
+              mbar_wait(bar_full + 8 * stage, phase);
+              if (kPair) mbar_wait_cluster(bar_peer_full + 8 * stage, phase);
+              tc_fence_after();
+              if (elect_one()) {
+                const uint64_t b_desc = desc_hi | (uint64_t)(((sbase + OFF_STAGE + stage * STAGE_BYTES) & 0x3FFFF) >> 4);
+#pragma unroll
+                for (int t = 0; t < TILES; ++t) {
+                  const uint64_t a_desc = desc_hi | (uint64_t)(((sbase + OFF_EMB + t * CHUNK_BYTES + 3 * 32) & 0x3FFFF) >> 4);
+                  if (kPair) mma_f16_ss_pair(tmem_base + t * W, a_desc, b_desc, idesc, 1u);
+                  else mma_f16_ss(tmem_base + t * W + nh * STAGE_N, a_desc, b_desc, idesc, 1u);
+                }
+                if (kPair) mma_commit_pair(bar_empty + 8 * stage, (uint16_t)3);
+                else mma_commit(bar_empty + 8 * stage);
+              }
+              __syncwarp();
+              if (++stage == NUM_STAGES) { stage = 0; phase ^= 1; }
+            }
+          }
+          if (elect_one()) {                                             // accumulators of this layer complete
+            if (kPair) mma_commit_pair(bar_acc, (uint16_t)3);
+            else mma_commit(bar_acc);
           }
           __syncwarp();
-          if (++stage == NUM_STAGES) { stage = 0; phase ^= 1; }
         }
-        if (elect_one()) mma_commit(bar_acc);           // accumulators of this layer complete
-        __syncwarp();
       }
     }
   } else if (warp >= 4) {
@@ -402,9 +492,19 @@ __global__ void __launch_bounds__(THREADS, 1) nerf_mlp_tc_kernel(const __grid_co
     const uint32_t t_lane = tmem_base + ((uint32_t)(quarter * 32) << 16) + tile * W;
     const PackedTail* tail = reinterpret_cast<const PackedTail*>(a.packed + (size_t)plan.stages_per_pass * STAGE_BYTES);
     uint32_t acc_phase = 0;
+    const uint32_t aready_target = (kPair && cta_rank != 0) ? map_to_cta(bar_aready, 0) : 0;
+    auto signal_a_ready = [&]() {
+      if (kPair) fence_proxy_async_all(); else fence_proxy_async();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (kPair && cta_rank != 0) mbar_arrive_remote(aready_target);
+        else mbar_arrive(bar_aready);
+      }
+    };
 
     for (int64_t step = unit0; step < n_steps; step += n_units) {
-      const int64_t pair = kCluster ? 2 * step + cta_rank : step;
+      const int64_t pair = kPair ? 2 * step + cta_rank : step;
       const int64_t p_raw = pair * (TILES * TILE_M) + tile * TILE_M + row;
       const bool live = p_raw < a.P;
       const int64_t p = live ? p_raw : a.P - 1;
@@ -464,10 +564,7 @@ __global__ void __launch_bounds__(THREADS, 1) nerf_mlp_tc_kernel(const __grid_co
           }
         }
       }
-      fence_proxy_async();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_aready);
+      signal_a_ready();
 
       float alpha = 0.f;
       for (int l = 0; l < plan.n_layers; ++l) {
@@ -508,10 +605,7 @@ __global__ void __launch_bounds__(THREADS, 1) nerf_mlp_tc_kernel(const __grid_co
               *reinterpret_cast<uint4*>(chunk + sw128_offset(row, (c8 & 1) * 4 + pc)) = q;
             }
           }
-          fence_proxy_async();
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(bar_aready);
+          signal_a_ready();
         } else {
           // views layer (N = 128) + rgb_linear + output                          H:238-242
           float cr = 0.f, cg = 0.f, cb = 0.f;
@@ -543,10 +637,11 @@ __global__ void __launch_bounds__(THREADS, 1) nerf_mlp_tc_kernel(const __grid_co
 
   tc_fence_before();
   __syncthreads();
-  if (kCluster) cluster_sync_all();        // no CTA leaves while its peer may still multicast into it
+  if (kPair) cluster_sync_all();           // no CTA leaves (or frees TMEM) while the pair's MMAs / arrivals are in flight
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    if (kPair) tmem_dealloc_pair(tmem_base, 512);
+    else tmem_dealloc(tmem_base, 512);
   }
 }
 
@@ -575,12 +670,11 @@ __global__ void pack_kernel(const __grid_constant__ PackPlan plan, uint8_t* __re
     int n = idx / KCHUNK, k = idx % KCHUNK;
     __half hv = __float2half_rn(0.f);
     if (sd.bias_mode == 2) {
-      // K-step j (columns 16j..16j+15) feeds N half j; positions 12/13 meet the encoding chunk's 1.0 columns
-      int j = k >> 4, i = k & 15;
-      if (j < 2 && (i == 12 || i == 13)) {
+      // bias stage of one N half: K-step 0 only; positions 12/13 meet the encoding chunk's 1.0 columns (60/61 = 48+12/13)
+      if (k == 12 || k == 13) {
         __half hi, lo;
-        split_f16(sd.bias[j * STAGE_N + n], &hi, &lo);
-        hv = (i == 12) ? hi : lo;
+        split_f16(sd.bias[sd.row0 + n], &hi, &lo);
+        hv = (k == 12) ? hi : lo;
       }
     } else {
       int sc = k - sd.dst_col0;
@@ -596,8 +690,18 @@ __global__ void pack_kernel(const __grid_constant__ PackPlan plan, uint8_t* __re
   }
 }
 
-// Build the layer table and the stage list for a network description.
-static void build_plans(const scade_net& net, NetPlan* np, PackPlan* pp) {
+// Process-wide choice of the kernel form (SCADE_TC_PAIR=0 selects the single-CTA form).
+static bool use_pair() {
+  static const bool v = []() {
+    const char* e = getenv("SCADE_TC_PAIR");
+    return !(e && e[0] == '0');
+  }();
+  return v;
+}
+
+// Build the layer table and the stage list for a network description.  Stage order = consumption order:
+// layer -> K chunk -> N half (pair mode: CTA 0's half, CTA 1's half), then the layer's two bias stages.
+static void build_plans(const scade_net& net, bool pair, NetPlan* np, PackPlan* pp) {
   const scade_net_desc& d = net.desc;
   NetDims nd(d);
   NetPlan P{};
@@ -611,18 +715,22 @@ static void build_plans(const scade_net& net, NetPlan* np, PackPlan* pp) {
                        bool with_h, int n_out, int relu, int kind, const float* bias) {
     LayerDesc L{};
     L.n_halves = n_out / STAGE_N;
-    L.relu = relu; L.kind = kind;
+    L.relu = relu; L.kind = kind; L.n_out = n_out;
     L.bias_stage = with_emb ? 0 : 1;
     int nk = 0;
     if (with_emb) L.a_src[nk++] = SRC_EMB;
     if (with_h) for (int c = 0; c < 4; ++c) L.a_src[nk++] = c;
     L.n_k = nk;
+    // pair mode always splits N over the two CTAs (N/2 rows each); single mode walks 128-row halves
+    const int parts = pair ? 2 : L.n_halves;
+    const int rows = n_out / parts;
     for (int kc = 0; kc < nk; ++kc)
-      for (int nh = 0; nh < L.n_halves; ++nh) {
-        if (L.a_src[kc] == SRC_EMB) add_stage(Wt, fan_in, emb_col0, emb_ncols, emb_dst, nh * STAGE_N, STAGE_N, bias, 1);
-        else add_stage(Wt, fan_in, h_col0 + 64 * L.a_src[kc], 64, 0, nh * STAGE_N, STAGE_N, nullptr, 0);
+      for (int h = 0; h < parts; ++h) {
+        if (L.a_src[kc] == SRC_EMB) add_stage(Wt, fan_in, emb_col0, emb_ncols, emb_dst, h * rows, rows, bias, 1);
+        else add_stage(Wt, fan_in, h_col0 + 64 * L.a_src[kc], 64, 0, h * rows, rows, nullptr, 0);
       }
-    if (L.bias_stage) add_stage(nullptr, 0, 0, 0, 0, 0, 0, bias, 2);
+    if (L.bias_stage)
+      for (int h = 0; h < 2; ++h) add_stage(nullptr, 0, 0, 0, 0, h * STAGE_N, STAGE_N, bias, 2);
     P.layers[P.n_layers++] = L;
   };
   for (int i = 0; i < d.D; ++i) {
@@ -643,11 +751,11 @@ static void build_plans(const scade_net& net, NetPlan* np, PackPlan* pp) {
   if (pp) *pp = Q;
 }
 
-static int count_stages(const scade_net_desc& d) {
+static int count_stages(const scade_net_desc& d, bool pair) {
   int n = 2;                                   // layer 0: 1 K chunk x 2 halves (bias inside)
-  for (int i = 1; i < d.D; ++i) n += (i - 1 == d.skip) ? 10 : 9;     // 4 K chunks x 2 halves + bias stage, or 5 x 2
-  n += 9;                                      // feature + bias stage
-  n += 5;                                      // views (N = 128)
+  for (int i = 1; i < d.D; ++i) n += 10;       // 4 K chunks x 2 halves + 2 bias stages, or (skip layer) 5 x 2
+  n += 10;                                     // feature + 2 bias stages
+  n += pair ? 10 : 5;                          // views (N = 128): 5 K chunks, split over the pair or not
   return n;
 }
 
@@ -656,16 +764,16 @@ static int count_stages(const scade_net_desc& d) {
 bool mlp_tc_supported(const scade_net_desc& d) {
   NetDims nd(d);
   return d.W == tc::W && d.D >= 2 && d.D <= 8 && nd.in_all <= tc::ONES_COL && d.multires <= 9 && d.multires_views == 0 &&
-         d.skip != d.D - 1 && tc::count_stages(d) <= tc::MAX_STAGE_DESCS;
+         d.skip != d.D - 1 && tc::count_stages(d, true) <= tc::MAX_STAGE_DESCS;
 }
 
 size_t mlp_tc_packed_bytes(const scade_net_desc& d) {
-  return (size_t)tc::count_stages(d) * tc::STAGE_BYTES + align_up(sizeof(tc::PackedTail));
+  return (size_t)tc::count_stages(d, tc::use_pair()) * tc::STAGE_BYTES + align_up(sizeof(tc::PackedTail));
 }
 
 int mlp_tc_pack(const scade_net& net, void* packed_out, cudaStream_t st) {
   tc::PackPlan pp;
-  tc::build_plans(net, nullptr, &pp);
+  tc::build_plans(net, tc::use_pair(), nullptr, &pp);
   tc::pack_kernel<<<pp.n_stages + 1, 256, 0, st>>>(pp, reinterpret_cast<uint8_t*>(packed_out));
   SCADE_LAUNCH_CHECK();
   return SCADE_OK;
@@ -681,10 +789,7 @@ int mlp_tc_forward(const scade_net& net, const float* rays, int ray_stride, cons
     set_error("SCADE_PREC_TC_F16 forward does not stash activations for backward in this version");
     return SCADE_ERR_UNSUPPORTED;
   }
-  static const bool use_cluster = []() {
-    const char* e = getenv("SCADE_TC_CLUSTER");
-    return !(e && e[0] == '0');
-  }();
+  const bool pair = tc::use_pair();
   static bool attr_set = false;
   if (!attr_set) {
     SCADE_CUDA(cudaFuncSetAttribute(tc::nerf_mlp_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
@@ -692,7 +797,7 @@ int mlp_tc_forward(const scade_net& net, const float* rays, int ray_stride, cons
     attr_set = true;
   }
   tc::NetPlan plan;
-  tc::build_plans(net, &plan, nullptr);
+  tc::build_plans(net, pair, &plan, nullptr);
   NetDims nd(net.desc);
   tc::FwdArgs a{};
   a.packed = reinterpret_cast<const uint8_t*>(net.packed_f16);
@@ -704,7 +809,7 @@ int mlp_tc_forward(const scade_net& net, const float* rays, int ray_stride, cons
   a.multires = net.desc.multires; a.multires_views = net.desc.multires_views;
   a.out = reinterpret_cast<float4*>(raw_out);
   a.n_pairs = ceil_div<int64_t>(a.P, tc::TILES * tc::TILE_M);
-  if (use_cluster) {
+  if (pair) {
     int64_t n_steps = (a.n_pairs + 1) / 2;
     int clusters = (int)std::min<int64_t>(n_steps, num_sms() / 2);
     cudaLaunchConfig_t cfg{};
