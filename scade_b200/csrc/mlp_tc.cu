@@ -75,6 +75,8 @@ struct NetPlan {
   int n_layers;
   int stages_per_pass;
   LayerDesc layers[MAX_LAYERS];
+  int first_stage[MAX_LAYERS];   // the layer's stages are [first_stage, first_stage + n_stages) of the packed stream
+  int n_stages[MAX_LAYERS];
 };
 
 // small fp32 table behind the stage images in the packed buffer
@@ -314,7 +316,12 @@ struct FwdArgs {
 //                 CTA, N=256); each CTA streams only ITS half (128 N rows) of every weight block, so the B operand read
 //                 per SM and the weight bytes per SM are halved (the single-CTA form is shared-memory-bandwidth bound:
 //                 4 KB of A + 4 KB of B per 64-cycle instruction = 128 B/cycle).
-template <bool kPair>
+// kPing == false: the two row tiles of a CTA run in lock-step and share every weight stage.
+// kPing == true : the two row tiles are independent pipelines that alternate on the tensor pipe: while tile 0's
+//                 accumulators are drained by its epilogue warps, tile 1's MMAs run (and vice versa), which hides the
+//                 epilogue and the per-layer barrier/pipeline latencies.  Each layer's weight stages are streamed twice
+//                 (once per tile); the pair form keeps that at 16 KB per 512 MMA cycles per SM.
+template <bool kPair, bool kPing>
 __global__ void __launch_bounds__(THREADS, 1) nerf_mlp_tc_kernel(const __grid_constant__ FwdArgs a,
                                                                  const __grid_constant__ NetPlan plan) {
   extern __shared__ uint8_t smem_raw[];
@@ -326,12 +333,13 @@ __global__ void __launch_bounds__(THREADS, 1) nerf_mlp_tc_kernel(const __grid_co
   const int64_t unit0 = kPair ? cluster_id_x() : blockIdx.x;
   const int64_t n_units = kPair ? num_clusters_x() : gridDim.x;
   const int64_t n_steps = kPair ? (a.n_pairs + 1) / 2 : a.n_pairs;
+  constexpr int kStreams = kPing ? 2 : 1;          // independent tile pipelines per CTA
 
-  // barriers: full[4], empty[4], acc_full, a_ready, peer_full[4] (leader: the peer's stage has landed), TMEM base slot
+  // barriers: full[4], empty[4], peer_full[4] (leader: the peer's stage has landed), acc_full[2], a_ready[2], TMEM slot
   const uint32_t bar_full = sbase + OFF_BAR, bar_empty = bar_full + 8 * NUM_STAGES;
-  const uint32_t bar_acc = bar_empty + 8 * NUM_STAGES, bar_aready = bar_acc + 8;
-  const uint32_t bar_peer_full = bar_aready + 8;
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + OFF_BAR + 8 * (3 * NUM_STAGES + 2));
+  const uint32_t bar_peer_full = bar_empty + 8 * NUM_STAGES;
+  const uint32_t bar_acc = bar_peer_full + 8 * NUM_STAGES, bar_aready = bar_acc + 16;
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + OFF_BAR + 8 * (3 * NUM_STAGES + 4));
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < NUM_STAGES; ++s) {
@@ -339,8 +347,11 @@ __global__ void __launch_bounds__(THREADS, 1) nerf_mlp_tc_kernel(const __grid_co
       mbar_init(bar_empty + 8 * s, 1);
       mbar_init(bar_peer_full + 8 * s, 1);
     }
-    mbar_init(bar_acc, 1);
-    mbar_init(bar_aready, kPair ? 2 * EPI_WARPS : EPI_WARPS);     // pair: the peer's epilogue warps arrive remotely
+    for (int t = 0; t < 2; ++t) {
+      mbar_init(bar_acc + 8 * t, 1);
+      // arrivals: one per epilogue warp of the stream (pair form: the peer CTA's warps arrive remotely as well)
+      mbar_init(bar_aready + 8 * t, (kPair ? 2 : 1) * (EPI_WARPS / kStreams));
+    }
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -358,40 +369,55 @@ __global__ void __launch_bounds__(THREADS, 1) nerf_mlp_tc_kernel(const __grid_co
   if (warp < 4) asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");
   else asm volatile("setmaxnreg.inc.sync.aligned.u32 200;");
 
-  if (warp == 0) {
-    // ================= TMA producer: stream the packed weight stages =================
-    // pair mode: stages alternate (CTA 0's half, CTA 1's half); each CTA fetches only its own
-    if (lane == 0) {
+  if (warp == 0 || (warp == 2 && kPair)) {
+    // ================= warp 0: TMA producer -- streams the packed weight stages =================
+    //   pair form: stages alternate (CTA 0's half, CTA 1's half); each CTA fetches only its own;
+    //   ping-pong : every layer's stage list is streamed once per tile stream.
+    // ================= warp 2 (pair form, non-leader CTA): relay -- tells the leader that this CTA's stage landed ====
+    const bool is_relay = warp == 2;
+    if (lane == 0 && (!is_relay || cta_rank != 0)) {
       uint32_t stage = 0, phase = 0;
       const int s0 = kPair ? (int)cta_rank : 0, ds = kPair ? 2 : 1;
+      const uint32_t leader_peer_full = kPair ? map_to_cta(bar_peer_full, 0) : 0;
       for (int64_t step = unit0; step < n_steps; step += n_units) {
-        for (int s = s0; s < plan.stages_per_pass; s += ds) {
-          mbar_wait(bar_empty + 8 * stage, phase ^ 1);
-          mbar_expect_tx(bar_full + 8 * stage, STAGE_BYTES);
-          bulk_g2s(sbase + OFF_STAGE + stage * STAGE_BYTES, a.packed + (size_t)s * STAGE_BYTES, STAGE_BYTES, bar_full + 8 * stage);
-          if (++stage == NUM_STAGES) { stage = 0; phase ^= 1; }
-        }
-      }
-    }
-  } else if (warp == 2) {
-    // ================= relay (pair mode, non-leader CTA): tell the leader that this CTA's stage has landed =========
-    if (kPair && cta_rank != 0 && lane == 0) {
-      uint32_t stage = 0, phase = 0;
-      const uint32_t leader_peer_full = map_to_cta(bar_peer_full, 0);
-      for (int64_t step = unit0; step < n_steps; step += n_units) {
-        for (int s = 1; s < plan.stages_per_pass; s += 2) {
-          mbar_wait(bar_full + 8 * stage, phase);
-          mbar_arrive_remote(leader_peer_full + 8 * stage);
-          if (++stage == NUM_STAGES) { stage = 0; phase ^= 1; }
+        for (int l = 0; l < plan.n_layers; ++l) {
+          const int first = plan.first_stage[l], last = first + plan.n_stages[l];
+          for (int rep = 0; rep < kStreams; ++rep) {
+            for (int s = first + s0; s < last; s += ds) {
+              if (!is_relay) {
+                mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+                mbar_expect_tx(bar_full + 8 * stage, STAGE_BYTES);
+                bulk_g2s(sbase + OFF_STAGE + stage * STAGE_BYTES, a.packed + (size_t)s * STAGE_BYTES, STAGE_BYTES,
+                         bar_full + 8 * stage);
+              } else {
+                mbar_wait(bar_full + 8 * stage, phase);
+                mbar_arrive_remote(leader_peer_full + 8 * stage);
+              }
+              if (++stage == NUM_STAGES) { stage = 0; phase ^= 1; }
+            }
+          }
         }
       }
     }
   } else if (warp == 1) {
     // ================= MMA issuer =================
     // The whole warp walks the loops (warp-uniform control flow keeps descriptors in uniform registers);
-    // one elected lane issues the tcgen05 instructions.  In pair mode only the leader CTA issues.
-    uint32_t stage = 0, phase = 0, a_phase = 0;
+    // one elected lane issues the tcgen05 instructions.  In pair form only the leader CTA issues.
+    uint32_t stage = 0, phase = 0, a_phase0 = 0, a_phase1 = 0;
     constexpr uint64_t desc_hi = ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61) | ((uint64_t)1 << 16);
+    auto wait_stage = [&]() {
+      mbar_wait(bar_full + 8 * stage, phase);
+      if (kPair) mbar_wait_cluster(bar_peer_full + 8 * stage, phase);
+      tc_fence_after();
+    };
+    auto release_stage = [&]() {                        // (elected lane) frees the slot once the MMAs issued so far retire
+      if (kPair) mma_commit_pair(bar_empty + 8 * stage, (uint16_t)3);
+      else mma_commit(bar_empty + 8 * stage);
+    };
+    auto next_stage = [&]() {
+      __syncwarp();
+      if (++stage == NUM_STAGES) { stage = 0; phase ^= 1; }
+    };
     if (!kPair || cta_rank == 0) {
       for (int64_t step = unit0; step < n_steps; step += n_units) {
         for (int l = 0; l < plan.n_layers; ++l) {
@@ -400,84 +426,69 @@ __global__ void __launch_bounds__(THREADS, 1) nerf_mlp_tc_kernel(const __grid_co
           int a_src[5];
 #pragma unroll
           for (int i = 0; i < 5; ++i) a_src[i] = plan.layers[l].a_src[i];
-          if (kPair) mbar_wait_cluster(bar_aready, a_phase); else mbar_wait(bar_aready, a_phase);
-          a_phase ^= 1;
-          tc_fence_after();
 #pragma unroll 1
-          for (int kc = 0; kc < n_k; ++kc) {
-            int src = a_src[0];
-#pragma unroll
-            for (int i = 1; i < 5; ++i) src = (kc == i) ? a_src[i] : src;
-            const uint32_t a_off = (src == SRC_EMB) ? OFF_EMB : OFF_A + src * CHUNK_BYTES;
-            const uint32_t a_stride = (src == SRC_EMB) ? CHUNK_BYTES : 4 * CHUNK_BYTES;
-            if (kPair) {
-              mbar_wait(bar_full + 8 * stage, phase);
-              mbar_wait_cluster(bar_peer_full + 8 * stage, phase);
+          for (int sidx = 0; sidx < kStreams; ++sidx) {
+            const int t_lo = kPing ? sidx : 0, t_hi = kPing ? sidx + 1 : TILES;
+            {
+              const uint32_t ph = sidx == 0 ? a_phase0 : a_phase1;
+              if (kPair) mbar_wait_cluster(bar_aready + 8 * sidx, ph); else mbar_wait(bar_aready + 8 * sidx, ph);
+              if (sidx == 0) a_phase0 ^= 1; else a_phase1 ^= 1;
               tc_fence_after();
-              if (elect_one()) {
-                const uint64_t b_desc = desc_hi | (uint64_t)(((sbase + OFF_STAGE + stage * STAGE_BYTES) & 0x3FFFF) >> 4);
-#pragma unroll
-                for (int t = 0; t < TILES; ++t) {
-                  const uint64_t a_desc = desc_hi | (uint64_t)(((sbase + a_off + t * a_stride) & 0x3FFFF) >> 4);
-#pragma unroll
-                  for (int ks = 0; ks < KCHUNK / 16; ++ks)
-                    mma_f16_ss_pair(tmem_base + t * W, a_desc + 2 * ks, b_desc + 2 * ks, idesc, (kc | ks) != 0 ? 1u : 0u);
-                }
-                mma_commit_pair(bar_empty + 8 * stage, (uint16_t)3);     // frees this slot in both CTAs
-              }
-              __syncwarp();
-              if (++stage == NUM_STAGES) { stage = 0; phase ^= 1; }
-            } else {
+            }
 #pragma unroll 1
-              for (int nh = 0; nh < n_halves; ++nh) {
-                mbar_wait(bar_full + 8 * stage, phase);
-                tc_fence_after();
+            for (int kc = 0; kc < n_k; ++kc) {
+              int src = a_src[0];
+#pragma unroll
+              for (int i = 1; i < 5; ++i) src = (kc == i) ? a_src[i] : src;
+              const uint32_t a_off = (src == SRC_EMB) ? OFF_EMB : OFF_A + src * CHUNK_BYTES;
+              const uint32_t a_stride = (src == SRC_EMB) ? CHUNK_BYTES : 4 * CHUNK_BYTES;
+              const int n_parts = kPair ? 1 : n_halves;          // pair form: one M=256, N=n_out instruction series per K chunk
+#pragma unroll 1
+              for (int nh = 0; nh < n_parts; ++nh) {
+                wait_stage();
                 if (elect_one()) {
                   const uint64_t b_desc = desc_hi | (uint64_t)(((sbase + OFF_STAGE + stage * STAGE_BYTES) & 0x3FFFF) >> 4);
-#pragma unroll
-                  for (int t = 0; t < TILES; ++t) {
+#pragma unroll 1
+                  for (int t = t_lo; t < t_hi; ++t) {
                     const uint64_t a_desc = desc_hi | (uint64_t)(((sbase + a_off + t * a_stride) & 0x3FFFF) >> 4);
                     const uint32_t d_addr = tmem_base + t * W + nh * STAGE_N;
 #pragma unroll
-                    for (int ks = 0; ks < KCHUNK / 16; ++ks)
-                      mma_f16_ss(d_addr, a_desc + 2 * ks, b_desc + 2 * ks, idesc, (kc | ks) != 0 ? 1u : 0u);
+                    for (int ks = 0; ks < KCHUNK / 16; ++ks) {
+                      if (kPair) mma_f16_ss_pair(d_addr, a_desc + 2 * ks, b_desc + 2 * ks, idesc, (kc | ks) != 0 ? 1u : 0u);
+                      else mma_f16_ss(d_addr, a_desc + 2 * ks, b_desc + 2 * ks, idesc, (kc | ks) != 0 ? 1u : 0u);
+                    }
                   }
-                  mma_commit(bar_empty + 8 * stage);                     // frees the weight stage when these MMAs retire
+                  release_stage();
                 }
-                __syncwarp();
-                if (++stage == NUM_STAGES) { stage = 0; phase ^= 1; }
+                next_stage();
               }
             }
-          }
-          if (bias_stage) {
-            // bias: A = K-step 3 of the encoding chunk (columns 48..63: zero-weighted encoding + the two 1.0 columns),
-            // B = K-step 0 of a bias stage (hi/lo fp16 halves of the bias at K positions 12/13); one stage per N half
-            const int n_b = kPair ? 1 : 2;
+            if (bias_stage) {
+              // bias: A = K-step 3 of the encoding chunk (columns 48..63: zero-weighted encoding + the two 1.0 columns),
+              // B = K-step 0 of a bias stage (hi/lo fp16 halves of the bias at K positions 12/13); one stage per N half
+              const int n_b = kPair ? 1 : 2;
 #pragma unroll 1
-            for (int nh = 0; nh < n_b; ++nh) {
-              mbar_wait(bar_full + 8 * stage, phase);
-              if (kPair) mbar_wait_cluster(bar_peer_full + 8 * stage, phase);
-              tc_fence_after();
-              if (elect_one()) {
-                const uint64_t b_desc = desc_hi | (uint64_t)(((sbase + OFF_STAGE + stage * STAGE_BYTES) & 0x3FFFF) >> 4);
-#pragma unroll
-                for (int t = 0; t < TILES; ++t) {
-                  const uint64_t a_desc = desc_hi | (uint64_t)(((sbase + OFF_EMB + t * CHUNK_BYTES + 3 * 32) & 0x3FFFF) >> 4);
-                  if (kPair) mma_f16_ss_pair(tmem_base + t * W, a_desc, b_desc, idesc, 1u);
-                  else mma_f16_ss(tmem_base + t * W + nh * STAGE_N, a_desc, b_desc, idesc, 1u);
+              for (int nh = 0; nh < n_b; ++nh) {
+                wait_stage();
+                if (elect_one()) {
+                  const uint64_t b_desc = desc_hi | (uint64_t)(((sbase + OFF_STAGE + stage * STAGE_BYTES) & 0x3FFFF) >> 4);
+#pragma unroll 1
+                  for (int t = t_lo; t < t_hi; ++t) {
+                    const uint64_t a_desc = desc_hi | (uint64_t)(((sbase + OFF_EMB + t * CHUNK_BYTES + 3 * 32) & 0x3FFFF) >> 4);
+                    if (kPair) mma_f16_ss_pair(tmem_base + t * W, a_desc, b_desc, idesc, 1u);
+                    else mma_f16_ss(tmem_base + t * W + nh * STAGE_N, a_desc, b_desc, idesc, 1u);
+                  }
+                  release_stage();
                 }
-                if (kPair) mma_commit_pair(bar_empty + 8 * stage, (uint16_t)3);
-                else mma_commit(bar_empty + 8 * stage);
+                next_stage();
               }
-              __syncwarp();
-              if (++stage == NUM_STAGES) { stage = 0; phase ^= 1; }
             }
+            if (elect_one()) {                                           // accumulators of this stream's layer complete
+              if (kPair) mma_commit_pair(bar_acc + 8 * sidx, (uint16_t)3);
+              else mma_commit(bar_acc + 8 * sidx);
+            }
+            __syncwarp();
           }
-          if (elect_one()) {                                             // accumulators of this layer complete
-            if (kPair) mma_commit_pair(bar_acc, (uint16_t)3);
-            else mma_commit(bar_acc);
-          }
-          __syncwarp();
         }
       }
     }
@@ -492,14 +503,16 @@ __global__ void __launch_bounds__(THREADS, 1) nerf_mlp_tc_kernel(const __grid_co
     const uint32_t t_lane = tmem_base + ((uint32_t)(quarter * 32) << 16) + tile * W;
     const PackedTail* tail = reinterpret_cast<const PackedTail*>(a.packed + (size_t)plan.stages_per_pass * STAGE_BYTES);
     uint32_t acc_phase = 0;
-    const uint32_t aready_target = (kPair && cta_rank != 0) ? map_to_cta(bar_aready, 0) : 0;
+    const int sidx = kPing ? tile : 0;                  // which stream's barriers this warp uses
+    const uint32_t my_acc = bar_acc + 8 * sidx, my_aready = bar_aready + 8 * sidx;
+    const uint32_t aready_target = (kPair && cta_rank != 0) ? map_to_cta(my_aready, 0) : 0;
     auto signal_a_ready = [&]() {
       if (kPair) fence_proxy_async_all(); else fence_proxy_async();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
         if (kPair && cta_rank != 0) mbar_arrive_remote(aready_target);
-        else mbar_arrive(bar_aready);
+        else mbar_arrive(my_aready);
       }
     };
 
@@ -569,7 +582,7 @@ __global__ void __launch_bounds__(THREADS, 1) nerf_mlp_tc_kernel(const __grid_co
       float alpha = 0.f;
       for (int l = 0; l < plan.n_layers; ++l) {
         const int kind = plan.layers[l].kind, relu = plan.layers[l].relu;
-        mbar_wait(bar_acc, acc_phase);
+        mbar_wait(my_acc, acc_phase);
         acc_phase ^= 1;
         tc_fence_after();
         if (kind != 3) {
@@ -714,6 +727,7 @@ static void build_plans(const scade_net& net, bool pair, NetPlan* np, PackPlan* 
   auto add_layer = [&](const float* Wt, int fan_in, bool with_emb, int emb_col0, int emb_ncols, int emb_dst, int h_col0,
                        bool with_h, int n_out, int relu, int kind, const float* bias) {
     LayerDesc L{};
+    P.first_stage[P.n_layers] = Q.n_stages;
     L.n_halves = n_out / STAGE_N;
     L.relu = relu; L.kind = kind; L.n_out = n_out;
     L.bias_stage = with_emb ? 0 : 1;
@@ -731,6 +745,7 @@ static void build_plans(const scade_net& net, bool pair, NetPlan* np, PackPlan* 
       }
     if (L.bias_stage)
       for (int h = 0; h < 2; ++h) add_stage(nullptr, 0, 0, 0, 0, h * STAGE_N, STAGE_N, bias, 2);
+    P.n_stages[P.n_layers] = Q.n_stages - P.first_stage[P.n_layers];
     P.layers[P.n_layers++] = L;
   };
   for (int i = 0; i < d.D; ++i) {
@@ -790,10 +805,16 @@ int mlp_tc_forward(const scade_net& net, const float* rays, int ray_stride, cons
     return SCADE_ERR_UNSUPPORTED;
   }
   const bool pair = tc::use_pair();
+  static const bool ping = []() {
+    const char* e = getenv("SCADE_TC_PING");
+    return !(e && e[0] == '0');
+  }();
+  using KernelFn = void (*)(const tc::FwdArgs, const tc::NetPlan);
+  KernelFn kern = pair ? (ping ? (KernelFn)tc::nerf_mlp_tc_kernel<true, true> : (KernelFn)tc::nerf_mlp_tc_kernel<true, false>)
+                       : (ping ? (KernelFn)tc::nerf_mlp_tc_kernel<false, true> : (KernelFn)tc::nerf_mlp_tc_kernel<false, false>);
   static bool attr_set = false;
   if (!attr_set) {
-    SCADE_CUDA(cudaFuncSetAttribute(tc::nerf_mlp_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
-    SCADE_CUDA(cudaFuncSetAttribute(tc::nerf_mlp_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
+    SCADE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
     attr_set = true;
   }
   tc::NetPlan plan;
@@ -821,10 +842,10 @@ int mlp_tc_forward(const scade_net& net, const float* rays, int ray_stride, cons
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    SCADE_CUDA(cudaLaunchKernelEx(&cfg, tc::nerf_mlp_tc_kernel<true>, a, plan));
+    SCADE_CUDA(cudaLaunchKernelEx(&cfg, kern, a, plan));
   } else {
     int grid = (int)std::min<int64_t>(a.n_pairs, num_sms());
-    tc::nerf_mlp_tc_kernel<false><<<grid, tc::THREADS, tc::SMEM_BYTES, st>>>(a, plan);
+    kern<<<grid, tc::THREADS, tc::SMEM_BYTES, st>>>(a, plan);
   }
   SCADE_LAUNCH_CHECK();
   return SCADE_OK;
