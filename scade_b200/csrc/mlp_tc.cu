@@ -658,6 +658,345 @@ __global__ void __launch_bounds__(THREADS, 1) nerf_mlp_tc_kernel(const __grid_co
   }
 }
 
+// =====================================================================================================
+// v6: SM-pair kernel with the two row tiles ping-ponging on ONE shared weight ring
+// =====================================================================================================
+// Cluster of 2 CTAs.  "Super-tile" t = row tile t of both CTAs (256 points); the leader CTA issues
+// tcgen05.mma.cta_group::2 (M=256, N=256/128).  Each CTA streams only its own N half of every weight block, ONCE per
+// layer, through a 4-slot ring.  Super-tile 0 runs up to 4 stages ahead of super-tile 1; a slot is released by
+// super-tile 1's MMAs.  So while tile 1's MMAs of layer l occupy the tensor pipe, tile 0's epilogue warps turn its
+// layer-l accumulators into the layer-(l+1) operand, and vice versa: epilogue, barrier round trips and pipeline
+// fill/drain of one tile hide under the other tile's MMAs, with no extra weight traffic and no extra shared memory.
+// 16 epilogue warps (8 per tile: thread = one row x 128 columns) keep a tile's epilogue shorter than a layer of MMAs.
+constexpr int PP_EPI_WARPS = 16;
+constexpr int PP_THREADS = 128 + PP_EPI_WARPS * 32;
+
+__global__ void __launch_bounds__(PP_THREADS, 1) nerf_mlp_tc_pp_kernel(const __grid_constant__ FwdArgs a,
+                                                                       const __grid_constant__ NetPlan plan) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const uint32_t sbase = smem_u32(smem);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t cta_rank = cluster_ctarank();
+  const int64_t unit0 = cluster_id_x(), n_units = num_clusters_x();
+  const int64_t n_steps = (a.n_pairs + 1) / 2;
+
+  const uint32_t bar_full = sbase + OFF_BAR, bar_empty = bar_full + 8 * NUM_STAGES;
+  const uint32_t bar_peer_full = bar_empty + 8 * NUM_STAGES;
+  const uint32_t bar_acc = bar_peer_full + 8 * NUM_STAGES, bar_aready = bar_acc + 16;
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + OFF_BAR + 8 * (3 * NUM_STAGES + 4));
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < NUM_STAGES; ++s) {
+      mbar_init(bar_full + 8 * s, 1);
+      mbar_init(bar_empty + 8 * s, 1);
+      mbar_init(bar_peer_full + 8 * s, 1);
+    }
+    for (int t = 0; t < 2; ++t) {
+      mbar_init(bar_acc + 8 * t, 1);
+      mbar_init(bar_aready + 8 * t, PP_EPI_WARPS);      // 8 local + 8 remote epilogue warps per super-tile
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc_pair(smem_u32((const void*)tmem_slot), 512);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0 || warp == 2) {
+    // warp 0: TMA producer of this CTA's half stages (every stage once per layer).
+    // warp 2 (non-leader CTA): relay -- forwards "my stage has landed" to the leader's peer_full barrier.
+    const bool is_relay = warp == 2;
+    if (lane == 0 && (!is_relay || cta_rank != 0)) {
+      uint32_t stage = 0, phase = 0;
+      const uint32_t leader_peer_full = map_to_cta(bar_peer_full, 0);
+      for (int64_t step = unit0; step < n_steps; step += n_units) {
+        for (int l = 0; l < plan.n_layers; ++l) {
+          const int first = plan.first_stage[l], last = first + plan.n_stages[l];
+          for (int s = first + (int)cta_rank; s < last; s += 2) {
+            if (!is_relay) {
+              mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+              mbar_expect_tx(bar_full + 8 * stage, STAGE_BYTES);
+              bulk_g2s(sbase + OFF_STAGE + stage * STAGE_BYTES, a.packed + (size_t)s * STAGE_BYTES, STAGE_BYTES,
+                       bar_full + 8 * stage);
+            } else {
+              mbar_wait(bar_full + 8 * stage, phase);
+              mbar_arrive_remote(leader_peer_full + 8 * stage);
+            }
+            if (++stage == NUM_STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer (leader CTA) =================
+    if (cta_rank == 0) {
+      constexpr uint64_t desc_hi = ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61) | ((uint64_t)1 << 16);
+      // ring position of each super-tile (tile 1 trails tile 0)
+      uint32_t slot0 = 0, slot1 = 0, ph0 = 0, ph1 = 0, a_ph0 = 0, a_ph1 = 0;
+      for (int64_t step = unit0; step < n_steps; step += n_units) {
+        for (int l = 0; l < plan.n_layers; ++l) {
+          const int n_k = plan.layers[l].n_k, bias_stage = plan.layers[l].bias_stage;
+          const int n_own = n_k + bias_stage;                      // this layer's stages per CTA (<= 5)
+          const int has_emb = plan.layers[l].a_src[0] == SRC_EMB;
+          const uint32_t idesc = make_idesc(2 * TILE_M, plan.layers[l].n_out);
+          // one (stage, tile): wait for the slot in both CTAs, issue its MMAs for super-tile t, optionally release it
+          auto consume_at = [&](int t, uint32_t& slot_ref, uint32_t& ph_ref, int i, bool release) {
+            const uint32_t sl = slot_ref, p = ph_ref;
+            mbar_wait(bar_full + 8 * sl, p);
+            mbar_wait(bar_peer_full + 8 * sl, p);
+            tc_fence_after();
+            if (elect_one()) {
+              const uint64_t b_desc = desc_hi | (uint64_t)(((sbase + OFF_STAGE + sl * STAGE_BYTES) & 0x3FFFF) >> 4);
+              const uint32_t d_addr = tmem_base + t * W;
+              if (i < n_k) {
+                const bool emb = has_emb && i == 0;
+                const uint32_t a_addr = emb ? sbase + OFF_EMB + t * CHUNK_BYTES
+                                            : sbase + OFF_A + (t * 4 + (i - has_emb)) * CHUNK_BYTES;
+                const uint64_t a_desc = desc_hi | (uint64_t)((a_addr & 0x3FFFF) >> 4);
+#pragma unroll
+                for (int ks = 0; ks < KCHUNK / 16; ++ks)
+                  mma_f16_ss_pair(d_addr, a_desc + 2 * ks, b_desc + 2 * ks, idesc, (i | ks) != 0 ? 1u : 0u);
+              } else {
+                // bias stage: A = K-step 3 of the encoding chunk (the two 1.0 columns), B = K-step 0 (bias hi/lo)
+                const uint64_t a_desc = desc_hi | (uint64_t)(((sbase + OFF_EMB + t * CHUNK_BYTES + 3 * 32) & 0x3FFFF) >> 4);
+                mma_f16_ss_pair(d_addr, a_desc, b_desc, idesc, 1u);
+              }
+              if (release) mma_commit_pair(bar_empty + 8 * sl, (uint16_t)3);
+            }
+            __syncwarp();
+            if (++slot_ref == NUM_STAGES) { slot_ref = 0; ph_ref ^= 1; }
+          };
+          auto consume = [&](int t, int i, bool release) {
+            if (t == 0) consume_at(0, slot0, ph0, i, release);
+            else consume_at(1, slot1, ph1, i, release);
+          };
+          auto wait_a = [&](int t) {
+            if (t == 0) { mbar_wait(bar_aready, a_ph0); a_ph0 ^= 1; }
+            else { mbar_wait(bar_aready + 8, a_ph1); a_ph1 ^= 1; }
+            tc_fence_after();
+          };
+          auto publish = [&](int t) {
+            if (elect_one()) mma_commit_pair(bar_acc + 8 * t, (uint16_t)3);
+            __syncwarp();
+          };
+          // tile 0 first (at most NUM_STAGES ahead of tile 1), then tile 1, which releases the slots
+          wait_a(0);
+          const int lead = n_own < NUM_STAGES ? n_own : NUM_STAGES;
+          for (int i = 0; i < lead; ++i) consume(0, i, false);
+          int i1 = 0;
+          if (n_own > NUM_STAGES) {                                // 5-stage layer: tile 1 must free a slot first
+            wait_a(1);
+            consume(1, 0, true);
+            i1 = 1;
+            consume(0, NUM_STAGES, false);
+          }
+          publish(0);
+          if (i1 == 0) wait_a(1);
+          for (int i = i1; i < n_own; ++i) consume(1, i, true);
+          publish(1);
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ================= prologue / epilogue warps: thread == one row x 128 columns =================
+    const int ew = warp - 4;
+    const int tile = ew >> 3;
+    const int quarter = warp & 3;                       // TMEM lane quarter this warp may access
+    const int half = (ew >> 2) & 1;                     // which 128 accumulator columns
+    const int row = quarter * 32 + lane;
+    uint8_t* a_tile = smem + OFF_A + tile * 4 * CHUNK_BYTES;
+    uint8_t* emb_tile = smem + OFF_EMB + tile * CHUNK_BYTES;
+    const uint32_t t_lane = tmem_base + ((uint32_t)(quarter * 32) << 16) + tile * W;
+    const PackedTail* tail = reinterpret_cast<const PackedTail*>(a.packed + (size_t)plan.stages_per_pass * STAGE_BYTES);
+    const uint32_t my_acc = bar_acc + 8 * tile, my_aready = bar_aready + 8 * tile;
+    const uint32_t aready_target = cta_rank != 0 ? map_to_cta(my_aready, 0) : my_aready;
+    uint32_t acc_phase = 0;
+    auto signal_a_ready = [&]() {
+      fence_proxy_async();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (cta_rank != 0) mbar_arrive_remote(aready_target);
+        else mbar_arrive(my_aready);
+      }
+    };
+
+    for (int64_t step = unit0; step < n_steps; step += n_units) {
+      const int64_t pair = 2 * step + cta_rank;
+      const int64_t p_raw = pair * (TILES * TILE_M) + tile * TILE_M + row;
+      const bool live = p_raw < a.P;
+      const int64_t p = live ? p_raw : a.P - 1;
+
+      // ---- positional encoding: this thread writes encoding-chunk columns [32*half, 32*half + 32) of its row ----
+      {
+        float v[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = 0.f;
+        if (a.rays != nullptr) {
+          const int64_t r = p / a.S;
+          const float* ray = a.rays + r * a.ray_stride;
+          const float zz = a.z[p];
+          const float cen[3] = {a.cx, a.cy, a.cz};
+          const int in_ch = 3 + 6 * a.multires;
+#pragma unroll
+          for (int d = 0; d < 3; ++d) {
+            float pt = __fadd_rn(ray[d], __fmul_rn(ray[3 + d], zz));            // RS:657
+            float x = __fmul_rn(__fsub_rn(pt, cen[d]), a.bb_scale);             // RS:52
+            float xp = __fmul_rn(x, 3.14159274101257324f);                      // H:165
+            if (half == 0) {
+              v[d] = x;                                                         // columns 0..2
+#pragma unroll
+              for (int k = 0; k < 5; ++k) {
+                if (k < a.multires) {
+                  float s, c;
+                  sincos_reduced(__fmul_rn(xp, (float)(1 << k)), &s, &c);
+                  if (3 + 6 * k + d < 32) v[3 + 6 * k + d] = s;                 // sin block of octave k
+                  if (6 + 6 * k + d < 32) v[6 + 6 * k + d] = c;                 // cos block
+                }
+              }
+            } else {
+#pragma unroll
+              for (int k = 4; k < 9; ++k) {
+                if (k < a.multires) {
+                  float s, c;
+                  sincos_reduced(__fmul_rn(xp, (float)(1 << k)), &s, &c);
+                  if (3 + 6 * k + d >= 32) v[3 + 6 * k + d - 32] = s;
+                  if (6 + 6 * k + d >= 32) v[6 + 6 * k + d - 32] = c;
+                }
+              }
+            }
+          }
+          if (half == 1) {
+            v[ONES_COL - 32] = 1.0f;
+            v[ONES_COL + 1 - 32] = 1.0f;
+          }
+#pragma unroll
+          for (int pc = 0; pc < 4; ++pc) {
+            uint4 q;
+            q.x = pack_f16x2(v[pc * 8 + 0], v[pc * 8 + 1]);
+            q.y = pack_f16x2(v[pc * 8 + 2], v[pc * 8 + 3]);
+            q.z = pack_f16x2(v[pc * 8 + 4], v[pc * 8 + 5]);
+            q.w = pack_f16x2(v[pc * 8 + 6], v[pc * 8 + 7]);
+            *reinterpret_cast<uint4*>(emb_tile + sw128_offset(row, half * 4 + pc)) = q;
+          }
+          // view direction (multires_views == 0): columns in_ch .. in_ch+2, written by the thread that owns them
+#pragma unroll
+          for (int d = 0; d < 3; ++d) {
+            const int col = in_ch + d;
+            if ((col >> 5) == half)
+              *reinterpret_cast<__half*>(emb_tile + sw128_offset(row, col >> 3) + (col & 7) * 2) = __float2half_rn(ray[8 + d]);
+          }
+        } else {
+          const float* x = a.x_embedded + p * a.in_all;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const int col = 32 * half + i;
+            if (col < a.in_all) v[i] = x[col];
+            if (col == ONES_COL || col == ONES_COL + 1) v[i] = 1.0f;
+          }
+#pragma unroll
+          for (int pc = 0; pc < 4; ++pc) {
+            uint4 q;
+            q.x = pack_f16x2(v[pc * 8 + 0], v[pc * 8 + 1]);
+            q.y = pack_f16x2(v[pc * 8 + 2], v[pc * 8 + 3]);
+            q.z = pack_f16x2(v[pc * 8 + 4], v[pc * 8 + 5]);
+            q.w = pack_f16x2(v[pc * 8 + 6], v[pc * 8 + 7]);
+            *reinterpret_cast<uint4*>(emb_tile + sw128_offset(row, half * 4 + pc)) = q;
+          }
+        }
+      }
+      signal_a_ready();
+
+      float alpha = 0.f;
+      for (int l = 0; l < plan.n_layers; ++l) {
+        const int kind = plan.layers[l].kind, relu = plan.layers[l].relu;
+        mbar_wait(my_acc, acc_phase);
+        acc_phase ^= 1;
+        tc_fence_after();
+        if (kind != 3) {
+          // hidden / feature layer: this thread's 128 accumulator columns -> A chunks 2*half, 2*half+1
+          uint32_t rbuf[2][32];
+          const uint32_t t_col = t_lane + half * 128;
+          tmem_ld32(t_col, rbuf[0]);
+#pragma unroll
+          for (int c4 = 0; c4 < 4; ++c4) {
+            uint32_t* r = rbuf[c4 & 1];
+            tmem_ld_wait();
+            if (c4 + 1 < 4) tmem_ld32(t_col + (c4 + 1) * 32, rbuf[(c4 + 1) & 1]);
+            uint8_t* chunk = a_tile + (2 * half + (c4 >> 1)) * CHUNK_BYTES;
+#pragma unroll
+            for (int pc = 0; pc < 4; ++pc) {
+              uint4 q;
+              if (relu) {
+                q.x = pack_relu_f16x2(r[pc * 8 + 0], r[pc * 8 + 1]);
+                q.y = pack_relu_f16x2(r[pc * 8 + 2], r[pc * 8 + 3]);
+                q.z = pack_relu_f16x2(r[pc * 8 + 4], r[pc * 8 + 5]);
+                q.w = pack_relu_f16x2(r[pc * 8 + 6], r[pc * 8 + 7]);
+              } else {
+                q.x = pack_plain_f16x2(r[pc * 8 + 0], r[pc * 8 + 1]);
+                q.y = pack_plain_f16x2(r[pc * 8 + 2], r[pc * 8 + 3]);
+                q.z = pack_plain_f16x2(r[pc * 8 + 4], r[pc * 8 + 5]);
+                q.w = pack_plain_f16x2(r[pc * 8 + 6], r[pc * 8 + 7]);
+              }
+              *reinterpret_cast<uint4*>(chunk + sw128_offset(row, (c4 & 1) * 4 + pc)) = q;
+            }
+          }
+          if (kind == 1 && half == 0) {
+            // alpha_linear on the un-rounded fp32 activations of the last hidden layer (H:233): the half-0 thread of
+            // each row walks all 256 columns once more
+#pragma unroll 1
+            for (int c8 = 0; c8 < W / 32; ++c8) {
+              uint32_t r[32];
+              tmem_ld32(t_lane + c8 * 32, r);
+              tmem_ld_wait();
+              const float* wa = tail->w_alpha + c8 * 32;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) alpha = fmaf(fmaxf(__uint_as_float(r[j]), 0.f), __ldg(wa + j), alpha);
+            }
+          }
+          signal_a_ready();
+        } else {
+          // views layer (N = 128) + rgb_linear + output, done by the half-0 thread of each row      H:238-242
+          if (half == 0) {
+            float cr = 0.f, cg = 0.f, cb = 0.f;
+#pragma unroll 1
+            for (int c4 = 0; c4 < 4; ++c4) {
+              uint32_t r[32];
+              tmem_ld32(t_lane + c4 * 32, r);
+              tmem_ld_wait();
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                float h = fmaxf(__uint_as_float(r[j]), 0.f);
+                float4 w = __ldg(tail->w_rgb + c4 * 32 + j);
+                cr = fmaf(h, w.x, cr);
+                cg = fmaf(h, w.y, cg);
+                cb = fmaf(h, w.z, cb);
+              }
+            }
+            if (live) {
+              float al = alpha + __ldg(&tail->b_alpha);
+              a.out[p_raw] = make_float4(cr + __ldg(&tail->b_rgb[0]), cg + __ldg(&tail->b_rgb[1]),
+                                         cb + __ldg(&tail->b_rgb[2]), softplus_beta10(al));
+            }
+          }
+          tc_fence_before();
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_pair(tmem_base, 512);
+  }
+}
+
 // ---- weight packing ---------------------------------------------------------------------------------
 __device__ __forceinline__ void split_f16(float b, __half* hi, __half* lo) {
   *hi = __float2half_rn(b);
@@ -812,6 +1151,15 @@ int mlp_tc_forward(const scade_net& net, const float* rays, int ray_stride, cons
   using KernelFn = void (*)(const tc::FwdArgs, const tc::NetPlan);
   KernelFn kern = pair ? (ping ? (KernelFn)tc::nerf_mlp_tc_kernel<true, true> : (KernelFn)tc::nerf_mlp_tc_kernel<true, false>)
                        : (ping ? (KernelFn)tc::nerf_mlp_tc_kernel<false, true> : (KernelFn)tc::nerf_mlp_tc_kernel<false, false>);
+  static const bool use_pp = []() {
+    const char* e = getenv("SCADE_TC_PP");
+    return !(e && e[0] == '0');
+  }();
+  int threads = tc::THREADS;
+  if (pair && use_pp) {
+    kern = (KernelFn)tc::nerf_mlp_tc_pp_kernel;
+    threads = tc::PP_THREADS;
+  }
   static bool attr_set = false;
   if (!attr_set) {
     SCADE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
@@ -835,7 +1183,7 @@ int mlp_tc_forward(const scade_net& net, const float* rays, int ray_stride, cons
     int clusters = (int)std::min<int64_t>(n_steps, num_sms() / 2);
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(2 * clusters);
-    cfg.blockDim = dim3(tc::THREADS);
+    cfg.blockDim = dim3(threads);
     cfg.dynamicSmemBytes = tc::SMEM_BYTES;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
