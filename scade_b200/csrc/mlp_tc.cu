@@ -29,6 +29,7 @@
 //     -> st.shared only.
 //   * CTAs run as clusters of 2: each CTA bulk-copies half of every weight stage and multicasts it to both, so
 //     L2->SMEM weight traffic per SM is halved again (the v1 kernel was L2-bound at ~6 TB/s during MMA phases).
+#include <cuda.h>
 #include <cuda_fp16.h>
 
 #include <algorithm>
@@ -131,6 +132,15 @@ __device__ __forceinline__ void bulk_g2s_mcast(uint32_t dst, const void* src, ui
   asm volatile(
       "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(dst),
       "l"(src), "r"(bytes), "r"(bar), "h"(mask)
+      : "memory");
+}
+// 2D tiled TMA load issued by either CTA of an SM pair; the transaction bytes are credited to the LEADER CTA's
+// mbarrier (its address is this CTA's barrier address with the pair's peer bit cleared), so the leader's MMA warp
+// sees both halves of a weight stage on one barrier without a relay hop.
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const void* tmap, int32_t c0, int32_t c1, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(tmap), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1)
       : "memory");
 }
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -309,6 +319,7 @@ struct FwdArgs {
   int multires, multires_views;
   float4* out;
   int64_t n_pairs;
+  int dbg;              // timing ablations only (results are WRONG when set): 1 = skip peer_full waits, 2 = skip a_ready waits
 };
 
 // kPair == false: every CTA is independent (cta_group::1, M=128 MMAs, both N halves of every weight block).
@@ -672,7 +683,8 @@ constexpr int PP_EPI_WARPS = 16;
 constexpr int PP_THREADS = 128 + PP_EPI_WARPS * 32;
 
 __global__ void __launch_bounds__(PP_THREADS, 1) nerf_mlp_tc_pp_kernel(const __grid_constant__ FwdArgs a,
-                                                                       const __grid_constant__ NetPlan plan) {
+                                                                       const __grid_constant__ NetPlan plan,
+                                                                       const __grid_constant__ CUtensorMap tmap) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const uint32_t sbase = smem_u32(smem);
@@ -705,26 +717,18 @@ __global__ void __launch_bounds__(PP_THREADS, 1) nerf_mlp_tc_pp_kernel(const __g
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0 || warp == 2) {
-    // warp 0: TMA producer of this CTA's half stages (every stage once per layer).
-    // warp 2 (non-leader CTA): relay -- forwards "my stage has landed" to the leader's peer_full barrier.
-    const bool is_relay = warp == 2;
-    if (lane == 0 && (!is_relay || cta_rank != 0)) {
+  if (warp == 0) {
+    // TMA producer of this CTA's half stages (every stage once per layer).  The packed stream is addressed through a 2D
+    // tensor map ([rows of 128 B] x 128 rows per stage); completion of BOTH CTAs' copies lands on the leader's barrier.
+    if (lane == 0) {
       uint32_t stage = 0, phase = 0;
-      const uint32_t leader_peer_full = map_to_cta(bar_peer_full, 0);
       for (int64_t step = unit0; step < n_steps; step += n_units) {
         for (int l = 0; l < plan.n_layers; ++l) {
           const int first = plan.first_stage[l], last = first + plan.n_stages[l];
           for (int s = first + (int)cta_rank; s < last; s += 2) {
-            if (!is_relay) {
-              mbar_wait(bar_empty + 8 * stage, phase ^ 1);
-              mbar_expect_tx(bar_full + 8 * stage, STAGE_BYTES);
-              bulk_g2s(sbase + OFF_STAGE + stage * STAGE_BYTES, a.packed + (size_t)s * STAGE_BYTES, STAGE_BYTES,
-                       bar_full + 8 * stage);
-            } else {
-              mbar_wait(bar_full + 8 * stage, phase);
-              mbar_arrive_remote(leader_peer_full + 8 * stage);
-            }
+            mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+            if (cta_rank == 0) mbar_expect_tx(bar_full + 8 * stage, 2 * STAGE_BYTES);
+            tma_load_2d_pair(sbase + OFF_STAGE + stage * STAGE_BYTES, &tmap, 0, s * STAGE_N, bar_full + 8 * stage);
             if (++stage == NUM_STAGES) { stage = 0; phase ^= 1; }
           }
         }
@@ -745,8 +749,7 @@ __global__ void __launch_bounds__(PP_THREADS, 1) nerf_mlp_tc_pp_kernel(const __g
           // one (stage, tile): wait for the slot in both CTAs, issue its MMAs for super-tile t, optionally release it
           auto consume_at = [&](int t, uint32_t& slot_ref, uint32_t& ph_ref, int i, bool release) {
             const uint32_t sl = slot_ref, p = ph_ref;
-            mbar_wait(bar_full + 8 * sl, p);
-            mbar_wait(bar_peer_full + 8 * sl, p);
+            mbar_wait(bar_full + 8 * sl, p);                 // both CTAs' halves of the stage have landed
             tc_fence_after();
             if (elect_one()) {
               const uint64_t b_desc = desc_hi | (uint64_t)(((sbase + OFF_STAGE + sl * STAGE_BYTES) & 0x3FFFF) >> 4);
@@ -1156,13 +1159,11 @@ int mlp_tc_forward(const scade_net& net, const float* rays, int ray_stride, cons
     return !(e && e[0] == '0');
   }();
   int threads = tc::THREADS;
-  if (pair && use_pp) {
-    kern = (KernelFn)tc::nerf_mlp_tc_pp_kernel;
-    threads = tc::PP_THREADS;
-  }
+  const bool pp = pair && use_pp;
   static bool attr_set = false;
   if (!attr_set) {
     SCADE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
+    SCADE_CUDA(cudaFuncSetAttribute(tc::nerf_mlp_tc_pp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
     attr_set = true;
   }
   tc::NetPlan plan;
@@ -1178,19 +1179,50 @@ int mlp_tc_forward(const scade_net& net, const float* rays, int ray_stride, cons
   a.multires = net.desc.multires; a.multires_views = net.desc.multires_views;
   a.out = reinterpret_cast<float4*>(raw_out);
   a.n_pairs = ceil_div<int64_t>(a.P, tc::TILES * tc::TILE_M);
+  { const char* e = getenv("SCADE_TC_DBG"); a.dbg = e ? atoi(e) : 0; }
+  CUtensorMap tmap;
+  if (pp) {
+    // the packed stream as a 2D byte tensor: rows of 128 B (one swizzled K-major row), 128 rows per 16 KB stage
+    using EncodeFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeFn encode = nullptr;
+    if (!encode) {
+      void* fn = nullptr;
+      cudaDriverEntryPointQueryResult qres;
+      SCADE_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+      if (!fn || qres != cudaDriverEntryPointSuccess) {
+        set_error("cuTensorMapEncodeTiled is not available from the driver");
+        return SCADE_ERR_CUDA;
+      }
+      encode = reinterpret_cast<EncodeFn>(fn);
+    }
+    const cuuint64_t dims[2] = {128, (cuuint64_t)plan.stages_per_pass * tc::STAGE_N};
+    const cuuint64_t strides[1] = {128};
+    const cuuint32_t box[2] = {128, (cuuint32_t)tc::STAGE_N};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult r = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(net.packed_f16), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+      return SCADE_ERR_CUDA;
+    }
+  }
   if (pair) {
     int64_t n_steps = (a.n_pairs + 1) / 2;
     int clusters = (int)std::min<int64_t>(n_steps, num_sms() / 2);
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(2 * clusters);
-    cfg.blockDim = dim3(threads);
+    cfg.blockDim = dim3(pp ? tc::PP_THREADS : threads);
     cfg.dynamicSmemBytes = tc::SMEM_BYTES;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    SCADE_CUDA(cudaLaunchKernelEx(&cfg, kern, a, plan));
+    if (pp) SCADE_CUDA(cudaLaunchKernelEx(&cfg, tc::nerf_mlp_tc_pp_kernel, a, plan, tmap));
+    else SCADE_CUDA(cudaLaunchKernelEx(&cfg, kern, a, plan));
   } else {
     int grid = (int)std::min<int64_t>(a.n_pairs, num_sms());
     kern<<<grid, tc::THREADS, tc::SMEM_BYTES, st>>>(a, plan);
