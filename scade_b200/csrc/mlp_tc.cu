@@ -169,6 +169,12 @@ __device__ __forceinline__ uint32_t map_to_cta(uint32_t local_addr, uint32_t ran
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
+// Remote arrive without the cluster-scope release fence.  Used for "my A tile is written": the tile is consumed only by
+// this CTA's own tensor core (async proxy), for which fence.proxy.async has already been executed; the leader thread that
+// observes the arrival never reads the data itself.
+__device__ __forceinline__ void mbar_arrive_remote_relaxed(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
 // wait with cluster-scope acquire (the barrier receives arrivals from the peer CTA)
 __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
   asm volatile(
@@ -822,7 +828,7 @@ __global__ void __launch_bounds__(PP_THREADS, 1) nerf_mlp_tc_pp_kernel(const __g
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
-        if (cta_rank != 0) mbar_arrive_remote(aready_target);
+        if (cta_rank != 0) mbar_arrive_remote_relaxed(aready_target);
         else mbar_arrive(my_aready);
       }
     };
