@@ -94,10 +94,19 @@ int scade_mlp_forward_embedded(const scade_net* net, int precision, const float*
 
 /* Backward of either forward above (autograd of H:223-247, RS:985): d_out [P,4] -> gradients of all
  * parameter tensors, ACCUMULATED into grads[i] (HOST array of DEVICE pointers, same order/shape as
- * params).  Uses the stash a forward call with save_for_backward=1 left in `workspace`.
+ * params).  Uses the stash a forward call with save_for_backward=1 left in `workspace` (same precision).
+ * SCADE_PREC_TC_F16: dgrad chain and weight gradients on tcgen05 (fp16 operands, gradients scaled by a power of
+ * two taken from max|d_out|, fp32 accumulation and fp32 gradient tensors); grads must be 4-byte aligned fp32.
  * No gradient w.r.t. the inputs is produced (z samples are detached, RS:711). */
 int scade_mlp_backward(const scade_net* net, int precision, const float* d_out, int64_t P,
                        float* const* grads_host, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Diagnostic: byte offsets of the SCADE_PREC_TC_F16 training stash inside the workspace of a forward call with
+ * save_for_backward=1 (tests decode the stashed fp16 activations / gradients through it).  Fills out[0..n) with
+ * T (128-point tiles), D, total, emb, feat, hv, dzv, dzf, maskv, alpha, gs, h[8], dz[8], maskh[8]; returns the count.
+ * Every activation region is [T][chunks][128 rows][128 B]: the K-major SWIZZLE_128B image of a [128 points x 64
+ * features] fp16 tile (16-byte piece j of row r sits at r*128 + ((j ^ (r & 7)) << 4)). */
+int scade_mlp_tc_stash_layout(const scade_net_desc* desc, int64_t P, int64_t* out, int n);
 
 /* Embedder.embed (H:171-172): x [P,3] -> [P, 3 + 6*multires]. */
 int scade_embed(const float* x, int64_t P, int multires, float* out, void* stream);

@@ -109,16 +109,18 @@ extern "C" int scade_mlp_forward_embedded(const scade_net* net, int precision, c
 
 extern "C" int scade_mlp_backward(const scade_net* net, int precision, const float* d_out, int64_t P,
                                   float* const* grads_host, void* workspace, size_t workspace_bytes, void* stream) {
-  SCADE_TRY(check_net(net, SCADE_PREC_FP32));
+  SCADE_TRY(check_net(net, precision));
   SCADE_CHECK_ARG(d_out && grads_host && workspace && P >= 0, "mlp_backward: bad arguments");
   SCADE_CHECK_ARG((reinterpret_cast<uintptr_t>(d_out) & 15) == 0, "mlp_backward: d_out must be 16-byte aligned");
   for (int i = 0; i < num_param_tensors(net->desc); ++i) SCADE_CHECK_ARG(grads_host[i] != nullptr, "null gradient tensor %d", i);
-  if (precision != SCADE_PREC_FP32) {
-    set_error("mlp_backward: only SCADE_PREC_FP32 stashes activations for backward in this version");
-    return SCADE_ERR_UNSUPPORTED;
-  }
   if (P == 0) return SCADE_OK;
+  if (precision == SCADE_PREC_TC_F16) return mlp_tc_backward(*net, d_out, P, grads_host, workspace, workspace_bytes, as_stream(stream));
   return mlp_fp32_backward(*net, d_out, P, grads_host, workspace, workspace_bytes, as_stream(stream));
+}
+
+extern "C" int scade_mlp_tc_stash_layout(const scade_net_desc* desc, int64_t P, int64_t* out, int n) {
+  if (!desc || check_desc(*desc) != SCADE_OK || !mlp_tc_supported(*desc) || P < 0 || (n > 0 && !out)) return 0;
+  return mlp_tc_stash_layout(*desc, P, out, n);
 }
 
 extern "C" int scade_embed(const float* x, int64_t P, int multires, float* out, void* stream) {

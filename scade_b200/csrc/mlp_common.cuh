@@ -45,4 +45,8 @@ int mlp_tc_forward(const scade_net& net, const float* rays, int ray_stride, cons
                    int64_t N, int S, const float* bb_center, float bb_scale, float* raw_out, void* workspace,
                    size_t ws_bytes, int save, cudaStream_t st);
 
+int mlp_tc_backward(const scade_net& net, const float* d_out, int64_t P, float* const* grads, void* workspace, size_t ws_bytes,
+                    cudaStream_t st);
+int mlp_tc_stash_layout(const scade_net_desc& d, int64_t P, int64_t* out, int n);
+
 }  // namespace scade

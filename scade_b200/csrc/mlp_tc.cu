@@ -71,6 +71,7 @@ struct LayerDesc {
   int kind;               // 0 = hidden, 1 = last hidden (also computes alpha), 2 = feature, 3 = views (final)
   int bias_stage;         // 1: extra stages carry the bias (layer has no encoding K chunk)
   int n_out;              // output width (256, or 128 for the views layer)
+  int a_step;             // ping-pong issuer: K chunk i (after the encoding chunk) reads activation chunk a_step * i
 };
 
 struct NetPlan {
@@ -91,6 +92,7 @@ struct PackedTail {
 struct StageDesc {
   const float* W; int ld; int col0; int ncols; int dst_col0; int row0; int nrows;
   const float* bias; int bias_mode;   // 0 none; 1: cols 60/61 <- hi/lo of bias[row0+n]; 2: bias stage (both N halves)
+  int trans;                          // 1: stage element (n, k) = W[(col0 + k) * ld + row0 + n]  (dgrad: B = W^T)
 };
 struct PackPlan {
   int n_stages;
@@ -120,6 +122,31 @@ struct FwdArgs {
   float4* out;
   int64_t n_pairs;
   int dbg;              // timing ablations only (results are WRONG when set): 1 = skip peer_full waits, 2 = skip a_ready waits
+};
+
+// Activation / gradient stash of the tensor-core training path (workspace of a forward call with save_for_backward=1).
+// Every activation region is an array of 16 KB "chunks": the exact shared-memory image of a [128 points x 64 features]
+// fp16 tile in the K-major SWIZZLE_128B layout the forward MMAs consume -- which, read with points as the K dimension,
+// is also the canonical MN-major SWIZZLE_128B operand tile of the weight-gradient MMAs.  T = number of 128-point tiles.
+struct TrainLayout {
+  long long T;
+  int D, pad;
+  unsigned long long emb;        // [T][1]   encoding chunk (gamma(x), view dir, two 1.0 columns)
+  unsigned long long feat;       // [T][4]   feature_linear output (no activation)
+  unsigned long long hv;         // [T][2]   views layer output (post-ReLU)
+  unsigned long long dzv;        // [T][2]   d loss / d (views pre-activation), scaled
+  unsigned long long dzf;        // [T][4]   d loss / d feature
+  unsigned long long maskv;      // [T][128] uint4: sign bits of the views pre-activations (sign_mask32 order)
+  unsigned long long alpha;      // [T*128]  fp32 alpha pre-activation (H:233)
+  unsigned long long gs;         // 64 uint32: [0] = bit pattern of max |d_out|
+  unsigned long long total;
+  unsigned long long h[8];       // [T][4]   output of pts_linears[l] (post-ReLU)
+  unsigned long long dz[8];      // [T][4]   d loss / d (pre-activation of pts_linears[l]), scaled
+  unsigned long long maskh[8];   // [T][128][2] uint4: sign bits of pts_linears[l] pre-activations
+};
+struct StashArgs {
+  uint8_t* ws;
+  TrainLayout L;
 };
 
 // kPair == false: every CTA is independent (cta_group::1, M=128 MMAs, both N halves of every weight block).
@@ -482,9 +509,106 @@ __global__ void __launch_bounds__(THREADS, 1) nerf_mlp_tc_kernel(const __grid_co
 constexpr int PP_EPI_WARPS = 16;
 constexpr int PP_THREADS = 128 + PP_EPI_WARPS * 32;
 
+// ---- roles shared by the ping-pong forward kernel and the dgrad kernel ---------------------------------------------
+// TMA producer of this CTA's half stages (every stage once per layer).  The packed stream is addressed through a 2D
+// tensor map ([rows of 128 B] x 128 rows per stage); completion of BOTH CTAs' copies lands on the leader's barrier.
+__device__ __forceinline__ void pp_weight_producer(const NetPlan& plan, const CUtensorMap* tmap, uint32_t sbase,
+                                                   uint32_t bar_full, uint32_t bar_empty, uint32_t cta_rank, int64_t unit0,
+                                                   int64_t n_steps, int64_t n_units) {
+  uint32_t stage = 0, phase = 0;
+  for (int64_t step = unit0; step < n_steps; step += n_units) {
+    for (int l = 0; l < plan.n_layers; ++l) {
+      const int first = plan.first_stage[l], last = first + plan.n_stages[l];
+      for (int s = first + (int)cta_rank; s < last; s += 2) {
+        mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+        if (cta_rank == 0) mbar_expect_tx(bar_full + 8 * stage, 2 * STAGE_BYTES);
+        tma_load_2d_pair(sbase + OFF_STAGE + stage * STAGE_BYTES, tmap, 0, s * STAGE_N, bar_full + 8 * stage);
+        if (++stage == NUM_STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  }
+}
+
+// MMA issuer of the leader CTA (whole warp walks the loops, one elected lane issues).  Super-tile 0 runs up to
+// NUM_STAGES ring slots ahead of super-tile 1, whose MMAs release the slots.
+__device__ __forceinline__ void pp_mma_issuer(const NetPlan& plan, uint32_t sbase, uint32_t tmem_base, uint32_t bar_full,
+                                              uint32_t bar_empty, uint32_t bar_acc, uint32_t bar_aready, int64_t unit0,
+                                              int64_t n_steps, int64_t n_units) {
+  constexpr uint64_t desc_hi = ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61) | ((uint64_t)1 << 16);
+  // ring position of each super-tile (tile 1 trails tile 0)
+  uint32_t slot0 = 0, slot1 = 0, ph0 = 0, ph1 = 0, a_ph0 = 0, a_ph1 = 0;
+  for (int64_t step = unit0; step < n_steps; step += n_units) {
+    for (int l = 0; l < plan.n_layers; ++l) {
+      const int n_k = plan.layers[l].n_k, bias_stage = plan.layers[l].bias_stage;
+      const int n_own = n_k + bias_stage;                      // this layer's stages per CTA (<= 5)
+      const int has_emb = plan.layers[l].a_src[0] == SRC_EMB;
+      const int a_step = plan.layers[l].a_step;                // A chunk of K chunk i (after the encoding chunk) = a_step * i
+      const uint32_t idesc = make_idesc(2 * TILE_M, plan.layers[l].n_out);
+      // one (stage, tile): wait for the slot in both CTAs, issue its MMAs for super-tile t, optionally release it
+      auto consume_at = [&](int t, uint32_t& slot_ref, uint32_t& ph_ref, int i, bool release) {
+        const uint32_t sl = slot_ref, p = ph_ref;
+        mbar_wait(bar_full + 8 * sl, p);                 // both CTAs' halves of the stage have landed
+        tc_fence_after();
+        if (elect_one()) {
+          const uint64_t b_desc = desc_hi | (uint64_t)(((sbase + OFF_STAGE + sl * STAGE_BYTES) & 0x3FFFF) >> 4);
+          const uint32_t d_addr = tmem_base + t * W;
+          if (i < n_k) {
+            const bool emb = has_emb && i == 0;
+            const uint32_t a_addr = emb ? sbase + OFF_EMB + t * CHUNK_BYTES
+                                        : sbase + OFF_A + (t * 4 + (i - has_emb) * a_step) * CHUNK_BYTES;
+            const uint64_t a_desc = desc_hi | (uint64_t)((a_addr & 0x3FFFF) >> 4);
+#pragma unroll
+            for (int ks = 0; ks < KCHUNK / 16; ++ks)
+              mma_f16_ss_pair(d_addr, a_desc + 2 * ks, b_desc + 2 * ks, idesc, (i | ks) != 0 ? 1u : 0u);
+          } else {
+            // bias stage: A = K-step 3 of the encoding chunk (the two 1.0 columns), B = K-step 0 (bias hi/lo)
+            const uint64_t a_desc = desc_hi | (uint64_t)(((sbase + OFF_EMB + t * CHUNK_BYTES + 3 * 32) & 0x3FFFF) >> 4);
+            mma_f16_ss_pair(d_addr, a_desc, b_desc, idesc, 1u);
+          }
+          if (release) mma_commit_pair(bar_empty + 8 * sl, (uint16_t)3);
+        }
+        __syncwarp();
+        if (++slot_ref == NUM_STAGES) { slot_ref = 0; ph_ref ^= 1; }
+      };
+      auto consume = [&](int t, int i, bool release) {
+        if (t == 0) consume_at(0, slot0, ph0, i, release);
+        else consume_at(1, slot1, ph1, i, release);
+      };
+      auto wait_a = [&](int t) {
+        if (t == 0) { mbar_wait(bar_aready, a_ph0); a_ph0 ^= 1; }
+        else { mbar_wait(bar_aready + 8, a_ph1); a_ph1 ^= 1; }
+        tc_fence_after();
+      };
+      auto publish = [&](int t) {
+        if (elect_one()) mma_commit_pair(bar_acc + 8 * t, (uint16_t)3);
+        __syncwarp();
+      };
+      // tile 0 first (at most NUM_STAGES ahead of tile 1), then tile 1, which releases the slots
+      wait_a(0);
+      const int lead = n_own < NUM_STAGES ? n_own : NUM_STAGES;
+      for (int i = 0; i < lead; ++i) consume(0, i, false);
+      int i1 = 0;
+      if (n_own > NUM_STAGES) {                                // 5-stage layer: tile 1 must free a slot first
+        wait_a(1);
+        consume(1, 0, true);
+        i1 = 1;
+        consume(0, NUM_STAGES, false);
+      }
+      publish(0);
+      if (i1 == 0) wait_a(1);
+      for (int i = i1; i < n_own; ++i) consume(1, i, true);
+      publish(1);
+    }
+  }
+}
+
+// kStash: additionally write every layer's fp16 output chunk (TMA bulk store of the shared-memory image the next layer's
+// MMAs read anyway), the ReLU sign masks and the alpha pre-activation to the training stash.
+template <bool kStash>
 __global__ void __launch_bounds__(PP_THREADS, 1) nerf_mlp_tc_pp_kernel(const __grid_constant__ FwdArgs a,
                                                                        const __grid_constant__ NetPlan plan,
-                                                                       const __grid_constant__ CUtensorMap tmap) {
+                                                                       const __grid_constant__ CUtensorMap tmap,
+                                                                       const __grid_constant__ StashArgs sa) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const uint32_t sbase = smem_u32(smem);
@@ -518,91 +642,9 @@ __global__ void __launch_bounds__(PP_THREADS, 1) nerf_mlp_tc_pp_kernel(const __g
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // TMA producer of this CTA's half stages (every stage once per layer).  The packed stream is addressed through a 2D
-    // tensor map ([rows of 128 B] x 128 rows per stage); completion of BOTH CTAs' copies lands on the leader's barrier.
-    if (lane == 0) {
-      uint32_t stage = 0, phase = 0;
-      for (int64_t step = unit0; step < n_steps; step += n_units) {
-        for (int l = 0; l < plan.n_layers; ++l) {
-          const int first = plan.first_stage[l], last = first + plan.n_stages[l];
-          for (int s = first + (int)cta_rank; s < last; s += 2) {
-            mbar_wait(bar_empty + 8 * stage, phase ^ 1);
-            if (cta_rank == 0) mbar_expect_tx(bar_full + 8 * stage, 2 * STAGE_BYTES);
-            tma_load_2d_pair(sbase + OFF_STAGE + stage * STAGE_BYTES, &tmap, 0, s * STAGE_N, bar_full + 8 * stage);
-            if (++stage == NUM_STAGES) { stage = 0; phase ^= 1; }
-          }
-        }
-      }
-    }
+    if (lane == 0) pp_weight_producer(plan, &tmap, sbase, bar_full, bar_empty, cta_rank, unit0, n_steps, n_units);
   } else if (warp == 1) {
-    // ================= MMA issuer (leader CTA) =================
-    if (cta_rank == 0) {
-      constexpr uint64_t desc_hi = ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61) | ((uint64_t)1 << 16);
-      // ring position of each super-tile (tile 1 trails tile 0)
-      uint32_t slot0 = 0, slot1 = 0, ph0 = 0, ph1 = 0, a_ph0 = 0, a_ph1 = 0;
-      for (int64_t step = unit0; step < n_steps; step += n_units) {
-        for (int l = 0; l < plan.n_layers; ++l) {
-          const int n_k = plan.layers[l].n_k, bias_stage = plan.layers[l].bias_stage;
-          const int n_own = n_k + bias_stage;                      // this layer's stages per CTA (<= 5)
-          const int has_emb = plan.layers[l].a_src[0] == SRC_EMB;
-          const uint32_t idesc = make_idesc(2 * TILE_M, plan.layers[l].n_out);
-          // one (stage, tile): wait for the slot in both CTAs, issue its MMAs for super-tile t, optionally release it
-          auto consume_at = [&](int t, uint32_t& slot_ref, uint32_t& ph_ref, int i, bool release) {
-            const uint32_t sl = slot_ref, p = ph_ref;
-            mbar_wait(bar_full + 8 * sl, p);                 // both CTAs' halves of the stage have landed
-            tc_fence_after();
-            if (elect_one()) {
-              const uint64_t b_desc = desc_hi | (uint64_t)(((sbase + OFF_STAGE + sl * STAGE_BYTES) & 0x3FFFF) >> 4);
-              const uint32_t d_addr = tmem_base + t * W;
-              if (i < n_k) {
-                const bool emb = has_emb && i == 0;
-                const uint32_t a_addr = emb ? sbase + OFF_EMB + t * CHUNK_BYTES
-                                            : sbase + OFF_A + (t * 4 + (i - has_emb)) * CHUNK_BYTES;
-                const uint64_t a_desc = desc_hi | (uint64_t)((a_addr & 0x3FFFF) >> 4);
-#pragma unroll
-                for (int ks = 0; ks < KCHUNK / 16; ++ks)
-                  mma_f16_ss_pair(d_addr, a_desc + 2 * ks, b_desc + 2 * ks, idesc, (i | ks) != 0 ? 1u : 0u);
-              } else {
-                // bias stage: A = K-step 3 of the encoding chunk (the two 1.0 columns), B = K-step 0 (bias hi/lo)
-                const uint64_t a_desc = desc_hi | (uint64_t)(((sbase + OFF_EMB + t * CHUNK_BYTES + 3 * 32) & 0x3FFFF) >> 4);
-                mma_f16_ss_pair(d_addr, a_desc, b_desc, idesc, 1u);
-              }
-              if (release) mma_commit_pair(bar_empty + 8 * sl, (uint16_t)3);
-            }
-            __syncwarp();
-            if (++slot_ref == NUM_STAGES) { slot_ref = 0; ph_ref ^= 1; }
-          };
-          auto consume = [&](int t, int i, bool release) {
-            if (t == 0) consume_at(0, slot0, ph0, i, release);
-            else consume_at(1, slot1, ph1, i, release);
-          };
-          auto wait_a = [&](int t) {
-            if (t == 0) { mbar_wait(bar_aready, a_ph0); a_ph0 ^= 1; }
-            else { mbar_wait(bar_aready + 8, a_ph1); a_ph1 ^= 1; }
-            tc_fence_after();
-          };
-          auto publish = [&](int t) {
-            if (elect_one()) mma_commit_pair(bar_acc + 8 * t, (uint16_t)3);
-            __syncwarp();
-          };
-          // tile 0 first (at most NUM_STAGES ahead of tile 1), then tile 1, which releases the slots
-          wait_a(0);
-          const int lead = n_own < NUM_STAGES ? n_own : NUM_STAGES;
-          for (int i = 0; i < lead; ++i) consume(0, i, false);
-          int i1 = 0;
-          if (n_own > NUM_STAGES) {                                // 5-stage layer: tile 1 must free a slot first
-            wait_a(1);
-            consume(1, 0, true);
-            i1 = 1;
-            consume(0, NUM_STAGES, false);
-          }
-          publish(0);
-          if (i1 == 0) wait_a(1);
-          for (int i = i1; i < n_own; ++i) consume(1, i, true);
-          publish(1);
-        }
-      }
-    }
+    if (cta_rank == 0) pp_mma_issuer(plan, sbase, tmem_base, bar_full, bar_empty, bar_acc, bar_aready, unit0, n_steps, n_units);
   } else if (warp >= 4) {
     // ================= prologue / epilogue warps: thread == one row x 128 columns =================
     const int ew = warp - 4;
@@ -632,6 +674,7 @@ __global__ void __launch_bounds__(PP_THREADS, 1) nerf_mlp_tc_pp_kernel(const __g
       const int64_t p_raw = pair * (TILES * TILE_M) + tile * TILE_M + row;
       const bool live = p_raw < a.P;
       const int64_t p = live ? p_raw : a.P - 1;
+      const int64_t tile_g = 2 * pair + tile;            // 128-point tile index in the stash
 
       // ---- positional encoding: this thread writes encoding-chunk columns [32*half, 32*half + 32) of its row ----
       {
@@ -722,13 +765,23 @@ __global__ void __launch_bounds__(PP_THREADS, 1) nerf_mlp_tc_pp_kernel(const __g
         if (kind != 3) {
           // hidden / feature layer: this thread's 128 accumulator columns -> A chunks 2*half, 2*half+1
           uint32_t rbuf[2][32];
+          uint32_t sgn[4];
           const uint32_t t_col = t_lane + half * 128;
           tmem_ld32(t_col, rbuf[0]);
+          if (kStash) {
+            if (l == 0 && half == 0 && lane == 0) {       // the encoding chunk of this tile is complete: stash this warp's 32 rows
+              bulk_s2g(sa.ws + sa.L.emb + (size_t)tile_g * CHUNK_BYTES + quarter * 4096, smem_u32(emb_tile) + quarter * 4096, 4096);
+              bulk_commit();
+            }
+            if (lane == 0) bulk_wait_read0();             // earlier stash stores no longer read the rows overwritten below
+            __syncwarp();
+          }
 #pragma unroll
           for (int c4 = 0; c4 < 4; ++c4) {
             uint32_t* r = rbuf[c4 & 1];
             tmem_ld_wait();
             if (c4 + 1 < 4) tmem_ld32(t_col + (c4 + 1) * 32, rbuf[(c4 + 1) & 1]);
+            if (kStash) sgn[c4] = sign_mask32(r);
             uint8_t* chunk = a_tile + (2 * half + (c4 >> 1)) * CHUNK_BYTES;
 #pragma unroll
             for (int pc = 0; pc < 4; ++pc) {
@@ -761,10 +814,27 @@ __global__ void __launch_bounds__(PP_THREADS, 1) nerf_mlp_tc_pp_kernel(const __g
             }
           }
           signal_a_ready();
+          if (kStash) {
+            if (relu)
+              *reinterpret_cast<uint4*>(sa.ws + sa.L.maskh[l] + ((size_t)(tile_g * TILE_M + row) * 2 + half) * 16) =
+                  make_uint4(sgn[0], sgn[1], sgn[2], sgn[3]);
+            if (lane == 0) {
+              uint8_t* dst = sa.ws + (kind == 2 ? sa.L.feat : sa.L.h[l]) + (size_t)(tile_g * 4 + 2 * half) * CHUNK_BYTES + quarter * 4096;
+              const uint32_t src = smem_u32(a_tile) + 2 * half * CHUNK_BYTES + quarter * 4096;
+              bulk_s2g(dst, src, 4096);
+              bulk_s2g(dst + CHUNK_BYTES, src + CHUNK_BYTES, 4096);
+              bulk_commit();
+            }
+          }
         } else {
           // views layer (N = 128) + rgb_linear + output, done by the half-0 thread of each row      H:238-242
           if (half == 0) {
             float cr = 0.f, cg = 0.f, cb = 0.f;
+            uint32_t sgn[4];
+            if (kStash) {
+              if (lane == 0) bulk_wait_read0();           // A chunks 0/1 (feature, fully consumed by now) become the h_v staging area
+              __syncwarp();
+            }
 #pragma unroll 1
             for (int c4 = 0; c4 < 4; ++c4) {
               uint32_t r[32];
@@ -778,11 +848,39 @@ __global__ void __launch_bounds__(PP_THREADS, 1) nerf_mlp_tc_pp_kernel(const __g
                 cg = fmaf(h, w.y, cg);
                 cb = fmaf(h, w.z, cb);
               }
+              if (kStash) {
+                const uint32_t sg = sign_mask32(r);
+                sgn[0] = c4 == 0 ? sg : sgn[0]; sgn[1] = c4 == 1 ? sg : sgn[1];
+                sgn[2] = c4 == 2 ? sg : sgn[2]; sgn[3] = c4 == 3 ? sg : sgn[3];
+                uint8_t* chunk = a_tile + (c4 >> 1) * CHUNK_BYTES;
+#pragma unroll
+                for (int pc = 0; pc < 4; ++pc) {
+                  uint4 q;
+                  q.x = pack_relu_f16x2(r[pc * 8 + 0], r[pc * 8 + 1]);
+                  q.y = pack_relu_f16x2(r[pc * 8 + 2], r[pc * 8 + 3]);
+                  q.z = pack_relu_f16x2(r[pc * 8 + 4], r[pc * 8 + 5]);
+                  q.w = pack_relu_f16x2(r[pc * 8 + 6], r[pc * 8 + 7]);
+                  *reinterpret_cast<uint4*>(chunk + sw128_offset(row, (c4 & 1) * 4 + pc)) = q;
+                }
+              }
             }
+            const float al = alpha + __ldg(&tail->b_alpha);
             if (live) {
-              float al = alpha + __ldg(&tail->b_alpha);
               a.out[p_raw] = make_float4(cr + __ldg(&tail->b_rgb[0]), cg + __ldg(&tail->b_rgb[1]),
                                          cb + __ldg(&tail->b_rgb[2]), softplus_beta10(al));
+            }
+            if (kStash) {
+              *reinterpret_cast<uint4*>(sa.ws + sa.L.maskv + (size_t)(tile_g * TILE_M + row) * 16) = make_uint4(sgn[0], sgn[1], sgn[2], sgn[3]);
+              reinterpret_cast<float*>(sa.ws + sa.L.alpha)[tile_g * TILE_M + row] = al;
+              fence_proxy_async();
+              __syncwarp();
+              if (lane == 0) {
+                uint8_t* dst = sa.ws + sa.L.hv + (size_t)(tile_g * 2) * CHUNK_BYTES + quarter * 4096;
+                const uint32_t src = smem_u32(a_tile) + quarter * 4096;
+                bulk_s2g(dst, src, 4096);
+                bulk_s2g(dst + CHUNK_BYTES, src + CHUNK_BYTES, 4096);
+                bulk_commit();
+              }
             }
           }
           tc_fence_before();
@@ -791,6 +889,7 @@ __global__ void __launch_bounds__(PP_THREADS, 1) nerf_mlp_tc_pp_kernel(const __g
     }
   }
 
+  if (kStash && warp >= 4 && lane == 0) bulk_wait_all0();     // stash stores are complete before the CTA retires
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();
@@ -809,6 +908,7 @@ __device__ __forceinline__ void split_f16(float b, __half* hi, __half* lo) {
 __global__ void pack_kernel(const __grid_constant__ PackPlan plan, uint8_t* __restrict__ out) {
   if ((int)blockIdx.x == plan.n_stages) {
     // fp32 tail: rgb_linear as (r,g,b,0) per hidden column, alpha_linear, head biases
+    if (plan.w_alpha == nullptr) return;
     PackedTail* tail = reinterpret_cast<PackedTail*>(out + (size_t)plan.n_stages * STAGE_BYTES);
     for (int k = threadIdx.x; k < W / 2; k += blockDim.x)
       tail->w_rgb[k] = make_float4(plan.w_rgb[k], plan.w_rgb[W / 2 + k], plan.w_rgb[W + k], 0.f);
@@ -833,7 +933,9 @@ __global__ void pack_kernel(const __grid_constant__ PackPlan plan, uint8_t* __re
       }
     } else {
       int sc = k - sd.dst_col0;
-      if (n < sd.nrows && sc >= 0 && sc < sd.ncols) hv = __float2half_rn(sd.W[(int64_t)(sd.row0 + n) * sd.ld + sd.col0 + sc]);
+      if (n < sd.nrows && sc >= 0 && sc < sd.ncols)
+        hv = __float2half_rn(sd.trans ? sd.W[(int64_t)(sd.col0 + sc) * sd.ld + sd.row0 + n]
+                                      : sd.W[(int64_t)(sd.row0 + n) * sd.ld + sd.col0 + sc]);
       if (sd.bias_mode == 1 && n < sd.nrows && (k == ONES_COL || k == ONES_COL + 1)) {
         __half hi, lo;
         split_f16(sd.bias[sd.row0 + n], &hi, &lo);
@@ -863,7 +965,7 @@ static void build_plans(const scade_net& net, bool pair, NetPlan* np, PackPlan* 
   PackPlan Q{};
   auto add_stage = [&](const float* Wt, int ld, int col0, int ncols, int dst_col0, int row0, int nrows,
                        const float* bias, int bias_mode) {
-    StageDesc s{Wt, ld, col0, ncols, dst_col0, row0, nrows, bias, bias_mode};
+    StageDesc s{Wt, ld, col0, ncols, dst_col0, row0, nrows, bias, bias_mode, 0};
     Q.st[Q.n_stages++] = s;
   };
   auto add_layer = [&](const float* Wt, int fan_in, bool with_emb, int emb_col0, int emb_ncols, int emb_dst, int h_col0,
@@ -871,7 +973,7 @@ static void build_plans(const scade_net& net, bool pair, NetPlan* np, PackPlan* 
     LayerDesc L{};
     P.first_stage[P.n_layers] = Q.n_stages;
     L.n_halves = n_out / STAGE_N;
-    L.relu = relu; L.kind = kind; L.n_out = n_out;
+    L.relu = relu; L.kind = kind; L.n_out = n_out; L.a_step = 1;
     L.bias_stage = with_emb ? 0 : 1;
     int nk = 0;
     if (with_emb) L.a_src[nk++] = SRC_EMB;
@@ -916,6 +1018,116 @@ static int count_stages(const scade_net_desc& d, bool pair) {
   return n;
 }
 
+
+#include "mlp_tc_train.cuh"
+
+// ---- training: backward stream, stash layout ---------------------------------------------------------------------------
+// Backward weight stream (dgrad): layer j of the chain multiplies by W^T, so stage (K chunk kc, N half h) holds
+// B[n][k] = W[64 kc + k][col0 + 128 h + n].  Order: views, feature, pts_{D-1} .. pts_1 (pts_0 needs no input gradient).
+static int count_bwd_stages(const scade_net_desc& d) { return 4 + 8 + 8 * (d.D - 1); }
+
+static void build_bwd_plans(const scade_net& net, NetPlan* np, PackPlan* pp) {
+  const scade_net_desc& d = net.desc;
+  NetDims nd(d);
+  NetPlan P{};
+  PackPlan Q{};
+  auto add_layer = [&](const float* Wt, int ld, int n_out_fwd, int col0, int a_step) {
+    LayerDesc L{};
+    P.first_stage[P.n_layers] = Q.n_stages;
+    L.n_halves = 2; L.relu = 0; L.kind = 0; L.n_out = W; L.a_step = a_step; L.bias_stage = 0;
+    L.n_k = n_out_fwd / KCHUNK;
+    for (int kc = 0; kc < L.n_k; ++kc) {
+      L.a_src[kc] = kc * a_step;
+      for (int h = 0; h < 2; ++h) {
+        StageDesc sd{Wt, ld, 64 * kc, 64, 0, col0 + STAGE_N * h, STAGE_N, nullptr, 0, 1};
+        Q.st[Q.n_stages++] = sd;
+      }
+    }
+    P.n_stages[P.n_layers] = Q.n_stages - P.first_stage[P.n_layers];
+    P.layers[P.n_layers++] = L;
+  };
+  const int pv = 2 * d.D;
+  add_layer(net.params[pv], W + nd.in_views, W / 2, 0, 2);          // views_linears.0^T (feature columns)        H:235-238
+  add_layer(net.params[pv + 2], W, W, 0, 1);                        // feature_linear^T                           H:234
+  for (int i = d.D - 1; i >= 1; --i) {
+    const bool after_skip = (i - 1 == d.skip);                      // input = [input_pts, h]: h starts at column in_ch (H:230)
+    add_layer(net.params[2 * i], after_skip ? nd.in_ch + W : W, W, after_skip ? nd.in_ch : 0, 1);
+  }
+  P.stages_per_pass = Q.n_stages;
+  if (np) *np = P;
+  if (pp) *pp = Q;
+}
+
+static size_t fwd_stream_bytes(const scade_net_desc& d) {
+  return (size_t)count_stages(d, true) * STAGE_BYTES + align_up(sizeof(PackedTail), 1024);
+}
+
+static TrainLayout train_layout(const scade_net_desc& d, int64_t P) {
+  TrainLayout L{};
+  const int64_t n_pairs = ceil_div<int64_t>(P, TILES * TILE_M);
+  L.T = 4 * ((n_pairs + 1) / 2);
+  L.D = d.D;
+  unsigned long long off = 0;
+  auto chunks = [&](int per_tile) { unsigned long long o = off; off += (unsigned long long)L.T * per_tile * CHUNK_BYTES; return o; };
+  L.emb = chunks(1);
+  for (int l = 0; l < d.D; ++l) L.h[l] = chunks(4);
+  L.feat = chunks(4);
+  L.hv = chunks(2);
+  L.dzv = chunks(2);
+  L.dzf = chunks(4);
+  for (int l = 0; l < d.D; ++l) L.dz[l] = chunks(4);
+  for (int l = 0; l < d.D; ++l) { L.maskh[l] = off; off += (unsigned long long)L.T * TILE_M * 32; }
+  L.maskv = off; off += (unsigned long long)L.T * TILE_M * 16;
+  L.alpha = off; off += (unsigned long long)L.T * TILE_M * 4;
+  L.gs = off; off += 256;
+  L.total = off;
+  return L;
+}
+
+// the [rows x 128 B] view of a buffer of swizzled 128-byte rows, loaded in boxes of `box_rows` rows
+static int encode_rows_tmap(CUtensorMap* tmap, const void* base, size_t bytes, int box_rows) {
+  using EncodeFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeFn encode = nullptr;
+  if (!encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    SCADE_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    if (!fn || qres != cudaDriverEntryPointSuccess) {
+      set_error("cuTensorMapEncodeTiled is not available from the driver");
+      return SCADE_ERR_CUDA;
+    }
+    encode = reinterpret_cast<EncodeFn>(fn);
+  }
+  const cuuint64_t dims[2] = {128, (cuuint64_t)(bytes / 128)};
+  const cuuint64_t strides[1] = {128};
+  const cuuint32_t box[2] = {128, (cuuint32_t)box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  CUresult r = encode(tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(base), dims, strides, box, estr,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    return SCADE_ERR_CUDA;
+  }
+  return SCADE_OK;
+}
+
+static int launch_pair(const void* kern, int clusters, int threads, int smem, cudaStream_t st, void** args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(2 * clusters);
+  cfg.blockDim = dim3(threads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  SCADE_CUDA(cudaLaunchKernelExC(&cfg, kern, args));
+  return SCADE_OK;
+}
+
 }  // namespace tc
 
 bool mlp_tc_supported(const scade_net_desc& d) {
@@ -925,7 +1137,8 @@ bool mlp_tc_supported(const scade_net_desc& d) {
 }
 
 size_t mlp_tc_packed_bytes(const scade_net_desc& d) {
-  return (size_t)tc::count_stages(d, tc::use_pair()) * tc::STAGE_BYTES + align_up(sizeof(tc::PackedTail));
+  if (!tc::use_pair()) return (size_t)tc::count_stages(d, false) * tc::STAGE_BYTES + align_up(sizeof(tc::PackedTail));
+  return tc::fwd_stream_bytes(d) + (size_t)tc::count_bwd_stages(d) * tc::STAGE_BYTES;      // forward stream + tail | dgrad stream
 }
 
 int mlp_tc_pack(const scade_net& net, void* packed_out, cudaStream_t st) {
@@ -933,19 +1146,34 @@ int mlp_tc_pack(const scade_net& net, void* packed_out, cudaStream_t st) {
   tc::build_plans(net, tc::use_pair(), nullptr, &pp);
   tc::pack_kernel<<<pp.n_stages + 1, 256, 0, st>>>(pp, reinterpret_cast<uint8_t*>(packed_out));
   SCADE_LAUNCH_CHECK();
+  if (tc::use_pair()) {
+    tc::build_bwd_plans(net, nullptr, &pp);
+    tc::pack_kernel<<<pp.n_stages, 256, 0, st>>>(pp, reinterpret_cast<uint8_t*>(packed_out) + tc::fwd_stream_bytes(net.desc));
+    SCADE_LAUNCH_CHECK();
+  }
   return SCADE_OK;
 }
 
-size_t mlp_tc_workspace_bytes(const scade_net_desc&, int64_t, int) { return 256; }
+size_t mlp_tc_workspace_bytes(const scade_net_desc& d, int64_t P, int save) {
+  return save ? (size_t)tc::train_layout(d, P).total : 256;
+}
+
+int mlp_tc_stash_layout(const scade_net_desc& d, int64_t P, int64_t* out, int n) {
+  const tc::TrainLayout L = tc::train_layout(d, P);
+  int64_t v[64];
+  int k = 0;
+  v[k++] = L.T; v[k++] = L.D; v[k++] = (int64_t)L.total; v[k++] = (int64_t)L.emb; v[k++] = (int64_t)L.feat; v[k++] = (int64_t)L.hv;
+  v[k++] = (int64_t)L.dzv; v[k++] = (int64_t)L.dzf; v[k++] = (int64_t)L.maskv; v[k++] = (int64_t)L.alpha; v[k++] = (int64_t)L.gs;
+  for (int l = 0; l < 8; ++l) v[k++] = (int64_t)L.h[l];
+  for (int l = 0; l < 8; ++l) v[k++] = (int64_t)L.dz[l];
+  for (int l = 0; l < 8; ++l) v[k++] = (int64_t)L.maskh[l];
+  for (int i = 0; i < n && i < k; ++i) out[i] = v[i];
+  return k;
+}
 
 int mlp_tc_forward(const scade_net& net, const float* rays, int ray_stride, const float* z, const float* x_embedded,
                    int64_t N, int S, const float* bb_center, float bb_scale, float* raw_out, void* workspace,
                    size_t ws_bytes, int save, cudaStream_t st) {
-  (void)workspace; (void)ws_bytes;
-  if (save) {
-    set_error("SCADE_PREC_TC_F16 forward does not stash activations for backward in this version");
-    return SCADE_ERR_UNSUPPORTED;
-  }
   const bool pair = tc::use_pair();
   static const bool ping = []() {
     const char* e = getenv("SCADE_TC_PING");
@@ -958,12 +1186,16 @@ int mlp_tc_forward(const scade_net& net, const float* rays, int ray_stride, cons
     const char* e = getenv("SCADE_TC_PP");
     return !(e && e[0] == '0');
   }();
-  int threads = tc::THREADS;
   const bool pp = pair && use_pp;
+  if (save && !pp) {
+    set_error("SCADE_PREC_TC_F16 training needs the SM-pair ping-pong kernel (unset SCADE_TC_PAIR / SCADE_TC_PP)");
+    return SCADE_ERR_UNSUPPORTED;
+  }
   static bool attr_set = false;
   if (!attr_set) {
     SCADE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
-    SCADE_CUDA(cudaFuncSetAttribute(tc::nerf_mlp_tc_pp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
+    SCADE_CUDA(cudaFuncSetAttribute(tc::nerf_mlp_tc_pp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
+    SCADE_CUDA(cudaFuncSetAttribute(tc::nerf_mlp_tc_pp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
     attr_set = true;
   }
   tc::NetPlan plan;
@@ -980,54 +1212,132 @@ int mlp_tc_forward(const scade_net& net, const float* rays, int ray_stride, cons
   a.out = reinterpret_cast<float4*>(raw_out);
   a.n_pairs = ceil_div<int64_t>(a.P, tc::TILES * tc::TILE_M);
   { const char* e = getenv("SCADE_TC_DBG"); a.dbg = e ? atoi(e) : 0; }
-  CUtensorMap tmap;
   if (pp) {
     // the packed stream as a 2D byte tensor: rows of 128 B (one swizzled K-major row), 128 rows per 16 KB stage
-    using EncodeFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-    static EncodeFn encode = nullptr;
-    if (!encode) {
-      void* fn = nullptr;
-      cudaDriverEntryPointQueryResult qres;
-      SCADE_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
-      if (!fn || qres != cudaDriverEntryPointSuccess) {
-        set_error("cuTensorMapEncodeTiled is not available from the driver");
-        return SCADE_ERR_CUDA;
+    CUtensorMap tmap;
+    SCADE_TRY(tc::encode_rows_tmap(&tmap, net.packed_f16, (size_t)plan.stages_per_pass * tc::STAGE_BYTES, tc::STAGE_N));
+    tc::StashArgs sa{};
+    if (save) {
+      sa.L = tc::train_layout(net.desc, a.P);
+      if (workspace == nullptr || ws_bytes < sa.L.total) {
+        set_error("mlp_forward (tc_f16, save_for_backward): workspace %zu < %llu bytes", ws_bytes, sa.L.total);
+        return SCADE_ERR_WORKSPACE;
       }
-      encode = reinterpret_cast<EncodeFn>(fn);
+      if (reinterpret_cast<uintptr_t>(workspace) & 127) {
+        set_error("mlp_forward (tc_f16, save_for_backward): workspace must be 128-byte aligned");
+        return SCADE_ERR_INVALID_ARGUMENT;
+      }
+      sa.ws = reinterpret_cast<uint8_t*>(workspace);
     }
-    const cuuint64_t dims[2] = {128, (cuuint64_t)plan.stages_per_pass * tc::STAGE_N};
-    const cuuint64_t strides[1] = {128};
-    const cuuint32_t box[2] = {128, (cuuint32_t)tc::STAGE_N};
-    const cuuint32_t estr[2] = {1, 1};
-    CUresult r = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(net.packed_f16), dims, strides, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) {
-      set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
-      return SCADE_ERR_CUDA;
-    }
-  }
-  if (pair) {
-    int64_t n_steps = (a.n_pairs + 1) / 2;
-    int clusters = (int)std::min<int64_t>(n_steps, num_sms() / 2);
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(2 * clusters);
-    cfg.blockDim = dim3(pp ? tc::PP_THREADS : threads);
-    cfg.dynamicSmemBytes = tc::SMEM_BYTES;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
-    if (pp) SCADE_CUDA(cudaLaunchKernelEx(&cfg, tc::nerf_mlp_tc_pp_kernel, a, plan, tmap));
-    else SCADE_CUDA(cudaLaunchKernelEx(&cfg, kern, a, plan));
+    const int64_t n_steps = (a.n_pairs + 1) / 2;
+    const int clusters = (int)std::min<int64_t>(n_steps, num_sms() / 2);
+    void* args[] = {&a, &plan, &tmap, &sa};
+    SCADE_TRY(tc::launch_pair(save ? (const void*)tc::nerf_mlp_tc_pp_kernel<true> : (const void*)tc::nerf_mlp_tc_pp_kernel<false>,
+                              clusters, tc::PP_THREADS, tc::SMEM_BYTES, st, args));
+  } else if (pair) {
+    const int64_t n_steps = (a.n_pairs + 1) / 2;
+    const int clusters = (int)std::min<int64_t>(n_steps, num_sms() / 2);
+    void* args[] = {&a, &plan};
+    SCADE_TRY(tc::launch_pair((const void*)kern, clusters, tc::THREADS, tc::SMEM_BYTES, st, args));
   } else {
     int grid = (int)std::min<int64_t>(a.n_pairs, num_sms());
     kern<<<grid, tc::THREADS, tc::SMEM_BYTES, st>>>(a, plan);
   }
   SCADE_LAUNCH_CHECK();
+  return SCADE_OK;
+}
+
+// Backward of a forward call that stashed (save_for_backward = 1): gradients of all parameter tensors, accumulated.
+int mlp_tc_backward(const scade_net& net, const float* d_out, int64_t P, float* const* grads, void* workspace, size_t ws_bytes,
+                    cudaStream_t st) {
+  if (!tc::use_pair()) {
+    set_error("SCADE_PREC_TC_F16 training needs the SM-pair kernels (unset SCADE_TC_PAIR)");
+    return SCADE_ERR_UNSUPPORTED;
+  }
+  const scade_net_desc& d = net.desc;
+  NetDims nd(d);
+  const tc::TrainLayout L = tc::train_layout(d, P);
+  if (workspace == nullptr || ws_bytes < L.total) {
+    set_error("mlp_backward (tc_f16): workspace %zu < %llu bytes", ws_bytes, L.total);
+    return SCADE_ERR_WORKSPACE;
+  }
+  uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
+  static bool attr_set = false;
+  if (!attr_set) {
+    SCADE_CUDA(cudaFuncSetAttribute(tc::nerf_mlp_tc_dgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
+    SCADE_CUDA(cudaFuncSetAttribute(tc::nerf_mlp_tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::WG_SMEM_BYTES));
+    attr_set = true;
+  }
+  // 1. gradient scale from max |d_out|
+  SCADE_CUDA(cudaMemsetAsync(ws + L.gs, 0, 256, st));
+  {
+    const int blocks = (int)std::min<int64_t>(ceil_div<int64_t>(P, 256), 4 * num_sms());
+    tc::absmax_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const float4*>(d_out), P, reinterpret_cast<uint32_t*>(ws + L.gs));
+    SCADE_LAUNCH_CHECK();
+  }
+  const int64_t n_pairs = ceil_div<int64_t>(P, tc::TILES * tc::TILE_M);
+  const int64_t n_steps = (n_pairs + 1) / 2;
+  const int clusters = (int)std::min<int64_t>(n_steps, num_sms() / 2);
+  const uint8_t* packed = reinterpret_cast<const uint8_t*>(net.packed_f16);
+  const size_t bwd_off = tc::fwd_stream_bytes(d);
+  // 2. dgrad chain
+  {
+    tc::NetPlan plan;
+    tc::build_bwd_plans(net, &plan, nullptr);
+    CUtensorMap tmap;
+    SCADE_TRY(tc::encode_rows_tmap(&tmap, packed + bwd_off, (size_t)plan.stages_per_pass * tc::STAGE_BYTES, tc::STAGE_N));
+    tc::BwdArgs a{};
+    a.packed = packed;
+    a.tail_off = (unsigned long long)tc::count_stages(d, true) * tc::STAGE_BYTES;
+    a.ws = ws; a.L = L;
+    a.d_out = reinterpret_cast<const float4*>(d_out);
+    a.P = P; a.n_pairs = n_pairs;
+    void* args[] = {&a, &plan, &tmap};
+    SCADE_TRY(tc::launch_pair((const void*)tc::nerf_mlp_tc_dgrad_kernel, clusters, tc::PP_THREADS, tc::SMEM_BYTES, st, args));
+    SCADE_LAUNCH_CHECK();
+  }
+  // 3. weight + bias gradients of the wide layers
+  {
+    tc::WgArgs a{};
+    a.ws = ws; a.emb_off = L.emb; a.gs_off = L.gs; a.T = L.T;
+    const int pv = 2 * d.D;
+    for (int i = 0; i < d.D; ++i) {
+      tc::WgLayer& Ld = a.layers[a.n_layers++];
+      const bool after_skip = i >= 1 && (i - 1 == d.skip);
+      Ld.dz_off = L.dz[i]; Ld.dz_chunks = 4; Ld.n_out = tc::W;
+      Ld.has_x = i >= 1; Ld.x_off = i >= 1 ? L.h[i - 1] : 0;
+      Ld.gW = grads[2 * i]; Ld.gb = grads[2 * i + 1];
+      Ld.ld = i == 0 ? nd.in_ch : (after_skip ? nd.in_ch + tc::W : tc::W);
+      Ld.x_col0 = after_skip ? nd.in_ch : 0;
+      Ld.emb_lo = 0; Ld.emb_hi = (i == 0 || after_skip) ? nd.in_ch : 0; Ld.emb_dst = 0;
+      Ld.cost = 3 + 2 * Ld.has_x;
+    }
+    {
+      tc::WgLayer& Ld = a.layers[a.n_layers++];                    // feature_linear
+      Ld.dz_off = L.dzf; Ld.dz_chunks = 4; Ld.n_out = tc::W; Ld.has_x = 1; Ld.x_off = L.h[d.D - 1];
+      Ld.gW = grads[pv + 2]; Ld.gb = grads[pv + 3]; Ld.ld = tc::W; Ld.cost = 5;
+    }
+    {
+      tc::WgLayer& Ld = a.layers[a.n_layers++];                    // views_linears.0: input = [feature, input_views]  (H:235)
+      Ld.dz_off = L.dzv; Ld.dz_chunks = 2; Ld.n_out = tc::W / 2; Ld.has_x = 1; Ld.x_off = L.feat;
+      Ld.gW = grads[pv]; Ld.gb = grads[pv + 1]; Ld.ld = tc::W + nd.in_views;
+      Ld.emb_lo = nd.in_ch; Ld.emb_hi = nd.in_ch + nd.in_views; Ld.emb_dst = tc::W; Ld.cost = 5;
+    }
+    CUtensorMap tmap;
+    SCADE_TRY(tc::encode_rows_tmap(&tmap, ws, (size_t)L.maskh[0], 64));          // all chunk regions precede the masks
+    const int wclusters = (int)std::min<int64_t>(num_sms() / 2, std::max<int64_t>(1, L.T));
+    void* args[] = {&a, &tmap};
+    SCADE_TRY(tc::launch_pair((const void*)tc::nerf_mlp_tc_wgrad_kernel, wclusters, tc::WG_THREADS, tc::WG_SMEM_BYTES, st, args));
+    SCADE_LAUNCH_CHECK();
+  }
+  // 4. alpha_linear / rgb_linear
+  {
+    const int pv = 2 * d.D;
+    const int blocks = (int)std::min<int64_t>(L.T, 4 * num_sms());
+    tc::head_wgrad_tc_kernel<<<blocks, 256, 0, st>>>(ws, L, reinterpret_cast<const float4*>(d_out), P, grads[pv + 4], grads[pv + 5],
+                                                     grads[pv + 6], grads[pv + 7]);
+    SCADE_LAUNCH_CHECK();
+  }
   return SCADE_OK;
 }
 

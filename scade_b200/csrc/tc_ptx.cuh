@@ -217,5 +217,58 @@ __device__ __forceinline__ uint32_t pack_plain_f16x2(uint32_t lo_bits, uint32_t 
 }
 
 
+// ---- additions for the training kernels (stash stores, MN-major operands, mask expansion) --------------------
+// shared -> global bulk copy (TMA store of a linear range), tracked by the issuing thread's bulk async-group
+__device__ __forceinline__ void bulk_s2g(void* dst, uint32_t src_smem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src_smem), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all bulk stores of this thread have finished READING their shared-memory source (it may be overwritten)
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+// UMMA shared-memory descriptor for an MN-major SWIZZLE_128B operand: rows are K (128 B = 64 fp16 along M/N per row),
+// 8-row groups 1024 B apart along K (stride byte offset), 64-element M/N blocks `lbo_bytes` apart (leading byte offset).
+// Canonical form (cute::UMMA, Major::MN, B128): Swizzle<3,4,3> o ((8,8,m),(8,k)) : ((1,8,LBO),(64,SBO)) in fp16 elements.
+__device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t saddr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// kind::f16 instruction descriptor with both operands MN-major (bits 15 / 16 = A / B transpose)
+__host__ __device__ constexpr uint32_t make_idesc_mn(int M, int N) {
+  return (1u << 4) | (1u << 15) | (1u << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+// byte permute; selector nibbles with bit 3 set replicate the sign bit of the selected byte over the result byte
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
+  uint32_t d;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+  return d;
+}
+// fp32 pair -> fp16 pair, saturating to +-65504 instead of inf (scaled gradients must never turn into NaN downstream)
+__device__ __forceinline__ uint32_t pack_sat_f16x2(float lo, float hi) {
+  uint32_t d;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
+// Sign bits of 32 fp32 accumulators as one word, in the order the dgrad epilogue expands them with prmt:
+// bit (31 - 8g - s) <- element 4s + g   (s = 0..7, g = 0..3), so that (word << s) carries elements 4s..4s+3 in its 4 byte MSBs.
+__device__ __forceinline__ uint32_t sign_mask32(const uint32_t* r) {
+  uint32_t m = 0;
+#pragma unroll
+  for (int k = 0; k < 32; ++k) m = __funnelshift_l(r[4 * (k & 7) + (k >> 3)], m, 1);
+  return m;
+}
+// masks for the packed fp16 pairs (4s, 4s+1) and (4s+2, 4s+3): 0xFFFF where the sign bit was set (= inactive ReLU)
+__device__ __forceinline__ void inactive_masks(uint32_t word, int s, uint32_t* m01, uint32_t* m23) {
+  const uint32_t x = word << s;
+  *m01 = prmt(x, 0u, 0xAABBu);
+  *m23 = prmt(x, 0u, 0x8899u);
+}
+
 }  // namespace tc
 }  // namespace scade

@@ -74,9 +74,26 @@ class NetHandle:
         return _L().scade_mlp_workspace_bytes(byref(self.desc), int(P), int(precision), int(save))
 
 
+def tc_train_enabled():
+    """SCADE_TC_TRAIN=0 sends training through the fp32 FFMA GEMMs even when the network's precision is tc_f16."""
+    import os
+    return os.environ.get("SCADE_TC_TRAIN", "1") != "0"
+
+
+def stash_layout(handle, P):
+    """Offsets of the tensor-core training stash inside the forward workspace (scade_mlp_tc_stash_layout)."""
+    buf = (ctypes.c_int64 * 64)()
+    n = _L().scade_mlp_tc_stash_layout(byref(handle.desc), int(P), buf, 64)
+    v = list(buf[:n])
+    names = ["T", "D", "total", "emb", "feat", "hv", "dzv", "dzf", "maskv", "alpha", "gs"]
+    out = dict(zip(names, v[:11]))
+    out["h"], out["dz"], out["maskh"] = v[11:19], v[19:27], v[27:35]
+    return out
+
+
 def _mlp_backward(handle, precision, d_out, P, ws, device):
     grads = [torch.zeros_like(p) for p in handle.params]
-    net = handle.struct(PREC_FP32)
+    net = handle.struct(precision)
     arr = (c_void_p * len(grads))(*[g.data_ptr() for g in grads])
     check(_L().scade_mlp_backward(byref(net), precision, ptr(d_out), P, arr, ptr(ws), ws.numel(), stream_ptr()),
           "scade_mlp_backward")
@@ -133,8 +150,8 @@ def mlp_forward_rays(handle, rays, z_vals, bb_center, bb_scale, precision=PREC_F
     precision = PRECISIONS[precision]
     rays, z_vals = f32(rays), f32(z_vals)
     need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in handle.params)
-    if precision == PREC_TC_F16 and need_grad:
-        precision = PREC_FP32      # training stashes fp32 activations; tensor-core backward is future work
+    if precision == PREC_TC_F16 and need_grad and not (tc_train_enabled() and handle.tc_supported()):
+        precision = PREC_FP32      # fp32 FFMA training path (any D / W / multires)
     if rays.shape[0] == 0:
         return torch.empty((0, z_vals.shape[1], 4), dtype=torch.float32, device=z_vals.device)
     return _MLPRaysFn.apply(rays, z_vals, handle, precision, [float(c) for c in bb_center], float(bb_scale),
@@ -147,7 +164,7 @@ def mlp_forward_embedded(handle, x, precision=PREC_FP32):
     lead = x.shape[:-1]
     x2 = f32(x).reshape(-1, x.shape[-1])
     need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in handle.params)
-    if precision == PREC_TC_F16 and need_grad:
+    if precision == PREC_TC_F16 and need_grad and not (tc_train_enabled() and handle.tc_supported()):
         precision = PREC_FP32
     if x2.shape[0] == 0:
         return torch.empty((*lead, 4), dtype=torch.float32, device=x2.device)
