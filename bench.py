@@ -310,11 +310,11 @@ def run_train(args):
     pc, pf = net_pair(NET_D, NET_W)
     nets = []
     for p in (pc, pf):
-        net = NH.NeRF(D=NET_D, W=NET_W, input_ch=57, input_ch_views=3, output_ch=5, skips=[4], use_viewdirs=True, precision="fp32")
+        net = NH.NeRF(D=NET_D, W=NET_W, input_ch=57, input_ch_views=3, output_ch=5, skips=[4], use_viewdirs=True, precision=args.precision)
         net.load_state_dict({k: torch.from_numpy(v) for k, v in p.items()})
         nets.append(net.to(dev))
     bb_center, bb_scale = syn.bounding_box()
-    qf = R_.NetworkQuery(NH.get_embedder(9, 0)[0], NH.get_embedder(0, 0)[0], bb_center, bb_scale, precision="fp32")
+    qf = R_.NetworkQuery(NH.get_embedder(9, 0)[0], NH.get_embedder(0, 0)[0], bb_center, bb_scale, precision=args.precision)
     kw = dict(network_fn=nets[0], network_query_fn=qf, N_samples=Nc, embedded_cam=torch.tensor((), device=dev), perturb=1.0,
               N_importance=Nf, network_fine=nets[1], raw_noise_std=0.0)
     opt = torch.optim.Adam([p for n in nets for p in n.parameters()], lr=5e-4, betas=(0.9, 0.999))
@@ -358,8 +358,11 @@ def run_train(args):
         print(json.dumps({
             "metric": "train rays/sec (4096 rays, 64c+128f, K=20, fwd+loss+bwd+allreduce+Adam)", "value": N / sec, "unit": "rays/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": sec * 1e3, "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "BASELINE config 3 train step", "global_rays": N, "precision": "fp32 FFMA GEMMs (fwd+bwd)",
+            "scaling": "strong", "vs_baseline": None,
+            "dtype": "f16 operands / f32 accumulate (tcgen05 fwd+dgrad+wgrad)" if args.precision == "tc_f16" else "f32", "data": "synthetic",
+            "config": {"workload": "BASELINE config 3 train step", "global_rays": N,
+                       "precision": "tcgen05 fwd + dgrad + wgrad, fp32 master weights / gradients / Adam" if args.precision == "tc_f16"
+                       else "fp32 FFMA GEMMs (fwd+bwd)",
                        "collective": "1 NCCL all-reduce / step, flat fp32 buffer 4.72 MB"},
             "gpu_launches": int(lib.scade_kernel_launch_count() - l0), "loss": float(losses["loss"]),
             "roofline": {"bound": "tensor", "achieved": flop_step / sec / 1e12, "peak": sustained, "unit": "TFLOP/s",

@@ -440,51 +440,94 @@ __global__ void __launch_bounds__(WG_THREADS, 1) nerf_mlp_tc_wgrad_kernel(const 
 }
 
 // ---- skinny heads: alpha_linear (W -> 1) and rgb_linear (W/2 -> 3) gradients -----------------------------------------
-// block = 256 threads walking tiles; thread c owns column c of h_last (and of h_v for c < 128); per-block partial sums, one
-// atomicAdd per thread at the end.  Not scaled: d_out is used in fp32.
+// HBM-bound (768 B per point re-read from the stash).  Block = 8 warps; warp g walks rows g, g+8, ... of a tile, lane j owns the
+// 16-byte piece j of the row (8 columns of h_last; lanes < 16 also 8 columns of h_v) -- 512 B coalesced per warp load, the
+// swizzle position is fixed per thread because row & 7 == g.  Partials live in registers across tiles; one shared-memory
+// reduction over the 8 row groups and one atomicAdd per column at the end.  Not scaled: d_out is used in fp32.
 __global__ void __launch_bounds__(256) head_wgrad_tc_kernel(const uint8_t* __restrict__ ws, const __grid_constant__ TrainLayout L,
                                                             const float4* __restrict__ d_out, int64_t P,
                                                             float* __restrict__ g_alpha_w, float* __restrict__ g_alpha_b,
                                                             float* __restrict__ g_rgb_w, float* __restrict__ g_rgb_b) {
   __shared__ float4 sd[TILE_M];
-  const int c = threadIdx.x;
-  float acc_a = 0.f, ar = 0.f, ag = 0.f, ab = 0.f, bias = 0.f;
+  __shared__ float red[8][32][33];
+  const int lane = threadIdx.x & 31, g = threadIdx.x >> 5;
+  const int chunk = lane >> 3, pj = lane & 7;
+  const uint32_t piece_off = (uint32_t)chunk * CHUNK_BYTES + ((uint32_t)(pj ^ g) << 4);      // + row * 128
+  float aa[8], ar[8], ag[8], ab[8], bias[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int i = 0; i < 8; ++i) aa[i] = ar[i] = ag[i] = ab[i] = 0.f;
   for (long long tile = blockIdx.x; tile < L.T; tile += gridDim.x) {
-    if (c < TILE_M) {
-      const int64_t p = tile * TILE_M + c;
-      float4 g = p < P ? __ldg(d_out + p) : make_float4(0.f, 0.f, 0.f, 0.f);
+    if (threadIdx.x < TILE_M) {
+      const int64_t p = tile * TILE_M + threadIdx.x;
+      float4 d = p < P ? __ldg(d_out + p) : make_float4(0.f, 0.f, 0.f, 0.f);
       const float bx = reinterpret_cast<const float*>(ws + L.alpha)[p] * 10.0f;
-      g.w *= bx > 20.0f ? 1.0f : sigmoidf_(bx);
-      sd[c] = g;
+      d.w *= bx > 20.0f ? 1.0f : sigmoidf_(bx);
+      sd[threadIdx.x] = d;
     }
     __syncthreads();
-    const __half* hc = reinterpret_cast<const __half*>(ws + L.h[L.D - 1] + (size_t)(tile * 4 + (c >> 6)) * CHUNK_BYTES);
-    const __half* vc = reinterpret_cast<const __half*>(ws + L.hv + (size_t)(tile * 2 + ((c & 127) >> 6)) * CHUNK_BYTES);
-    const int col = c & 63;
+    const uint8_t* hbase = ws + L.h[L.D - 1] + (size_t)tile * 4 * CHUNK_BYTES + piece_off;
+    const uint8_t* vbase = ws + L.hv + (size_t)tile * 2 * CHUNK_BYTES + piece_off;
 #pragma unroll 4
-    for (int r = 0; r < TILE_M; ++r) {
-      const uint32_t off = (sw128_offset(r, col >> 3) >> 1) + (col & 7);
-      const float4 g = sd[r];
-      acc_a = fmaf(g.w, __half2float(hc[off]), acc_a);
-      if (c < TILE_M) {
-        const float v = __half2float(vc[off]);
-        ar = fmaf(g.x, v, ar); ag = fmaf(g.y, v, ag); ab = fmaf(g.z, v, ab);
+    for (int i = 0; i < 16; ++i) {
+      const int r = g + 8 * i;
+      const float4 d = sd[r];
+      const uint4 hq = __ldg(reinterpret_cast<const uint4*>(hbase + r * 128));
+      const uint32_t hw[4] = {hq.x, hq.y, hq.z, hq.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&hw[k]));
+        aa[2 * k] = fmaf(d.w, f.x, aa[2 * k]);
+        aa[2 * k + 1] = fmaf(d.w, f.y, aa[2 * k + 1]);
       }
-    }
-    if (c < 4) {
-      for (int r = 0; r < TILE_M; ++r) {
-        const float4 g = sd[r];
-        bias += c == 0 ? g.x : (c == 1 ? g.y : (c == 2 ? g.z : g.w));
+      if (lane < 16) {
+        const uint4 vq = __ldg(reinterpret_cast<const uint4*>(vbase + r * 128));
+        const uint32_t vw[4] = {vq.x, vq.y, vq.z, vq.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&vw[k]));
+          ar[2 * k] = fmaf(d.x, f.x, ar[2 * k]); ar[2 * k + 1] = fmaf(d.x, f.y, ar[2 * k + 1]);
+          ag[2 * k] = fmaf(d.y, f.x, ag[2 * k]); ag[2 * k + 1] = fmaf(d.y, f.y, ag[2 * k + 1]);
+          ab[2 * k] = fmaf(d.z, f.x, ab[2 * k]); ab[2 * k + 1] = fmaf(d.z, f.y, ab[2 * k + 1]);
+        }
       }
+      if (lane == 0) { bias[0] += d.x; bias[1] += d.y; bias[2] += d.z; bias[3] += d.w; }
     }
     __syncthreads();
   }
-  atomicAdd(g_alpha_w + c, acc_a);
-  if (c < TILE_M) {
-    atomicAdd(g_rgb_w + c, ar);
-    atomicAdd(g_rgb_w + TILE_M + c, ag);
-    atomicAdd(g_rgb_w + 2 * TILE_M + c, ab);
+  // reduce over the 8 row groups: red[g][lane][slot]; slots 0..7 alpha, 8..15 r, 16..23 g, 24..31 b, 32 unused
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    red[g][lane][i] = aa[i];
+    red[g][lane][8 + i] = ar[i];
+    red[g][lane][16 + i] = ag[i];
+    red[g][lane][24 + i] = ab[i];
   }
-  if (c < 3) atomicAdd(g_rgb_b + c, bias);
-  if (c == 3) atomicAdd(g_alpha_b, bias);
+  __syncthreads();
+  {
+    // thread t -> alpha column t (lane j = t / 8 owns columns 8j..8j+7)
+    const int t = threadIdx.x, j = t >> 3, i = t & 7;
+    float s = 0.f;
+#pragma unroll
+    for (int gg = 0; gg < 8; ++gg) s += red[gg][j][i];
+    atomicAdd(g_alpha_w + t, s);
+    if (t < TILE_M) {
+      float sr = 0.f, sg = 0.f, sb = 0.f;
+#pragma unroll
+      for (int gg = 0; gg < 8; ++gg) { sr += red[gg][j][8 + i]; sg += red[gg][j][16 + i]; sb += red[gg][j][24 + i]; }
+      atomicAdd(g_rgb_w + t, sr);
+      atomicAdd(g_rgb_w + TILE_M + t, sg);
+      atomicAdd(g_rgb_w + 2 * TILE_M + t, sb);
+    }
+  }
+  __syncthreads();
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) red[g][0][k] = bias[k];
+  }
+  __syncthreads();
+  if (threadIdx.x < 4) {
+    float s = 0.f;
+    for (int gg = 0; gg < 8; ++gg) s += red[gg][0][threadIdx.x];
+    atomicAdd(threadIdx.x < 3 ? g_rgb_b + threadIdx.x : g_alpha_b, s);
+  }
 }
