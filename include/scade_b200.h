@@ -96,7 +96,7 @@ int scade_mlp_forward_embedded(const scade_net* net, int precision, const float*
  * parameter tensors, ACCUMULATED into grads[i] (HOST array of DEVICE pointers, same order/shape as
  * params).  Uses the stash a forward call with save_for_backward=1 left in `workspace` (same precision).
  * SCADE_PREC_TC_F16: dgrad chain and weight gradients on tcgen05 (fp16 operands, gradients scaled by a power of
- * two taken from max|d_out|, fp32 accumulation and fp32 gradient tensors); grads must be 4-byte aligned fp32.
+ * two taken from the largest gradient entering the chain, fp32 accumulation, fp32 gradient tensors).
  * No gradient w.r.t. the inputs is produced (z samples are detached, RS:711). */
 int scade_mlp_backward(const scade_net* net, int precision, const float* d_out, int64_t P,
                        float* const* grads_host, void* workspace, size_t workspace_bytes, void* stream);

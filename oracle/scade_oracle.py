@@ -550,3 +550,51 @@ def nerf_forward_f16(params, x, input_ch=57, skips=(4,)):
     hv = np.maximum(zv + p["views_linears.0.bias"], 0)
     rgb = hv @ p["rgb_linear.weight"].T + p["rgb_linear.bias"]
     return np.concatenate([rgb, softplus_beta10(alpha)], -1).astype(np.float32)
+
+
+# --------------------------------------------------------------------------------------
+# teacher-forced backward for the tensor-core training path (test infrastructure)
+# --------------------------------------------------------------------------------------
+def nerf_backward_teacher_forced(params, emb, h, feature, hv, alpha_pre, inactive, inactive_v, d_out, input_ch=57,
+                                 input_views=3, skips=(4,)):
+    """Autograd of NeRF.forward (H:223-247) evaluated in float64 on GIVEN activations and ReLU masks.
+
+    The tensor-core forward rounds operands to fp16, which flips the sign of a few pre-activations that sit within
+    ~1e-3 of zero; a gradient check against `nerf_backward` would then measure those flips, not the backward kernels.
+    Here the activations (emb [P,>=input_ch+input_views], h[l] [P,W] post-ReLU outputs of pts_linears[l], feature [P,W],
+    hv [P,W/2], alpha_pre [P]) and the masks (inactive[l], inactive_v: True where the pre-activation was negative) are
+    the ones the kernel stashed, so the result isolates dgrad / wgrad arithmetic.  Returns (grads, dz) with dz the
+    per-layer pre-activation gradients {"v", "feature", 0..D-1}."""
+    f8 = np.float64
+    p = {k: np.asarray(v, f8) for k, v in params.items()}
+    D = _num_pts_layers(p)
+    emb, feature, hv = np.asarray(emb, f8), np.asarray(feature, f8), np.asarray(hv, f8)
+    h = [np.asarray(x, f8) for x in h]
+    d_out = np.asarray(d_out, f8)
+    d_rgb, d_sigma = d_out[:, :3], d_out[:, 3:4]
+    al = np.asarray(alpha_pre, f8).reshape(-1, 1)
+    d_alpha = d_sigma * np.where(al * 10.0 > 20.0, 1.0, 1.0 / (1.0 + np.exp(-al * 10.0)))       # softplus'(beta=10), H:242
+    g, dz = {}, {}
+    W = feature.shape[1]
+    input_pts, views = emb[:, :input_ch], emb[:, input_ch:input_ch + input_views]
+    g["rgb_linear.weight"] = d_rgb.T @ hv                                                        # H:241
+    g["rgb_linear.bias"] = d_rgb.sum(0)
+    dz["v"] = (d_rgb @ p["rgb_linear.weight"]) * (~np.asarray(inactive_v, bool))                 # H:239
+    g["views_linears.0.weight"] = dz["v"].T @ np.concatenate([feature, views], -1)               # H:235-238
+    g["views_linears.0.bias"] = dz["v"].sum(0)
+    dz["feature"] = (dz["v"] @ p["views_linears.0.weight"])[:, :W]
+    g["feature_linear.weight"] = dz["feature"].T @ h[D - 1]                                      # H:234
+    g["feature_linear.bias"] = dz["feature"].sum(0)
+    g["alpha_linear.weight"] = d_alpha.T @ h[D - 1]                                              # H:233
+    g["alpha_linear.bias"] = d_alpha.sum(0)
+    d_h = dz["feature"] @ p["feature_linear.weight"] + d_alpha @ p["alpha_linear.weight"]
+    for i in reversed(range(D)):
+        dz[i] = d_h * (~np.asarray(inactive[i], bool))                                           # H:228
+        x_in = input_pts if i == 0 else (np.concatenate([input_pts, h[i - 1]], -1) if (i - 1) in skips else h[i - 1])
+        g[f"pts_linears.{i}.weight"] = dz[i].T @ x_in                                            # H:227, H:230
+        g[f"pts_linears.{i}.bias"] = dz[i].sum(0)
+        if i > 0:
+            d_h = dz[i] @ p[f"pts_linears.{i}.weight"]
+            if (i - 1) in skips:
+                d_h = d_h[:, input_ch:]
+    return g, dz

@@ -138,7 +138,7 @@ struct TrainLayout {
   unsigned long long dzf;        // [T][4]   d loss / d feature
   unsigned long long maskv;      // [T][128] uint4: sign bits of the views pre-activations (sign_mask32 order)
   unsigned long long alpha;      // [T*128]  fp32 alpha pre-activation (H:233)
-  unsigned long long gs;         // 64 uint32: [0] = bit pattern of max |d_out|
+  unsigned long long gs;         // 64 uint32: [0] = bit pattern of max(|d_rgb_raw|, |d_alpha|) over the call's points
   unsigned long long total;
   unsigned long long h[8];       // [T][4]   output of pts_linears[l] (post-ReLU)
   unsigned long long dz[8];      // [T][4]   d loss / d (pre-activation of pts_linears[l]), scaled
@@ -1272,7 +1272,8 @@ int mlp_tc_backward(const scade_net& net, const float* d_out, int64_t P, float* 
   SCADE_CUDA(cudaMemsetAsync(ws + L.gs, 0, 256, st));
   {
     const int blocks = (int)std::min<int64_t>(ceil_div<int64_t>(P, 256), 4 * num_sms());
-    tc::absmax_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const float4*>(d_out), P, reinterpret_cast<uint32_t*>(ws + L.gs));
+    tc::absmax_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const float4*>(d_out), reinterpret_cast<const float*>(ws + L.alpha), P,
+                                                reinterpret_cast<uint32_t*>(ws + L.gs));
     SCADE_LAUNCH_CHECK();
   }
   const int64_t n_pairs = ceil_div<int64_t>(P, tc::TILES * tc::TILE_M);

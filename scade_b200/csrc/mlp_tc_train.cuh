@@ -14,8 +14,11 @@
 //                       The encoding chunk's constant-1 column turns the bias gradients into one more MMA column.
 //   heads             : alpha_linear / rgb_linear gradients (skinny) on CUDA cores from the stash.
 //
-// Gradients travel as fp16 scaled by a power of two chosen per call from max|d_out| (absmax kernel), so that the largest
-// incoming gradient sits at 2^6; conversions saturate instead of overflowing; the weight gradients are un-scaled in fp32.
+// Gradients travel as fp16 scaled by a power of two chosen per call (absmax kernel) so that the largest gradient entering the
+// chain sits in [32, 64): 2^10 of headroom before fp16 saturates (conversions use .satfinite, never inf) and 2^20 below it in
+// fp16's normal range; what falls under 2^-30 of the maximum is flushed, which fp32 accumulation of the same sums would lose too.
+// The weight gradients are un-scaled in fp32.  (bf16 gradients would need no scaling, but tcgen05 kind::f16 rejects mixed
+// bf16 x fp16 operands -- "illegal instruction" on B200 -- and the stashed activations are the forward's fp16 operand tiles.)
 #pragma once
 
 // scale = 2^(6 - (e+1)) with e = exponent of max|d_out|  ->  max scaled |d_out| in [32, 64)
@@ -26,11 +29,17 @@ __device__ __forceinline__ float grad_scale(uint32_t maxbits, float* inv) {
   return exp2f((float)(5 - e));
 }
 
-__global__ void absmax_kernel(const float4* __restrict__ x, int64_t n, uint32_t* __restrict__ out) {
+// max over points of (|d_rgb_raw|, |d_alpha|) with d_alpha = d_sigma * softplus'(alpha): the magnitudes that actually enter the
+// GEMM chain.  (d_sigma itself is useless for this: compute_weights' 1e10 "last interval" (RS:514-515) produces d_sigma outliers
+// many orders of magnitude above the rest, which softplus' then multiplies by ~1e-8.)
+__global__ void absmax_kernel(const float4* __restrict__ x, const float* __restrict__ alpha_pre, int64_t n, uint32_t* __restrict__ out) {
   uint32_t m = 0;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const float4 v = x[i];
-    m = max(m, __float_as_uint(fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w)))));
+    const float bx = alpha_pre[i] * 10.0f;
+    const float da = v.w * (bx > 20.0f ? 1.0f : sigmoidf_(bx));
+    const float mx = fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(da)));
+    if (mx < 3.0e38f) m = max(m, __float_as_uint(mx));          // ignore inf / nan rows (they saturate downstream)
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
@@ -126,7 +135,7 @@ __global__ void __launch_bounds__(PP_THREADS, 1) nerf_mlp_tc_dgrad_kernel(const 
         const float al = reinterpret_cast<const float*>(a.ws + a.L.alpha)[grow];
         const uint4 mv = *reinterpret_cast<const uint4*>(a.ws + a.L.maskv + grow * 16);
         const float bx = al * 10.0f;
-        d_alpha = g.w * gscale * (bx > 20.0f ? 1.0f : sigmoidf_(bx));
+        d_alpha = g.w * (bx > 20.0f ? 1.0f : sigmoidf_(bx)) * gscale;
         const float dr = g.x * gscale, dg = g.y * gscale, db = g.z * gscale;
         if (lane == 0) bulk_wait_read0();
         __syncwarp();

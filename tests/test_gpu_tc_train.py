@@ -1,0 +1,188 @@
+"""GPU parity of the tensor-core TRAINING path (SCADE_PREC_TC_F16 with save_for_backward): forward stash, tcgen05 dgrad
+chain, MN-major tcgen05 wgrad, head gradients -- called through the C ABI.
+
+Two references:
+  * teacher-forced (oracle.nerf_backward_teacher_forced): float64 autograd on the activations and ReLU masks the
+    forward kernel stashed.  Isolates the backward kernels; tolerance = fp16 rounding of the gradient operands.
+  * the plain oracle (oracle.nerf_backward, float64): includes the few ReLU sign flips the fp16 forward causes next to
+    z = 0; stated as a cosine similarity per parameter tensor.
+"""
+from ctypes import byref, c_void_p
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import scade_oracle as O
+from scade_b200 import synthetic as syn
+from tests.util import decode_sign_mask, stash_unswizzle
+
+pytestmark = pytest.mark.gpu
+
+PARAM_ORDER = [f"pts_linears.{i}.{k}" for i in range(8) for k in ("weight", "bias")] + [
+    "views_linears.0.weight", "views_linears.0.bias", "feature_linear.weight", "feature_linear.bias",
+    "alpha_linear.weight", "alpha_linear.bias", "rgb_linear.weight", "rgb_linear.bias"]
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    from scade_b200 import _lib
+    _lib.load()
+    return torch.device("cuda:0")
+
+
+def rel(a, b):
+    return float(np.abs(a - b).max() / (np.abs(b).max() + 1e-30))
+
+
+def cosine(a, b):
+    a, b = np.asarray(a, np.float64).ravel(), np.asarray(b, np.float64).ravel()
+    return float(a @ b / (np.linalg.norm(a) * np.linalg.norm(b) + 1e-300))
+
+
+def build_net(params, dev, requires_grad=True):
+    from scade_b200.nerf_helpers import NeRF
+    net = NeRF(D=8, W=256, input_ch=57, input_ch_views=3, output_ch=5, skips=[4], use_viewdirs=True, precision="tc_f16")
+    net.load_state_dict({k: torch.from_numpy(v) for k, v in params.items()})
+    net = net.to(dev)
+    for p in net.parameters():
+        p.requires_grad_(requires_grad)
+    return net
+
+
+@pytest.mark.parametrize("P,gscale", [(700, 1e-7), (2500, 3e5)])
+def test_tc_backward_teacher_forced(dev, P, gscale):
+    """Forward with stash -> backward, straight through the C ABI; every stashed tensor and every gradient is checked.
+    P = 700 leaves ragged tiles (dead rows) and an odd number of tile pairs; gscale exercises gradient
+    magnitudes far below and above fp16's range (handled by the per-call power-of-two scale)."""
+    from scade_b200 import _lib, functional as F_
+    params = syn.make_nerf_params(seed=12, D=8, W=256, bias_scale=0.1, alpha_bias=0.3)
+    net = build_net(params, dev)
+    rng = np.random.default_rng(13)
+    x = rng.uniform(-1, 1, (P, 60)).astype(np.float32)
+    d_out = (rng.standard_normal((P, 4)) * gscale).astype(np.float32)
+    h, L, prec = net.handle(), _lib.load(), _lib.PREC_TC_F16
+    ws = torch.zeros(h.workspace_bytes(P, prec, 1), dtype=torch.uint8, device=dev)
+    out = torch.empty((P, 4), dtype=torch.float32, device=dev)
+    xs = torch.from_numpy(x).to(dev)
+    cnet = h.struct(prec)
+    _lib.check(L.scade_mlp_forward_embedded(byref(cnet), prec, _lib.ptr(xs), P, _lib.ptr(out), _lib.ptr(ws), ws.numel(), 1,
+                                            _lib.stream_ptr()), "forward")
+    grads = [torch.zeros_like(p) for p in h.params]
+    arr = (c_void_p * len(grads))(*[g.data_ptr() for g in grads])
+    ds = torch.from_numpy(d_out).to(dev)
+    _lib.check(L.scade_mlp_backward(byref(cnet), prec, _lib.ptr(ds), P, arr, _lib.ptr(ws), ws.numel(), _lib.stream_ptr()),
+               "backward")
+    torch.cuda.synchronize()
+    lay = F_.stash_layout(h, P)
+    T, D, W = lay["T"], 8, 256
+    assert T % 4 == 0 and T * 128 >= P and lay["total"] == ws.numel()
+    buf = ws.cpu().numpy()
+
+    # ---- forward stash against the fp32 oracle (fp16 operand rounding: 2e-3 of each tensor's scale) ----
+    ref_out, acts = O.nerf_forward(params, x, return_acts=True)
+    assert rel(out.cpu().numpy(), ref_out) < 4e-3
+    emb = stash_unswizzle(buf, lay["emb"], T, 1)[:P]
+    assert rel(emb[:, :60], x) < 5e-4 and (emb[:, 60:62] == 1.0).all() and (emb[:, 62:] == 0).all()
+    hs, inact = [], []
+    for l in range(D):
+        hs.append(stash_unswizzle(buf, lay["h"][l], T, 4)[:P])
+        assert rel(hs[l], np.maximum(acts["pre"][l], 0)) < 2e-3, l
+        m = decode_sign_mask(buf[lay["maskh"][l]:lay["maskh"][l] + T * 128 * 32].view(np.uint32).reshape(T * 128, 8))[:P]
+        inact.append(m)
+        flips = m != (acts["pre"][l] < 0)
+        assert flips.mean() < 1e-3 and (not flips.any() or np.abs(acts["pre"][l][flips]).max() < 5e-3), l   # only next to zero
+        assert ((hs[l] == 0) | ~m).all(), l                                     # a masked element was stashed as 0
+    feat = stash_unswizzle(buf, lay["feat"], T, 4)[:P]
+    hv = stash_unswizzle(buf, lay["hv"], T, 2)[:P]
+    al = buf[lay["alpha"]:lay["alpha"] + T * 128 * 4].view(np.float32)[:P]
+    mv = decode_sign_mask(buf[lay["maskv"]:lay["maskv"] + T * 128 * 16].view(np.uint32).reshape(T * 128, 4))[:P]
+    assert rel(feat, acts["hv_in"][:, :W]) < 2e-3 and rel(hv, acts["hv"]) < 3e-3 and rel(al, acts["alpha"][:, 0]) < 3e-3
+    assert (mv != (acts["zv"] < 0)).mean() < 1e-3
+
+    # ---- backward against the teacher-forced float64 reference (fp16 gradient operands, power-of-two scale) ----
+    g_tf, dz = O.nerf_backward_teacher_forced(params, emb, hs, feat, hv, al, inact, mv, d_out)
+    maxbits = int(buf[lay["gs"]:lay["gs"] + 4].view(np.uint32)[0])
+    d_alpha = d_out[:, 3] * np.where(al * 10 > 20, 1.0, 1.0 / (1.0 + np.exp(-al.astype(np.float64) * 10)))
+    gmax = max(np.abs(d_out[:, :3]).max(), np.abs(d_alpha).max())
+    assert abs(np.array([maxbits], np.uint32).view(np.float32)[0] / gmax - 1) < 1e-5
+    scale = 2.0 ** (5 - ((maxbits >> 23) - 127))
+    assert 32.0 <= gmax * scale * (1 + 1e-5) and gmax * scale < 64.0 * (1 + 1e-5)
+    assert rel(stash_unswizzle(buf, lay["dzv"], T, 2)[:P] / scale, dz["v"]) < 1e-3
+    assert rel(stash_unswizzle(buf, lay["dzf"], T, 4)[:P] / scale, dz["feature"]) < 1.5e-3
+    for l in range(D):
+        assert rel(stash_unswizzle(buf, lay["dz"][l], T, 4)[:P] / scale, dz[l]) < 3e-3, l
+    dead = stash_unswizzle(buf, lay["dz"][0], T, 4)[P:]
+    assert (dead == 0).all()                                                   # rows beyond P carry no gradient
+    g_ref = O.nerf_backward(params, x, d_out, dtype=np.float64)
+    for name, g in zip(PARAM_ORDER, grads):
+        gn = g.cpu().numpy().astype(np.float64)
+        tol = 1e-5 if name.startswith(("alpha_linear", "rgb_linear")) else 3e-3      # heads: fp32 arithmetic on fp16 activations
+        assert rel(gn, g_tf[name].reshape(gn.shape)) < tol, (name, rel(gn, g_tf[name].reshape(gn.shape)))
+        assert cosine(gn, g_ref[name]) > 0.995, (name, cosine(gn, g_ref[name]))
+
+
+def test_tc_backward_accumulates_and_autograd(dev):
+    """The C call ACCUMULATES into the gradient tensors; the autograd wrapper (NeRF.forward on embedded inputs,
+    H:223-247) produces the same gradients as two direct calls summed."""
+    params = syn.make_nerf_params(seed=5, D=8, W=256, bias_scale=0.1, alpha_bias=0.3)
+    net = build_net(params, dev)
+    rng = np.random.default_rng(6)
+    x = torch.from_numpy(rng.uniform(-1, 1, (3, 300, 60)).astype(np.float32)).to(dev)
+    d = torch.from_numpy(rng.standard_normal((3, 300, 4)).astype(np.float32)).to(dev)
+    out = net(x)
+    out.backward(d)
+    g1 = [p.grad.clone() for p in net.parameters()]
+    out = net(x)
+    out.backward(d)                                  # second backward adds to .grad
+    for a, p in zip(g1, net.parameters()):
+        assert torch.allclose(p.grad, 2 * a, rtol=2e-3, atol=1e-3 * float(a.abs().max()))      # fp32 atomics: order-dependent round-off only
+    ref = O.nerf_backward(params, x.reshape(-1, 60).cpu().numpy(), d.reshape(-1, 4).cpu().numpy(), dtype=np.float64)
+    for (name, p), a in zip(net.named_parameters(), g1):
+        assert cosine(a.cpu().numpy(), ref[name]) > 0.995, name
+
+
+def test_tc_train_step_matches_fp32_path(dev):
+    """RS:954-985 with both networks on the tensor-core training path vs the same step on the fp32 FFMA path (itself
+    checked against the oracle in test_gpu_parity.py): losses within fp16-forward tolerance, gradient directions agree.
+    The fine network sees resampled z (inverse-CDF of the coarse weights), which amplifies forward differences, hence the
+    looser bound there."""
+    from scade_b200 import nerf_helpers as NH
+    from scade_b200 import render as R_
+    from scade_b200.render import NetworkQuery
+    from tests.golden.generate_goldens import net_pair
+    n, Nc, Nf = 256, 64, 128
+    pc, pf = net_pair(8, 256)
+    bb_center, bb_scale = syn.bounding_box()
+    rb = syn.make_ray_batch(n, seed=30)
+    t_rand, u_c, u_f = syn.make_uniforms(n, Nc, Nf, seed=31)
+    target_s, target_h = syn.make_train_targets(n, K=20, seed=32)
+    to = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    results = {}
+    for prec in ("fp32", "tc_f16"):
+        nets = []
+        for p in (pc, pf):
+            net = NH.NeRF(D=8, W=256, input_ch=57, input_ch_views=3, output_ch=5, skips=[4], use_viewdirs=True, precision=prec)
+            net.load_state_dict({k: torch.from_numpy(v) for k, v in p.items()})
+            nets.append(net.to(dev))
+        qf = NetworkQuery(NH.get_embedder(9, 0)[0], NH.get_embedder(0, 0)[0], bb_center, bb_scale, precision=prec)
+        kw = dict(network_fn=nets[0], network_query_fn=qf, N_samples=Nc, embedded_cam=torch.tensor((), device=dev),
+                  perturb=1.0, N_importance=Nf, network_fine=nets[1], raw_noise_std=0.0)
+        ret = R_.render_rays(to(rb), True, cached_u=to(u_f), t_rand=to(t_rand), u_coarse=to(u_c), **kw)
+        img_loss = NH.img2mse(ret["rgb_map"], to(target_s))
+        sc = NH.compute_space_carving_loss(ret["pred_hyp"], to(target_h), is_joint=False, norm_p=2, threshold=0.0)
+        img_loss0 = NH.img2mse(ret["rgb0"], to(target_s))
+        loss = img_loss + 0.007 * sc + img_loss0
+        loss.backward()
+        results[prec] = (float(img_loss.detach()), float(sc.detach()), float(img_loss0.detach()),
+                         [[p.grad.cpu().numpy() for p in net.parameters()] for net in nets])
+    a, b = results["fp32"], results["tc_f16"]
+    print("losses fp32", a[:3], "tc", b[:3])
+    print("cos coarse", [round(cosine(x, y), 4) for x, y in zip(a[3][0], b[3][0])])
+    print("cos fine  ", [round(cosine(x, y), 4) for x, y in zip(a[3][1], b[3][1])])
+    assert abs(a[2] - b[2]) < 2e-3 * abs(a[2]) and abs(a[0] - b[0]) < 2e-2 * abs(a[0]) and abs(a[1] - b[1]) < 2e-2 * abs(a[1])
+    for ga, gb in zip(a[3][0], b[3][0]):                     # coarse network: deterministic sample placement
+        assert cosine(ga, gb) > 0.99
+    for ga, gb in zip(a[3][1], b[3][1]):                     # fine network
+        assert cosine(ga, gb) > 0.9

@@ -4,6 +4,7 @@ import ctypes
 import os
 import re
 
+import numpy as np
 import pytest
 
 from scade_b200 import _lib
@@ -34,7 +35,13 @@ def test_argument_validation_without_gpu():
     assert lib.scade_mlp_workspace_bytes(ctypes.byref(bad), 1024, 0, 0) == 0
     good = _lib.NetDesc(8, 256, 9, 0, 4)
     assert lib.scade_mlp_workspace_bytes(ctypes.byref(good), 1024, 0, 0) > 1024 * 256 * 4
-    assert lib.scade_mlp_packed_bytes(ctypes.byref(good)) in (92 * 16384 + 3328, 87 * 16384 + 3328)   # weight stages (pair / single form) + fp32 head table
+    # forward weight stages (pair form) + fp32 head table + 68 dgrad (W^T) stages; or the single-CTA forward stream alone
+    assert lib.scade_mlp_packed_bytes(ctypes.byref(good)) in (92 * 16384 + 4096 + 68 * 16384, 87 * 16384 + 3328)
+    # training stash of the tensor-core path: 13 + 8 D chunks of 16 KB per 128-point tile + masks + alpha
+    lay = (ctypes.c_int64 * 64)()
+    assert lib.scade_mlp_tc_stash_layout(ctypes.byref(good), 1000, lay, 64) == 35
+    assert lay[0] == 8 and lay[1] == 8 and lay[2] == lib.scade_mlp_workspace_bytes(ctypes.byref(good), 1000, 1, 1)
+    assert lay[2] >= 8 * 77 * 16384
     assert lib.scade_mlp_packed_bytes(ctypes.byref(_lib.NetDesc(4, 128, 9, 0, 4))) == 0    # fp32 path only
     st = lib.scade_raw2outputs(None, None, None, 3, None, 4, 8, None, None, None, None, None, None)
     assert st == 1 and b"raw2outputs" in lib.scade_last_error_string()
@@ -47,3 +54,21 @@ def test_cpu_tensors_are_rejected():
     from scade_b200 import functional as F_
     with pytest.raises(_lib.ScadeError):
         F_.raw2outputs(torch.zeros(2, 4, 4), torch.zeros(2, 4), torch.ones(2, 3))
+
+
+def test_stash_image_helpers_roundtrip():
+    """The numpy model of the training-stash image (tests/util.py) is self-consistent: swizzle <-> unswizzle and the
+    sign-mask bit order (used by the GPU tests to decode what the kernels stashed)."""
+    from tests.util import decode_sign_mask, sign_mask_words, stash_swizzle, stash_unswizzle
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal((256, 128)).astype(np.float16).astype(np.float32)
+    img = stash_swizzle(x)
+    assert img.size == 2 * 2 * 16384
+    np.testing.assert_array_equal(stash_unswizzle(img, 0, 2, 2), x)
+    # element (row 9, col 3) of chunk 0: piece 0 ^ (9 & 7) = 1 of row 9
+    assert img[9 * 128 + (1 << 4) + 3 * 2:][:2].view(np.float16)[0] == np.float16(x[9, 3])
+    neg = rng.random((5, 128)) < 0.5
+    np.testing.assert_array_equal(decode_sign_mask(sign_mask_words(neg)), neg)
+    one = np.zeros((1, 32), bool)
+    one[0, 5] = True                                 # element 5 = 4*1 + 1 -> s = 1, g = 1 -> bit 31 - 8 - 1
+    assert sign_mask_words(one)[0, 0] == np.uint32(1 << 22)

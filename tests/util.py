@@ -44,3 +44,54 @@ def mean_close(a, b, mean_tol, max_tol, name=""):
     assert err.mean() <= mean_tol, f"{name}: mean abs err {err.mean():.3g} > {mean_tol}"
     assert err.max() <= max_tol, f"{name}: max abs err {err.max():.3g} > {max_tol}"
     return err
+
+
+# ---- tensor-core training stash (include/scade_b200.h: scade_mlp_tc_stash_layout) ----------------------------
+def stash_swizzle(x):
+    """float [T*128, chunks*64] -> uint8 image [T][chunks][128 rows][128 B] in the K-major SWIZZLE_128B layout
+    (16-byte piece j of row r at r*128 + ((j ^ (r & 7)) << 4)); the inverse of stash_unswizzle."""
+    n, c = x.shape
+    T, chunks = n // 128, c // 64
+    tiles = np.ascontiguousarray(x.astype(np.float16).reshape(T, 128, chunks, 64).transpose(0, 2, 1, 3))   # [T, chunks, 128, 64]
+    pieces = tiles.view(np.uint8).reshape(T, chunks, 128, 8, 16)
+    out = np.empty_like(pieces)
+    r = np.arange(128)[:, None]
+    j = np.arange(8)[None, :]
+    out[:, :, r, j ^ (r & 7), :] = pieces[:, :, r, j, :]
+    return out.reshape(-1)
+
+
+def stash_unswizzle(buf, off, T, chunks, bf16=False):
+    """uint8 workspace -> float32 [T*128, chunks*64] of the chunk region at byte offset `off` (fp16 activations, or
+    bf16 gradients with bf16=True)."""
+    raw = np.asarray(buf[off:off + T * chunks * 16384]).reshape(T, chunks, 128, 8, 16)
+    r = np.arange(128)[:, None]
+    j = np.arange(8)[None, :]
+    out = np.ascontiguousarray(raw[:, :, r, j ^ (r & 7), :]).reshape(T, chunks, 128, 128)
+    if bf16:
+        halfs = (out.view(np.uint16).astype(np.uint32) << np.uint32(16)).view(np.float32)
+    else:
+        halfs = out.view(np.float16).astype(np.float32)
+    return halfs.transpose(0, 2, 1, 3).reshape(T * 128, chunks * 64)
+
+
+_SIGN_ELEM = [4 * (k & 7) + (k >> 3) for k in range(32)]      # bit (31 - k) of a mask word <- element _SIGN_ELEM[k]
+
+
+def sign_mask_words(neg):
+    """bool [..., 32 n] (True = negative pre-activation) -> uint32 [..., n] in the kernel's sign_mask32 bit order."""
+    neg = np.asarray(neg, bool)
+    g = neg.reshape(neg.shape[:-1] + (neg.shape[-1] // 32, 32))
+    w = np.zeros(g.shape[:-1], np.uint32)
+    for k in range(32):
+        w |= g[..., _SIGN_ELEM[k]].astype(np.uint32) << np.uint32(31 - k)
+    return w
+
+
+def decode_sign_mask(words):
+    """uint32 [..., n] -> bool [..., 32 n] (True = sign bit set = inactive ReLU)."""
+    words = np.asarray(words, np.uint32)
+    out = np.zeros(words.shape + (32,), bool)
+    for k in range(32):
+        out[..., _SIGN_ELEM[k]] = (words >> np.uint32(31 - k)) & np.uint32(1)
+    return out.reshape(words.shape[:-1] + (words.shape[-1] * 32,))

@@ -15,15 +15,7 @@ from oracle import scade_oracle as O                      # noqa: E402
 from scade_b200 import _lib, functional as F_, nerf_helpers as NH, synthetic as syn   # noqa: E402
 
 
-def unswizzle(buf, off, T, chunks):
-    """[T][chunks][128][128 B] swizzled image -> float32 [T*128, chunks*64]."""
-    raw = buf[off:off + T * chunks * 16384].reshape(T, chunks, 128, 8, 16)
-    r = np.arange(128)[:, None]
-    j = np.arange(8)[None, :]
-    src = j ^ (r & 7)
-    out = raw[:, :, r, src, :]                                  # [T, chunks, 128, 8, 16]
-    halfs = out.reshape(T, chunks, 128, 128).view(np.float16).astype(np.float32)      # [T, chunks, 128, 64]
-    return halfs.transpose(0, 2, 1, 3).reshape(T * 128, chunks * 64)
+from tests.util import stash_unswizzle as unswizzle          # noqa: E402
 
 
 def decode_mask(words):
@@ -93,10 +85,9 @@ def main():
     _lib.check(L.scade_mlp_backward(byref(cnet), prec, _lib.ptr(ds), P, arr, _lib.ptr(ws), ws.numel(), _lib.stream_ptr()), "bwd")
     torch.cuda.synchronize()
     buf = ws.cpu().numpy()
-    maxbits = buf[lay["gs"]:lay["gs"] + 4].view(np.uint32)[0]
-    e = int(maxbits >> 23) - 127
-    scale = 2.0 ** (5 - e)
-    print("max|d_out| =", np.abs(d_out).max(), "decoded", np.array([maxbits], np.uint32).view(np.float32)[0], "scale", scale)
+    maxbits = int(buf[lay["gs"]:lay["gs"] + 4].view(np.uint32)[0])
+    scale = 2.0 ** (5 - ((maxbits >> 23) - 127))
+    print("scale", scale)
     # teacher-forced reference (fp64 arithmetic on the stashed fp16 activations and masks): isolates the backward kernels
     # from the sign flips the fp16 forward causes near z = 0
     p64 = {k: v.astype(np.float64) for k, v in params.items()}
