@@ -317,10 +317,19 @@ def run_train(args):
     qf = R_.NetworkQuery(NH.get_embedder(9, 0)[0], NH.get_embedder(0, 0)[0], bb_center, bb_scale, precision=args.precision)
     kw = dict(network_fn=nets[0], network_query_fn=qf, N_samples=Nc, embedded_cam=torch.tensor((), device=dev), perturb=1.0,
               N_importance=Nf, network_fine=nets[1], raw_noise_std=0.0)
-    opt = torch.optim.Adam([p for n in nets for p in n.parameters()], lr=5e-4, betas=(0.9, 0.999))
     scale = torch.ones(1, device=dev, requires_grad=True)
     shift = torch.zeros(1, device=dev, requires_grad=True)
-    opt_ss = torch.optim.Adam([scale, shift], lr=1e-6)
+    flat = None
+    if args.optimizer == "fused":
+        # parameters of both networks + scale / shift as views of one flat buffer: one memset, one all-reduce, one Adam launch
+        from scade_b200.optim import FusedAdam, flatten_parameters
+        net_params = [p for n in nets for p in n.parameters()]
+        flat = flatten_parameters(net_params, [scale, shift])
+        opt = FusedAdam(net_params, lr=5e-4, betas=(0.9, 0.999), flat=flat)              # RS:469
+        opt_ss = FusedAdam([scale, shift], lr=1e-6, flat=flat)                           # RS:888
+    else:
+        opt = torch.optim.Adam([p for n in nets for p in n.parameters()], lr=5e-4, betas=(0.9, 0.999))
+        opt_ss = torch.optim.Adam([scale, shift], lr=1e-6)
     lo, hi = shard_range(N, rank, world)
     to = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
     rb = to(syn.make_ray_batch(N, seed=80)[lo:hi])
@@ -329,8 +338,8 @@ def run_train(args):
 
     def step():
         opt.zero_grad(set_to_none=False)
-        opt_ss.zero_grad()
-        losses = sharded_train_step(rb, target_s, target_h, scale, shift, kw, n_global=N)
+        opt_ss.zero_grad(set_to_none=False)
+        losses = sharded_train_step(rb, target_s, target_h, scale, shift, kw, n_global=N, flat=flat)
         opt.step()
         opt_ss.step()
         return losses
@@ -363,7 +372,7 @@ def run_train(args):
             "config": {"workload": "BASELINE config 3 train step", "global_rays": N,
                        "precision": "tcgen05 fwd + dgrad + wgrad, fp32 master weights / gradients / Adam" if args.precision == "tc_f16"
                        else "fp32 FFMA GEMMs (fwd+bwd)",
-                       "collective": "1 NCCL all-reduce / step, flat fp32 buffer 4.72 MB"},
+                       "collective": "1 NCCL all-reduce / step, flat fp32 buffer 4.72 MB", "optimizer": args.optimizer},
             "gpu_launches": int(lib.scade_kernel_launch_count() - l0), "loss": float(losses["loss"]),
             "roofline": {"bound": "tensor", "achieved": flop_step / sec / 1e12, "peak": sustained, "unit": "TFLOP/s",
                          "frac": flop_step / sec / 1e12 / sustained, "peak_source": f"{src} bf16 sustained", "traffic": None}}), flush=True)
@@ -380,6 +389,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default="tc_f16", choices=["tc_f16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--optimizer", default="fused", choices=["fused", "torch"],
+                    help="train workload: fused = flat parameters + scade_adam_step (default); torch = torch.optim.Adam on 48 tensors")
     ap.add_argument("--workload", default="render", choices=["render", "train"],
                     help="render = BASELINE metric (default); train = config 3 (4096 rays, 64c+128f, K=20, fwd+loss+bwd+allreduce+Adam)")
     args = ap.parse_args()

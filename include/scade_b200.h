@@ -201,6 +201,17 @@ int scade_img2mse(const float* x, const float* y, int64_t n, int64_t denominator
                   float* loss_out, float* d_x, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Optimizer: torch.optim.Adam(grad_vars, lr, betas=(0.9, 0.999)).step()  (RS:469, RS:993)
+ * --------------------------------------------------------------------------------------------- */
+/* One Adam step (no amsgrad / weight decay) over a flat fp32 range of n parameters, in place: param, exp_avg, exp_avg_sq
+ * are updated from grad.  `step` is the 1-based step count AFTER this step (torch's state['step']); lr is the value
+ * update_learning_rate (train_utils/hyperparameter_update.py:3-5) put into param_groups.  All four buffers are
+ * 16-byte aligned device pointers.  Hyper-parameters are doubles (as in Python): 1 - beta and the bias corrections are
+ * formed in double and rounded to fp32 once, like torch does. */
+int scade_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, double lr,
+                    double beta1, double beta2, double eps, int64_t step, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * render_rays (RS:581-751), N_importance > 0 branch, forward only, one call, one stream
  * --------------------------------------------------------------------------------------------- */
 typedef struct {

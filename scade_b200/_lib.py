@@ -7,7 +7,7 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int64, c_size_t, c_void_p
+from ctypes import POINTER, Structure, c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_size_t, c_void_p
 
 import torch
 
@@ -74,6 +74,7 @@ _SIGNATURES = {
     "scade_space_carving_loss": (c_int, [_P, _P, c_int, _P, c_int, c_int64, c_int, c_int, c_float, c_float, _P, _P, _P,
                                          _P, c_size_t, _P]),
     "scade_img2mse": (c_int, [_P, _P, c_int64, c_int64, c_float, _P, _P, _P]),
+    "scade_adam_step": (c_int, [_P, _P, _P, _P, c_int64, c_double, c_double, c_double, c_double, c_int64, _P]),
     "scade_render_rays_workspace_bytes": (c_size_t, [POINTER(RenderCfg), POINTER(NetDesc), POINTER(NetDesc), c_int64]),
     "scade_render_rays_forward": (c_int, [POINTER(RenderCfg), _P, c_int64, POINTER(Net), POINTER(Net), _P, _P, _P,
                                           POINTER(RenderOut), _P, c_size_t, _P]),

@@ -65,13 +65,14 @@ class FlatAllReduce:
 
 def sharded_train_step(ray_batch, target_s, target_h, scale, shift, render_kwargs, n_global=None,
                        space_carving_weight=0.007, threshold=0.0, mask=None, t_rand=None, u_coarse=None, u_fine=None,
-                       group=None):
+                       group=None, flat=None):
     """One SCADE training step (RS:954-985) on this rank's ray shard, followed by the single gradient all-reduce.
 
     ray_batch [n_local,11], target_s [n_local,3], target_h [K,n_local,1] are this rank's slices of the step's
     N_rand rays (all from one image, same scale/shift on every rank, RS:945-952).  After the call every rank holds
     the global gradient in ``.grad`` of the network parameters / scale / shift, exactly as after ``loss.backward()``
-    on one GPU.  Returns a dict of GLOBAL losses (tensors)."""
+    on one GPU.  Returns a dict of GLOBAL losses (tensors).  `flat`: the FlatParams holding the networks' parameters and
+    scale / shift, if the caller flattened them (then the all-reduce is in place on its gradient buffer)."""
     from . import nerf_helpers as NH
     from . import render as R_
     rank, world = _world(group)
@@ -86,13 +87,23 @@ def sharded_train_step(ray_batch, target_s, target_h, scale, shift, render_kwarg
         * (float(n_local) / float(n_global))
     loss = img_loss + space_carving_weight * sc + img_loss0                             # RS:976,983
     loss.backward()                                                                     # RS:985
+    losses = torch.stack([img_loss.detach(), sc.detach(), img_loss0.detach()])
+    if flat is not None and flat.intact():
+        # parameters / gradients live in flat buffers (scade_b200.optim.FlatParams): the loss partial sums ride in the
+        # spare tail and the exchange is ONE in-place all-reduce -- nothing is packed or copied
+        tail = flat.tail()
+        tail[:3].copy_(losses)
+        if world > 1:
+            dist.all_reduce(flat.flat_grad, op=dist.ReduceOp.SUM, group=group)
+        losses = tail[:3].clone()
+        return {"img_loss": losses[0], "space_carving": losses[1], "img_loss0": losses[2],
+                "loss": losses[0] + space_carving_weight * losses[1] + losses[2]}
     nets = [R_._unwrap(render_kwargs["network_fn"]), R_._unwrap(render_kwargs["network_fine"] or render_kwargs["network_fn"])]
     params = [p for net in dict.fromkeys(nets) for p in net.parameters() if p.requires_grad]
     for p in params:
         if p.grad is None:
             p.grad = torch.zeros_like(p)
     extras = [t.grad for t in (scale, shift) if torch.is_tensor(t) and t.requires_grad and t.grad is not None]
-    losses = torch.stack([img_loss.detach(), sc.detach(), img_loss0.detach()])
     FlatAllReduce([p.grad for p in params] + extras + [losses]).all_reduce(group)
     return {"img_loss": losses[0], "space_carving": losses[1], "img_loss0": losses[2],
             "loss": losses[0] + space_carving_weight * losses[1] + losses[2]}

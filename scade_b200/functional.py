@@ -21,6 +21,16 @@ def _L():
     return _lib.load()
 
 
+_weights_epoch = 0
+
+
+def mark_weights_changed():
+    """Parameters were updated behind autograd's back (a raw kernel such as scade_adam_step does not bump tensor version
+    counters): every NetHandle re-packs its fp16 tile image on next use."""
+    global _weights_epoch
+    _weights_epoch += 1
+
+
 def _bytes(n, device):
     return torch.empty(max(int(n), 256), dtype=torch.uint8, device=device)
 
@@ -58,7 +68,7 @@ class NetHandle:
         return net
 
     def packed(self):
-        key = tuple((p.data_ptr(), p._version) for p in self.params)
+        key = (_weights_epoch,) + tuple((p.data_ptr(), p._version) for p in self.params)
         if self._packed is None or key != self._packed_key:
             nbytes = _L().scade_mlp_packed_bytes(byref(self.desc))
             if nbytes == 0:
@@ -92,12 +102,25 @@ def stash_layout(handle, P):
 
 
 def _mlp_backward(handle, precision, d_out, P, ws, device):
-    grads = [torch.zeros_like(p) for p in handle.params]
+    """scade_mlp_backward ACCUMULATES.  When every parameter already owns a contiguous fp32 .grad (the training loop's state
+    after zero_grad(set_to_none=False), or scade_b200.optim.FlatParams views) the kernels add straight into it and autograd gets
+    None for the parameters; otherwise one zeroed flat buffer is carved into per-parameter gradients and returned."""
+    params = handle.params
+    direct = all(p.grad is not None and p.grad.is_contiguous() and p.grad.dtype == torch.float32 and p.grad.is_cuda for p in params)
+    if direct:
+        grads = [p.grad for p in params]
+    else:
+        sizes = [(p.numel() + 3) // 4 * 4 for p in params]
+        flat = torch.zeros(sum(sizes), dtype=torch.float32, device=device)
+        grads, off = [], 0
+        for p, n in zip(params, sizes):
+            grads.append(flat[off:off + p.numel()].view(p.shape))
+            off += n
     net = handle.struct(precision)
     arr = (c_void_p * len(grads))(*[g.data_ptr() for g in grads])
     check(_L().scade_mlp_backward(byref(net), precision, ptr(d_out), P, arr, ptr(ws), ws.numel(), stream_ptr()),
           "scade_mlp_backward")
-    return grads
+    return [None] * len(params) if direct else grads
 
 
 class _MLPRaysFn(torch.autograd.Function):

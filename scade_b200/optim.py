@@ -1,0 +1,160 @@
+"""Flat parameter storage and a fused Adam for the SCADE training step.
+
+The reference keeps 48 parameter tensors (two NeRFs) in one ``torch.optim.Adam`` (run_scade_scannet.py:469) and a second
+Adam for the per-image depth scale / shift (RS:888); every step runs ``zero_grad`` -> ``backward`` -> ``step`` over all of
+them (RS:966-997).  Here the same ``nn.Parameter`` objects are re-homed as views of ONE flat fp32 buffer, with ``.grad``
+views of a second one, so that per step
+
+  * ``zero_grad`` is one memset,
+  * the CUDA backward kernels accumulate straight into ``.grad`` (no per-tensor temporaries, no AccumulateGrad adds),
+  * the multi-GPU gradient exchange is one in-place all-reduce of the flat gradient (scade_b200/dist.py),
+  * ``FusedAdam.step`` is one kernel launch (``scade_adam_step``).
+
+``FusedAdam`` is a ``torch.optim.Optimizer``: ``param_groups[i]['lr']`` is honoured, so ``update_learning_rate``
+(train_utils/hyperparameter_update.py:3-5) keeps working, and ``state_dict()`` has torch.optim.Adam's layout
+(``step``, ``exp_avg``, ``exp_avg_sq`` per parameter), so the reference's checkpoints (RS:1006-1011) stay loadable.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+from ._lib import check, ptr, stream_ptr
+
+TAIL = 8        # spare floats behind the flat gradient: loss partial sums ride along in the single all-reduce
+
+
+class FlatParams:
+    """Re-homes `params` (fp32, same device) as views of one buffer; their gradients as views of another."""
+
+    def __init__(self, params):
+        self.params = [p for p in params]
+        if not self.params:
+            raise ValueError("no parameters")
+        dev = self.params[0].device
+        offs, off = [], 0
+        for p in self.params:
+            if p.dtype != torch.float32 or p.device != dev:
+                raise ValueError("FlatParams needs fp32 parameters on one device")
+            offs.append(off)
+            off += (p.numel() + 3) // 4 * 4                   # keep every view 16-byte aligned
+        self.offsets, self.numel = offs, off
+        self.flat = torch.zeros(off, dtype=torch.float32, device=dev)
+        self.flat_grad = torch.zeros(off + TAIL, dtype=torch.float32, device=dev)
+        with torch.no_grad():
+            for p, o in zip(self.params, offs):
+                n = p.numel()
+                self.flat[o:o + n].copy_(p.data.reshape(-1))
+                p.data = self.flat[o:o + n].view(p.shape)
+                p.grad = self.flat_grad[o:o + n].view(p.shape)
+
+    def grads(self):
+        return self.flat_grad[:self.numel]
+
+    def tail(self):
+        return self.flat_grad[self.numel:]
+
+    def zero_grad(self):
+        self.flat_grad.zero_()
+
+    def intact(self):
+        """True while every parameter and gradient still aliases the flat buffers (p.grad = None or p.data = ... breaks it)."""
+        b, g = self.flat.data_ptr(), self.flat_grad.data_ptr()
+        return all(p.data_ptr() == b + 4 * o and p.grad is not None and p.grad.data_ptr() == g + 4 * o
+                   for p, o in zip(self.params, self.offsets))
+
+
+def flatten_parameters(*modules_or_params):
+    """FlatParams over the parameters of the given modules / iterables of parameters / parameters, in order, de-duplicated."""
+    params, seen = [], set()
+    for m in modules_or_params:
+        it = m.parameters() if isinstance(m, torch.nn.Module) else ([m] if torch.is_tensor(m) else m)
+        for p in it:
+            if id(p) not in seen:
+                seen.add(id(p))
+                params.append(p)
+    return FlatParams(params)
+
+
+class FusedAdam(torch.optim.Optimizer):
+    """torch.optim.Adam(params, lr, betas, eps) semantics (RS:469) with one CUDA launch per contiguous parameter range.
+
+    ``FusedAdam(flat)``: all parameters of a FlatParams, one launch.  ``FusedAdam(params, flat=flat)``: `params` must be a
+    consecutive run of ``flat.params`` (e.g. the two networks, or scale / shift with their own learning rate, RS:888), one
+    launch on that slice.  ``FusedAdam(params)``: any CUDA fp32 parameters, one launch each."""
+
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, flat=None):
+        if isinstance(params, FlatParams):
+            flat, params = params, params.params
+        plist = list(params)
+        super().__init__(plist, dict(lr=lr, betas=betas, eps=eps))
+        self.flat, self._range = flat, None
+        if flat is not None:
+            ids = [id(p) for p in flat.params]
+            i0 = ids.index(id(plist[0]))
+            if [id(p) for p in plist] != ids[i0:i0 + len(plist)]:
+                raise ValueError("FusedAdam(params, flat=...): params must be a consecutive run of flat.params")
+            end = flat.offsets[i0 + len(plist)] if i0 + len(plist) < len(ids) else flat.numel
+            self._range = (flat.offsets[i0], end, i0, i0 + len(plist))
+        self._m = self._v = None
+        self._step = 0
+
+    def _flat_state(self):
+        if self._m is None:
+            f = self.flat
+            o0, o1, i0, i1 = self._range
+            self._m = torch.zeros(o1 - o0, dtype=torch.float32, device=f.flat.device)
+            self._v = torch.zeros_like(self._m)
+            for p, o in zip(f.params[i0:i1], f.offsets[i0:i1]):
+                st = self.state[p]
+                n, o = p.numel(), o - o0
+                if "exp_avg" in st:                           # state loaded from a checkpoint: adopt it
+                    self._m[o:o + n].copy_(st["exp_avg"].reshape(-1))
+                    self._v[o:o + n].copy_(st["exp_avg_sq"].reshape(-1))
+                    self._step = int(st.get("step", self._step))
+                st["exp_avg"], st["exp_avg_sq"] = self._m[o:o + n].view(p.shape), self._v[o:o + n].view(p.shape)
+        return self._m, self._v
+
+    def zero_grad(self, set_to_none=False):
+        if self.flat is not None and self.flat.intact():
+            o0, o1 = self._range[:2]
+            if o0 == 0 and o1 == self.flat.numel:
+                self.flat.zero_grad()
+            else:
+                self.flat.flat_grad[o0:o1].zero_()
+        else:
+            super().zero_grad(set_to_none=set_to_none)
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        from . import functional as F_
+        loss = closure() if closure is not None else None
+        L = _lib.load()
+        g0 = self.param_groups[0]
+        if self.flat is not None and self.flat.intact() and len(self.param_groups) == 1:
+            m, v = self._flat_state()
+            self._step += 1
+            f = self.flat
+            o0, o1, i0, i1 = self._range
+            check(L.scade_adam_step(ptr(f.flat[o0:o1]), ptr(f.flat_grad[o0:o1]), ptr(m), ptr(v), o1 - o0, float(g0["lr"]),
+                                    float(g0["betas"][0]), float(g0["betas"][1]), float(g0["eps"]), self._step, stream_ptr()),
+                  "scade_adam_step")
+            for p in f.params[i0:i1]:
+                self.state[p]["step"] = self._step
+            F_.mark_weights_changed()
+            return loss
+        for group in self.param_groups:
+            for p in group["params"]:
+                if p.grad is None:
+                    continue
+                st = self.state[p]
+                if "exp_avg" not in st:
+                    st["step"], st["exp_avg"], st["exp_avg_sq"] = 0, torch.zeros_like(p), torch.zeros_like(p)
+                st["step"] = int(st["step"]) + 1
+                if p.data_ptr() % 16 or p.grad.data_ptr() % 16 or not p.is_contiguous() or not p.grad.is_contiguous():
+                    raise _lib.ScadeError("FusedAdam needs contiguous 16-byte aligned fp32 CUDA parameters and gradients")
+                check(L.scade_adam_step(ptr(p.data), ptr(p.grad), ptr(st["exp_avg"]), ptr(st["exp_avg_sq"]), p.numel(),
+                                        float(group["lr"]), float(group["betas"][0]), float(group["betas"][1]), float(group["eps"]),
+                                        st["step"], stream_ptr()), "scade_adam_step")
+        F_.mark_weights_changed()
+        return loss
