@@ -33,6 +33,7 @@
 #include <cuda_fp16.h>
 
 #include <algorithm>
+#include <type_traits>
 
 #include "mlp_common.cuh"
 #include "tc_ptx.cuh"
@@ -142,7 +143,7 @@ struct TrainLayout {
   unsigned long long total;
   unsigned long long h[8];       // [T][4]   output of pts_linears[l] (post-ReLU)
   unsigned long long dz[8];      // [T][4]   d loss / d (pre-activation of pts_linears[l]), scaled
-  unsigned long long maskh[8];   // [T][128][2] uint4: sign bits of pts_linears[l] pre-activations
+  unsigned long long maskh[8];   // [T][2 column halves][128 rows] uint4: sign bits of pts_linears[l] pre-activations (a warp stores 512 B)
 };
 struct StashArgs {
   uint8_t* ws;
@@ -770,10 +771,10 @@ __global__ void __launch_bounds__(PP_THREADS, 1) nerf_mlp_tc_pp_kernel(const __g
           tmem_ld32(t_col, rbuf[0]);
           if (kStash) {
             if (l == 0 && half == 0 && lane == 0) {       // the encoding chunk of this tile is complete: stash this warp's 32 rows
-              bulk_s2g(sa.ws + sa.L.emb + (size_t)tile_g * CHUNK_BYTES + quarter * 4096, smem_u32(emb_tile) + quarter * 4096, 4096);
+              if (!(a.dbg & 4)) bulk_s2g(sa.ws + sa.L.emb + (size_t)tile_g * CHUNK_BYTES + quarter * 4096, smem_u32(emb_tile) + quarter * 4096, 4096);
               bulk_commit();
             }
-            if (lane == 0) bulk_wait_read0();             // earlier stash stores no longer read the rows overwritten below
+            if (lane == 0 && !(a.dbg & 16)) bulk_wait_read0();             // earlier stash stores no longer read the rows overwritten below
             __syncwarp();
           }
 #pragma unroll
@@ -815,14 +816,14 @@ __global__ void __launch_bounds__(PP_THREADS, 1) nerf_mlp_tc_pp_kernel(const __g
           }
           signal_a_ready();
           if (kStash) {
-            if (relu)
-              *reinterpret_cast<uint4*>(sa.ws + sa.L.maskh[l] + ((size_t)(tile_g * TILE_M + row) * 2 + half) * 16) =
+            if (relu && !(a.dbg & 8))
+              *reinterpret_cast<uint4*>(sa.ws + sa.L.maskh[l] + ((size_t)(tile_g * 2 + half) * TILE_M + row) * 16) =
                   make_uint4(sgn[0], sgn[1], sgn[2], sgn[3]);
             if (lane == 0) {
               uint8_t* dst = sa.ws + (kind == 2 ? sa.L.feat : sa.L.h[l]) + (size_t)(tile_g * 4 + 2 * half) * CHUNK_BYTES + quarter * 4096;
               const uint32_t src = smem_u32(a_tile) + 2 * half * CHUNK_BYTES + quarter * 4096;
-              bulk_s2g(dst, src, 4096);
-              bulk_s2g(dst + CHUNK_BYTES, src + CHUNK_BYTES, 4096);
+              if (!(a.dbg & 4)) bulk_s2g(dst, src, 4096);
+              if (!(a.dbg & 4)) bulk_s2g(dst + CHUNK_BYTES, src + CHUNK_BYTES, 4096);
               bulk_commit();
             }
           }
@@ -832,7 +833,7 @@ __global__ void __launch_bounds__(PP_THREADS, 1) nerf_mlp_tc_pp_kernel(const __g
             float cr = 0.f, cg = 0.f, cb = 0.f;
             uint32_t sgn[4];
             if (kStash) {
-              if (lane == 0) bulk_wait_read0();           // A chunks 0/1 (feature, fully consumed by now) become the h_v staging area
+              if (lane == 0 && !(a.dbg & 16)) bulk_wait_read0();           // A chunks 0/1 (feature, fully consumed by now) become the h_v staging area
               __syncwarp();
             }
 #pragma unroll 1
@@ -877,8 +878,8 @@ __global__ void __launch_bounds__(PP_THREADS, 1) nerf_mlp_tc_pp_kernel(const __g
               if (lane == 0) {
                 uint8_t* dst = sa.ws + sa.L.hv + (size_t)(tile_g * 2) * CHUNK_BYTES + quarter * 4096;
                 const uint32_t src = smem_u32(a_tile) + quarter * 4096;
-                bulk_s2g(dst, src, 4096);
-                bulk_s2g(dst + CHUNK_BYTES, src + CHUNK_BYTES, 4096);
+                if (!(a.dbg & 4)) bulk_s2g(dst, src, 4096);
+                if (!(a.dbg & 4)) bulk_s2g(dst + CHUNK_BYTES, src + CHUNK_BYTES, 4096);
                 bulk_commit();
               }
             }

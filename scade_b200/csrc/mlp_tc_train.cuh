@@ -173,12 +173,14 @@ __global__ void __launch_bounds__(PP_THREADS, 1) nerf_mlp_tc_dgrad_kernel(const 
       }
 
       // ---- layers, backwards: j = 0 views^T -> d_feature; j = 1 feature^T (+ alpha) -> dZ_{D-1}; j >= 2 pts_{D+1-j}^T -> dZ_{D-j}
-      for (int j = 0; j < plan.n_layers; ++j) {
-        uint4 mk = make_uint4(0u, 0u, 0u, 0u);
-        if (j >= 1) mk = *reinterpret_cast<const uint4*>(a.ws + a.L.maskh[D - j] + (grow * 2 + half) * 16);
-        mbar_wait(my_acc, acc_phase);
-        acc_phase ^= 1;
-        tc_fence_after();
+      // The body is instantiated twice (with / without the alpha_linear term) so that the 8 common layers carry no predicated
+      // FFMA / LDG; addresses are formed from per-thread constants hoisted out of the loops.
+      const uint32_t row_off = (uint32_t)((row >> 3) * 1024 + (row & 7) * 128);
+      const uint32_t rx16 = (uint32_t)(row & 7) << 4;
+      uint8_t* const my_chunks = a_tile + 2 * half * CHUNK_BYTES + row_off;          // this thread's row in chunks 2h, 2h+1
+      const float4* const wa4 = reinterpret_cast<const float4*>(tail->w_alpha) + half * 32;
+      auto layer_epilogue = [&](auto alpha_tag, const uint4 mk) {
+        constexpr bool kAlpha = decltype(alpha_tag)::value;
         uint32_t rbuf[2][32];
         const uint32_t t_col = t_lane + half * 128;
         tmem_ld32(t_col, rbuf[0]);
@@ -190,8 +192,7 @@ __global__ void __launch_bounds__(PP_THREADS, 1) nerf_mlp_tc_dgrad_kernel(const 
           tmem_ld_wait();
           if (c4 + 1 < 4) tmem_ld32(t_col + (c4 + 1) * 32, rbuf[(c4 + 1) & 1]);
           const uint32_t word = c4 == 0 ? mk.x : (c4 == 1 ? mk.y : (c4 == 2 ? mk.z : mk.w));
-          const float* wa = tail->w_alpha + half * 128 + c4 * 32;
-          uint8_t* chunk = a_tile + (2 * half + (c4 >> 1)) * CHUNK_BYTES;
+          uint8_t* const dst = my_chunks + (c4 >> 1) * CHUNK_BYTES;
 #pragma unroll
           for (int pc = 0; pc < 4; ++pc) {
             uint32_t qq[4];
@@ -200,18 +201,29 @@ __global__ void __launch_bounds__(PP_THREADS, 1) nerf_mlp_tc_dgrad_kernel(const 
               const int s = 2 * pc + ss;
               float v[4];
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                v[e] = __uint_as_float(r[4 * s + e]);
-                if (j == 1) v[e] = fmaf(d_alpha, __ldg(wa + 4 * s + e), v[e]);       // alpha_linear^T  (H:233)
+              for (int e = 0; e < 4; ++e) v[e] = __uint_as_float(r[4 * s + e]);
+              if (kAlpha) {                                                           // alpha_linear^T  (H:233)
+                const float4 w = __ldg(wa4 + c4 * 8 + s);
+                v[0] = fmaf(d_alpha, w.x, v[0]); v[1] = fmaf(d_alpha, w.y, v[1]);
+                v[2] = fmaf(d_alpha, w.z, v[2]); v[3] = fmaf(d_alpha, w.w, v[3]);
               }
               uint32_t m01, m23;
               inactive_masks(word, s, &m01, &m23);                                    // j == 0: word = 0 -> nothing masked
               qq[2 * ss] = pack_sat_f16x2(v[0], v[1]) & ~m01;
               qq[2 * ss + 1] = pack_sat_f16x2(v[2], v[3]) & ~m23;
             }
-            *reinterpret_cast<uint4*>(chunk + sw128_offset(row, (c4 & 1) * 4 + pc)) = make_uint4(qq[0], qq[1], qq[2], qq[3]);
+            *reinterpret_cast<uint4*>(dst + ((uint32_t)(((c4 & 1) * 4 + pc) << 4) ^ rx16)) = make_uint4(qq[0], qq[1], qq[2], qq[3]);
           }
         }
+      };
+      for (int j = 0; j < plan.n_layers; ++j) {
+        uint4 mk = make_uint4(0u, 0u, 0u, 0u);
+        if (j >= 1) mk = *reinterpret_cast<const uint4*>(a.ws + a.L.maskh[D - j] + ((size_t)(tile_g * 2 + half) * TILE_M + row) * 16);
+        mbar_wait(my_acc, acc_phase);
+        acc_phase ^= 1;
+        tc_fence_after();
+        if (j == 1) layer_epilogue(std::true_type{}, mk);
+        else layer_epilogue(std::false_type{}, mk);
         if (j + 1 < plan.n_layers) {
           signal_a_ready();
         } else {

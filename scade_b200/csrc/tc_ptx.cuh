@@ -243,25 +243,32 @@ __device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t saddr, uint32_t l
 __host__ __device__ constexpr uint32_t make_idesc_mn(int M, int N) {
   return (1u << 4) | (1u << 15) | (1u << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
-// byte permute; selector nibbles with bit 3 set replicate the sign bit of the selected byte over the result byte
-__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
-  uint32_t d;
-  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
-  return d;
-}
 // fp32 pair -> fp16 pair, saturating to +-65504 instead of inf (scaled gradients must never turn into NaN downstream)
 __device__ __forceinline__ uint32_t pack_sat_f16x2(float lo, float hi) {
   uint32_t d;
   asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
   return d;
 }
+// byte permute; selector nibbles with bit 3 set replicate the sign bit of the selected byte over the result byte
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
+  uint32_t d;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+  return d;
+}
 // Sign bits of 32 fp32 accumulators as one word, in the order the dgrad epilogue expands them with prmt:
 // bit (31 - 8g - s) <- element 4s + g   (s = 0..7, g = 0..3), so that (word << s) carries elements 4s..4s+3 in its 4 byte MSBs.
 __device__ __forceinline__ uint32_t sign_mask32(const uint32_t* r) {
-  uint32_t m = 0;
+  // four independent 8-deep funnel-shift chains (one per byte of the result) instead of one 32-deep chain: the epilogue
+  // that calls this sits on the kernel's critical path and a dependent SHF chain costs its latency, not its issue slots
+  uint32_t part[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
-  for (int k = 0; k < 32; ++k) m = __funnelshift_l(r[4 * (k & 7) + (k >> 3)], m, 1);
-  return m;
+  for (int s = 0; s < 8; ++s) {
+#pragma unroll
+    for (int g = 0; g < 4; ++g) part[g] = __funnelshift_l(r[4 * s + g], part[g], 1);      // bit (7 - s) of part[g] <- element 4s + g
+  }
+  const uint32_t lo = prmt(part[3], part[2], 0x0040u);      // byte 0 = part[3], byte 1 = part[2]
+  const uint32_t hi = prmt(part[1], part[0], 0x0040u);      // byte 0 = part[1], byte 1 = part[0]
+  return prmt(lo, hi, 0x5410u);                             // bytes (part[3], part[2], part[1], part[0]) -> bit 31 - 8g - s
 }
 // masks for the packed fp16 pairs (4s, 4s+1) and (4s+2, 4s+3): 0xFFFF where the sign bit was set (= inactive ReLU)
 __device__ __forceinline__ void inactive_masks(uint32_t word, int s, uint32_t* m01, uint32_t* m23) {

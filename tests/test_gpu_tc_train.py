@@ -89,7 +89,7 @@ def test_tc_backward_teacher_forced(dev, P, gscale):
     for l in range(D):
         hs.append(stash_unswizzle(buf, lay["h"][l], T, 4)[:P])
         assert rel(hs[l], np.maximum(acts["pre"][l], 0)) < 2e-3, l
-        m = decode_sign_mask(buf[lay["maskh"][l]:lay["maskh"][l] + T * 128 * 32].view(np.uint32).reshape(T * 128, 8))[:P]
+        m = decode_sign_mask(buf[lay["maskh"][l]:lay["maskh"][l] + T * 128 * 32].view(np.uint32).reshape(T, 2, 128, 4).transpose(0, 2, 1, 3).reshape(T * 128, 8))[:P]
         inact.append(m)
         flips = m != (acts["pre"][l] < 0)
         assert flips.mean() < 1e-3 and (not flips.any() or np.abs(acts["pre"][l][flips]).max() < 5e-3), l   # only next to zero

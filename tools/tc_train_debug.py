@@ -64,7 +64,7 @@ def main():
     for l in range(D):
         hh = unswizzle(buf, lay["h"][l], T, 4)[:P]
         print(f"h[{l}]  rel err:", rel(hh, np.maximum(acts["pre"][l], 0)))
-        mw = buf[lay["maskh"][l]:lay["maskh"][l] + T * 128 * 32].view(np.uint32).reshape(T * 128, 8)
+        mw = buf[lay["maskh"][l]:lay["maskh"][l] + T * 128 * 32].view(np.uint32).reshape(T, 2, 128, 4).transpose(0, 2, 1, 3).reshape(T * 128, 8)
         inact = decode_mask(mw)[:P]
         refm = acts["pre"][l] < 0
         print(f"mask[{l}] mismatches:", int((inact != refm).sum()), "of", refm.size,
@@ -92,7 +92,7 @@ def main():
     # from the sign flips the fp16 forward causes near z = 0
     p64 = {k: v.astype(np.float64) for k, v in params.items()}
     H = [unswizzle(buf, lay["h"][l], T, 4)[:P].astype(np.float64) for l in range(D)]
-    inact = [decode_mask(buf[lay["maskh"][l]:lay["maskh"][l] + T * 128 * 32].view(np.uint32).reshape(T * 128, 8))[:P] for l in range(D)]
+    inact = [decode_mask(buf[lay["maskh"][l]:lay["maskh"][l] + T * 128 * 32].view(np.uint32).reshape(T, 2, 128, 4).transpose(0, 2, 1, 3).reshape(T * 128, 8))[:P] for l in range(D)]
     feat64, hv64, emb64 = feat.astype(np.float64), hv.astype(np.float64), emb.astype(np.float64)
     d_rgb, d_sigma = d_out[:, :3].astype(np.float64), d_out[:, 3:4].astype(np.float64)
     al64 = al.astype(np.float64)[:, None]
