@@ -89,13 +89,7 @@ def sharded_train_step(ray_batch, target_s, target_h, scale, shift, render_kwarg
     loss.backward()                                                                     # RS:985
     losses = torch.stack([img_loss.detach(), sc.detach(), img_loss0.detach()])
     if flat is not None and flat.intact():
-        # parameters / gradients live in flat buffers (scade_b200.optim.FlatParams): the loss partial sums ride in the
-        # spare tail and the exchange is ONE in-place all-reduce -- nothing is packed or copied
-        tail = flat.tail()
-        tail[:3].copy_(losses)
-        if world > 1:
-            dist.all_reduce(flat.flat_grad, op=dist.ReduceOp.SUM, group=group)
-        losses = tail[:3].clone()
+        losses = flat_exchange(flat, losses, group)
         return {"img_loss": losses[0], "space_carving": losses[1], "img_loss0": losses[2],
                 "loss": losses[0] + space_carving_weight * losses[1] + losses[2]}
     nets = [R_._unwrap(render_kwargs["network_fn"]), R_._unwrap(render_kwargs["network_fine"] or render_kwargs["network_fn"])]
@@ -107,6 +101,18 @@ def sharded_train_step(ray_batch, target_s, target_h, scale, shift, render_kwarg
     FlatAllReduce([p.grad for p in params] + extras + [losses]).all_reduce(group)
     return {"img_loss": losses[0], "space_carving": losses[1], "img_loss0": losses[2],
             "loss": losses[0] + space_carving_weight * losses[1] + losses[2]}
+
+
+def flat_exchange(flat, partials, group=None):
+    """Gradient exchange when parameters / gradients live in flat buffers (scade_b200.optim.FlatParams): the loss partial
+    sums ride in the spare tail behind the gradients and the exchange is ONE in-place all-reduce of that buffer -- nothing
+    is packed or copied.  Returns the reduced partial sums."""
+    k = partials.numel()
+    tail = flat.tail()
+    tail[:k].copy_(partials)
+    if _world(group)[1] > 1:
+        dist.all_reduce(flat.flat_grad, op=dist.ReduceOp.SUM, group=group)
+    return tail[:k].clone()
 
 
 def F_img2mse(x, y, denominator):

@@ -9,7 +9,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from scade_b200.dist import FlatAllReduce, shard_range
+from scade_b200.dist import FlatAllReduce, flat_exchange, shard_range
 
 
 def test_shard_range_partitions_exactly():
@@ -46,6 +46,19 @@ def _worker(rank, world, port, out_dir):
     part = (x[lo:hi] ** 2).sum().reshape(1) / (n * 3)
     FlatAllReduce([part]).all_reduce()
     assert torch.allclose(part, (x ** 2).mean().reshape(1), rtol=1e-5)
+    # flat parameter storage: gradients + loss partials in ONE in-place all-reduce (scade_b200.optim.FlatParams)
+    from scade_b200.optim import flatten_parameters
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.Linear(5, 2))
+    scale = torch.ones(1, requires_grad=True)
+    flat = flatten_parameters(net, [scale])
+    xs = torch.from_numpy(np.random.default_rng(9).random((8, 6)).astype(np.float32))
+    lo, hi = shard_range(8, rank, world)
+    loss = (net(xs[lo:hi]) * scale).pow(2).sum() / 8
+    loss.backward()
+    red = flat_exchange(flat, torch.stack([loss.detach(), loss.detach() * 0 + 1.0]))
+    torch.save({"grads": [p.grad.clone() for p in flat.params], "red": red, "intact": flat.intact()},
+               os.path.join(out_dir, f"flat{rank}.pt"))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -58,3 +71,18 @@ def test_flat_allreduce_world2(tmp_path):
         want = sum(r["sent"][i] for r in res)
         for r in res:
             assert torch.allclose(r["got"][i], want, rtol=1e-6, atol=1e-6)
+    # flat path: every rank ends with the single-process gradient of the global-mean loss, and the summed partials
+    from scade_b200.optim import flatten_parameters
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.Linear(5, 2))
+    scale = torch.ones(1, requires_grad=True)
+    flat = flatten_parameters(net, [scale])
+    xs = torch.from_numpy(np.random.default_rng(9).random((8, 6)).astype(np.float32))
+    loss = (net(xs) * scale).pow(2).sum() / 8
+    loss.backward()
+    for r in range(world):
+        got = torch.load(os.path.join(tmp_path, f"flat{r}.pt"))
+        assert got["intact"]
+        for a, b in zip(got["grads"], [p.grad for p in flat.params]):
+            assert torch.allclose(a, b, rtol=1e-5, atol=1e-6)
+        assert torch.allclose(got["red"], torch.stack([loss.detach(), torch.tensor(float(world))]), rtol=1e-5)
