@@ -201,6 +201,23 @@ int scade_img2mse(const float* x, const float* y, int64_t n, int64_t denominator
                   float* loss_out, float* d_x, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Training ray-batch construction: get_ray_batch_from_one_image_hypothesis_idx (RS:772-827)
+ * --------------------------------------------------------------------------------------------- */
+/* For the N selected pixels (select_inds: DEVICE int64 flat indices row*W+col, the np.random.choice of H:281) of ONE
+ * training image: get_rays (H:285-305) at those pixels, the [N,11] ray batch of render() (RS:123-141), and the gathers of
+ * RS:788-821.  image [H,W,3]; depth [H,W,depth_channels] or NULL; valid_depth [H,W] (bool bytes) or NULL; hypotheses
+ * [K,H,W] or NULL (all_hypothesis[img_i] with its trailing singleton axis dropped); cached_u [H,W,n_u] or NULL.
+ * Outputs (NULL = skip, except target_s): ray_batch [N,11]; rays_o_d [2,N,3] (= batch_rays, RS:824); target_s [N,3];
+ * target_d [N,depth_channels]; target_vd [N]; target_h [K,N]; mask [N] (1, or 0 inside the four 20x20 corners when
+ * mask_corners, RS:810-821); u_out [N,n_u].  intrinsic_host: HOST (fx,fy,cx,cy); c2w_host: HOST 3x4 row-major. */
+int scade_gather_train_batch(int H, int W, const float* intrinsic_host, const float* c2w_host,
+                             const int64_t* select_inds, int64_t N, float near, float far, const float* image,
+                             const float* depth, int depth_channels, const uint8_t* valid_depth,
+                             const float* hypotheses, int K, const float* cached_u, int n_u, int mask_corners,
+                             float* ray_batch, float* rays_o_d, float* target_s, float* target_d,
+                             uint8_t* target_vd, float* target_h, float* mask, float* u_out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Optimizer: torch.optim.Adam(grad_vars, lr, betas=(0.9, 0.999)).step()  (RS:469, RS:993)
  * --------------------------------------------------------------------------------------------- */
 /* One Adam step (no amsgrad / weight decay) over a flat fp32 range of n parameters, in place: param, exp_avg, exp_avg_sq
@@ -210,6 +227,19 @@ int scade_img2mse(const float* x, const float* y, int64_t n, int64_t denominator
  * formed in double and rounded to fp32 once, like torch does. */
 int scade_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, double lr,
                     double beta1, double beta2, double eps, int64_t step, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Video / eval post-processing: render_video (RS:236-262), write_images_with_metrics (RS:395-405)
+ * --------------------------------------------------------------------------------------------- */
+/* One frame: rgb [H,W,3], depth_map [H,W], z_vals / weights [H,W,S] (render() outputs) ->
+ *   frame_out [H, 3W, 3] uint8 BGR (nullable) = [ to8b(rgb) | LUT_depth[to8b(depth / depth_scale)] | LUT_std[to8b(std)] ]
+ *   depth_std_out [H,W] (nullable) = sqrt(clamp(sum_s (z - depth)^2 w, 0, 1))                      (RS:257-258)
+ *   depth16_out [H,W] uint16 (nullable) = to16b(depth)                                             (H:14, RS:403)
+ * to8b / to16b truncate like numpy's astype (H:13-14).  lut_depth / lut_std: DEVICE [256,3] BGR tables (cv2.applyColorMap's
+ * COLORMAP_TURBO / COLORMAP_VIRIDIS, RS:255,259) or NULL for grey. */
+int scade_video_frame(const float* rgb, const float* depth_map, const float* z_vals, const float* weights, int H,
+                      int W, int S, float depth_scale, const uint8_t* lut_depth, const uint8_t* lut_std,
+                      uint8_t* frame_out, float* depth_std_out, uint16_t* depth16_out, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * render_rays (RS:581-751), N_importance > 0 branch, forward only, one call, one stream

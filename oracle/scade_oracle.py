@@ -598,3 +598,52 @@ def nerf_backward_teacher_forced(params, emb, h, feature, hv, alpha_pre, inactiv
             if (i - 1) in skips:
                 d_h = d_h[:, input_ch:]
     return g, dz
+
+
+# --------------------------------------------------------------------------------------
+# §8(f) rows: training sampler and video post-processing (restated for the next-row kernels)
+# --------------------------------------------------------------------------------------
+def train_batch(H, W, img_i, images, depths, valid_depths, poses, intrinsics, all_hypothesis, select_inds, cached_u=None,
+                mask_corners=False, near=0.0, far=1.0, dtype=F32):
+    """get_ray_batch_from_one_image_hypothesis_idx (RS:772-827) for GIVEN flat pixel indices (the reference draws them with
+    np.random.choice, H:281) + the [N,11] ray batch render() assembles from batch_rays (RS:123-141)."""
+    rays_o, rays_d = get_rays(H, W, intrinsics[img_i], poses[img_i][:3, :4], dtype)          # RS:784
+    rr, cc = np.asarray(select_inds) // W, np.asarray(select_inds) % W                        # coords[select_inds], H:282
+    o, d = rays_o[rr, cc], rays_d[rr, cc]
+    out = {"batch_rays": np.stack([o, d], 0), "target_s": images[img_i][rr, cc], "target_d": depths[img_i][rr, cc],
+           "target_vd": valid_depths[img_i][rr, cc], "target_h": all_hypothesis[img_i][:, rr, cc],       # RS:786-791
+           "ray_batch": make_ray_batch(o, d, near, far, dtype)}
+    if cached_u is not None:
+        out["cached_u"] = cached_u[img_i][rr, cc]                                             # RS:805-806
+    if mask_corners:                                                                           # RS:810-821
+        m = np.ones((H, W), dtype)
+        m[:20, :20] = 0; m[:20, -20:] = 0; m[-20:, :20] = 0; m[-20:, -20:] = 0
+        out["mask"] = m[rr, cc]
+    return out
+
+
+def to8b(x):
+    """H:13"""
+    return (255 * np.clip(x, 0, 1)).astype(np.uint8)
+
+
+def to16b(x):
+    """H:14"""
+    return ((2 ** 16 - 1) * np.clip(x, 0, 1)).astype(np.uint16)
+
+
+def depth_std(z_vals, weights, depth_map, dtype=F32):
+    """RS:257-258"""
+    z_vals, weights, depth_map = (np.asarray(a, dtype) for a in (z_vals, weights, depth_map))
+    var = (((z_vals - depth_map[..., None]) ** 2) * weights).sum(-1)
+    return np.sqrt(np.clip(var, 0.0, 1.0)).astype(dtype)
+
+
+def video_frame(rgb, depth_map, z_vals, weights, depth_scale, lut_depth=None, lut_std=None):
+    """The frame render_video writes (RS:252-259): [to8b(rgb) in BGR | colour-mapped to8b(depth / far) | colour-mapped
+    to8b(depth_std)], side by side.  lut_*: [256,3] uint8 BGR tables (cv2.applyColorMap's) or None for grey."""
+    rgb8 = to8b(np.asarray(rgb, F32))[..., ::-1]                                              # cv2.COLOR_RGB2BGR
+    d8 = to8b((np.asarray(depth_map, F32) / F32(depth_scale)))
+    s8 = to8b(depth_std(z_vals, weights, depth_map))
+    pan = lambda q, lut: (lut[q] if lut is not None else np.repeat(q[..., None], 3, -1))
+    return np.concatenate([rgb8, pan(d8, lut_depth), pan(s8, lut_std)], 1)

@@ -74,6 +74,9 @@ _SIGNATURES = {
     "scade_space_carving_loss": (c_int, [_P, _P, c_int, _P, c_int, c_int64, c_int, c_int, c_float, c_float, _P, _P, _P,
                                          _P, c_size_t, _P]),
     "scade_img2mse": (c_int, [_P, _P, c_int64, c_int64, c_float, _P, _P, _P]),
+    "scade_gather_train_batch": (c_int, [c_int, c_int, POINTER(c_float), POINTER(c_float), _P, c_int64, c_float, c_float, _P, _P,
+                                         c_int, _P, _P, c_int, _P, c_int, c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "scade_video_frame": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_float, _P, _P, _P, _P, _P, _P]),
     "scade_adam_step": (c_int, [_P, _P, _P, _P, c_int64, c_double, c_double, c_double, c_double, c_int64, _P]),
     "scade_render_rays_workspace_bytes": (c_size_t, [POINTER(RenderCfg), POINTER(NetDesc), POINTER(NetDesc), c_int64]),
     "scade_render_rays_forward": (c_int, [POINTER(RenderCfg), _P, c_int64, POINTER(Net), POINTER(Net), _P, _P, _P,
@@ -113,7 +116,7 @@ def check(status: int, what: str = ""):
 
 
 def ptr(t):
-    """Device pointer of a tensor (None -> NULL).  The tensor must be CUDA, fp32 (or raw bytes), contiguous."""
+    """Device pointer of a tensor (None -> NULL).  The tensor must be CUDA and contiguous (dtype is the caller's business)."""
     if t is None:
         return None
     if not t.is_cuda:

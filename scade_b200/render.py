@@ -222,7 +222,11 @@ def render(H, W, intrinsic, chunk=1024 * 32, rays=None, c2w=None, ndc=True, near
             viewdirs = rays_d / torch.norm(rays_d, dim=-1, keepdim=True)
             ray_batch = torch.cat([rays_o, rays_d, near * ones, far * ones, viewdirs], -1)
         else:
-            ray_batch = F_.make_ray_batch(rays_o, rays_d, near, far)                # RS:123-141
+            pre = getattr(rays, "scade_ray_batch", None)         # scade_b200.sampler already assembled the [N,11] batch
+            if pre is not None and pre[1] == float(near) and pre[2] == float(far) and pre[0].shape[0] == rays_d.reshape(-1, 3).shape[0]:
+                ray_batch = pre[0]
+            else:
+                ray_batch = F_.make_ray_batch(rays_o, rays_d, near, far)            # RS:123-141
     all_ret = batchify_rays(ray_batch, chunk, use_viewdirs, **kwargs)               # RS:147
     for k in all_ret:
         all_ret[k] = torch.reshape(all_ret[k], list(sh[:-1]) + list(all_ret[k].shape[1:]))   # RS:148-150

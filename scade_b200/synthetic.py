@@ -145,3 +145,22 @@ def spiral_poses(n_frames=120, radius=0.3, turns=2.0):
         c2w[2, 3] = 0.1 * radius * math.sin(0.5 * a)
         poses.append(c2w[:3])
     return np.stack(poses, 0)
+
+
+def make_train_scene(n_img=2, H=48, W=64, K=3, n_u=0, seed=40, near=NEAR, far=FAR, depth_channels=1):
+    """A tiny synthetic training scene in the reference's array layouts (data/load_scene.py:243-360): images [n,H,W,3],
+    depths [n,H,W,C], valid_depths [n,H,W] bool, poses [n,4,4], intrinsics [n,4], all_hypothesis [n,K,H,W,1] clipped to
+    [near, far], optional cached_u [n,H,W,n_u]."""
+    rng = np.random.default_rng(seed)
+    images = rng.random((n_img, H, W, 3)).astype(np.float32)
+    depths = rng.uniform(near, far, (n_img, H, W, depth_channels)).astype(np.float32)
+    valid = rng.random((n_img, H, W)) < 0.7
+    poses = np.tile(np.eye(4, dtype=np.float32), (n_img, 1, 1))
+    for i in range(n_img):
+        a = 0.3 * (i + 1)
+        poses[i, :3, :3] = np.array([[np.cos(a), 0, np.sin(a)], [0, 1, 0], [-np.sin(a), 0, np.cos(a)]], np.float32)
+        poses[i, :3, 3] = rng.uniform(-0.5, 0.5, 3).astype(np.float32)
+    intr = np.tile(np.array([W * 0.9, W * 0.91, W / 2 - 0.5, H / 2 + 0.25], np.float32), (n_img, 1))
+    hyp = np.clip(rng.uniform(near - 0.5, far + 0.5, (n_img, K, H, W, 1)), near, far).astype(np.float32)
+    cu = rng.random((n_img, H, W, n_u)).astype(np.float32) if n_u else None
+    return dict(images=images, depths=depths, valid_depths=valid, poses=poses, intrinsics=intr, all_hypothesis=hyp, cached_u=cu)
