@@ -16,9 +16,15 @@ CSRC = os.path.join(PKG, "csrc")
 LIBDIR = os.path.join(PKG, "_lib")
 LIB = os.path.join(LIBDIR, "libscade_b200.so")
 STAMP = os.path.join(LIBDIR, "build.stamp")
+TRACE = os.environ.get("SCADE_TC_TRACE", "0") == "1"      # timeline-tracing variant of the library (tools/tc_trace.py)
+if TRACE:
+    LIB = os.path.join(LIBDIR, "libscade_b200_trace.so")
+    STAMP = os.path.join(LIBDIR, "build_trace.stamp")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-Xcompiler", "-fPIC",
          "--expt-relaxed-constexpr"]
+if TRACE:
+    FLAGS.append("-DSCADE_TC_TRACE=1")
 
 
 def _sources():
@@ -49,7 +55,7 @@ def build(force=False, verbose=False):
     objs = []
     procs = []
     for src in _sources():
-        obj = os.path.join(LIBDIR, os.path.basename(src)[:-3] + ".o")
+        obj = os.path.join(LIBDIR, os.path.basename(src)[:-3] + ("_trace.o" if TRACE else ".o"))
         cmd = [NVCC, *FLAGS, "-c", src, "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")

@@ -102,6 +102,30 @@ struct PackPlan {
 };
 constexpr int ONES_COL = 60;      // encoding-chunk columns 60 and 61 hold 1.0 (bias hi / lo ride on them)
 
+// ---- timeline tracing (tools/tc_trace.py; compiled in only with -DSCADE_TC_TRACE=1, a separate library) ----------------
+// Lane 0 of every warp of CTA 0 appends (tag << 48 | clock) words to its own 8192-entry region of a global buffer.
+#ifndef SCADE_TC_TRACE
+#define SCADE_TC_TRACE 0
+#endif
+#if SCADE_TC_TRACE
+constexpr int TRACE_CAP = 8192;
+__device__ unsigned long long* g_trace_buf = nullptr;
+struct Tracer {
+  unsigned long long* buf; int n;
+  __device__ __forceinline__ Tracer() : buf(nullptr), n(1) {
+    if (g_trace_buf != nullptr && blockIdx.x == 0 && (threadIdx.x & 31) == 0) buf = g_trace_buf + (threadIdx.x >> 5) * TRACE_CAP;
+  }
+  __device__ __forceinline__ void operator()(int tag) {
+    if (buf != nullptr && n < TRACE_CAP) { buf[n++] = ((unsigned long long)tag << 48) | ((unsigned long long)clock64() & 0xFFFFFFFFFFFFull); }
+  }
+  __device__ __forceinline__ ~Tracer() { if (buf != nullptr) buf[0] = (unsigned long long)n; }
+};
+#define TRACE(tr, tag) (tr)(tag)
+#else
+struct Tracer { };
+#define TRACE(tr, tag) do { } while (0)
+#endif
+
 // sin/cos of arguments up to ~pi*2^8 for fp16 consumers: two-term Cody-Waite reduction by 2*pi, then the
 // MUFU approximations on [-pi, pi] (abs error ~5e-7, three orders below the fp16 rounding that follows).
 __device__ __forceinline__ void sincos_reduced(float arg, float* s, float* c) {
@@ -534,10 +558,11 @@ __device__ __forceinline__ void pp_weight_producer(const NetPlan& plan, const CU
 // NUM_STAGES ring slots ahead of super-tile 1, whose MMAs release the slots.
 __device__ __forceinline__ void pp_mma_issuer(const NetPlan& plan, uint32_t sbase, uint32_t tmem_base, uint32_t bar_full,
                                               uint32_t bar_empty, uint32_t bar_acc, uint32_t bar_aready, int64_t unit0,
-                                              int64_t n_steps, int64_t n_units) {
+                                              int64_t n_steps, int64_t n_units, int dbg = 0) {
   constexpr uint64_t desc_hi = ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61) | ((uint64_t)1 << 16);
   // ring position of each super-tile (tile 1 trails tile 0)
   uint32_t slot0 = 0, slot1 = 0, ph0 = 0, ph1 = 0, a_ph0 = 0, a_ph1 = 0;
+  [[maybe_unused]] Tracer tr;
   for (int64_t step = unit0; step < n_steps; step += n_units) {
     for (int l = 0; l < plan.n_layers; ++l) {
       const int n_k = plan.layers[l].n_k, bias_stage = plan.layers[l].bias_stage;
@@ -548,6 +573,9 @@ __device__ __forceinline__ void pp_mma_issuer(const NetPlan& plan, uint32_t sbas
       // one (stage, tile): wait for the slot in both CTAs, issue its MMAs for super-tile t, optionally release it
       auto consume_at = [&](int t, uint32_t& slot_ref, uint32_t& ph_ref, int i, bool release) {
         const uint32_t sl = slot_ref, p = ph_ref;
+#if SCADE_TC_TRACE
+        if (!(dbg & 1))                                  // timing ablation: ignore weight arrival (results are wrong)
+#endif
         mbar_wait(bar_full + 8 * sl, p);                 // both CTAs' halves of the stage have landed
         tc_fence_after();
         if (elect_one()) {
@@ -576,13 +604,19 @@ __device__ __forceinline__ void pp_mma_issuer(const NetPlan& plan, uint32_t sbas
         else consume_at(1, slot1, ph1, i, release);
       };
       auto wait_a = [&](int t) {
+        TRACE(tr, 0x100 + 2 * l + t);                    // issuer: begins waiting for tile t's operand of layer l
+#if SCADE_TC_TRACE
+        if (dbg & 2) { TRACE(tr, 0x200 + 2 * l + t); return; }     // timing ablation: ignore operand readiness
+#endif
         if (t == 0) { mbar_wait(bar_aready, a_ph0); a_ph0 ^= 1; }
         else { mbar_wait(bar_aready + 8, a_ph1); a_ph1 ^= 1; }
         tc_fence_after();
+        TRACE(tr, 0x200 + 2 * l + t);                    // issuer: operand ready
       };
       auto publish = [&](int t) {
         if (elect_one()) mma_commit_pair(bar_acc + 8 * t, (uint16_t)3);
         __syncwarp();
+        TRACE(tr, 0x300 + 2 * l + t);                    // issuer: all MMAs of (layer l, tile t) issued + commit
       };
       // tile 0 first (at most NUM_STAGES ahead of tile 1), then tile 1, which releases the slots
       wait_a(0);
@@ -645,7 +679,7 @@ __global__ void __launch_bounds__(PP_THREADS, 1) nerf_mlp_tc_pp_kernel(const __g
   if (warp == 0) {
     if (lane == 0) pp_weight_producer(plan, &tmap, sbase, bar_full, bar_empty, cta_rank, unit0, n_steps, n_units);
   } else if (warp == 1) {
-    if (cta_rank == 0) pp_mma_issuer(plan, sbase, tmem_base, bar_full, bar_empty, bar_acc, bar_aready, unit0, n_steps, n_units);
+    if (cta_rank == 0) pp_mma_issuer(plan, sbase, tmem_base, bar_full, bar_empty, bar_acc, bar_aready, unit0, n_steps, n_units, a.dbg);
   } else if (warp >= 4) {
     // ================= prologue / epilogue warps: thread == one row x 128 columns =================
     const int ew = warp - 4;
@@ -660,6 +694,7 @@ __global__ void __launch_bounds__(PP_THREADS, 1) nerf_mlp_tc_pp_kernel(const __g
     const uint32_t my_acc = bar_acc + 8 * tile, my_aready = bar_aready + 8 * tile;
     const uint32_t aready_target = cta_rank != 0 ? map_to_cta(my_aready, 0) : my_aready;
     uint32_t acc_phase = 0;
+    [[maybe_unused]] Tracer tr;
     auto signal_a_ready = [&]() {
       fence_proxy_async();
       tc_fence_before();
@@ -678,6 +713,7 @@ __global__ void __launch_bounds__(PP_THREADS, 1) nerf_mlp_tc_pp_kernel(const __g
       const int64_t tile_g = 2 * pair + tile;            // 128-point tile index in the stash
 
       // ---- positional encoding: this thread writes encoding-chunk columns [32*half, 32*half + 32) of its row ----
+      TRACE(tr, 0x400);                                  // epilogue warp: prologue begins
       {
         float v[32];
 #pragma unroll
@@ -756,6 +792,7 @@ __global__ void __launch_bounds__(PP_THREADS, 1) nerf_mlp_tc_pp_kernel(const __g
         }
       }
       signal_a_ready();
+      TRACE(tr, 0x401);                                  // prologue done, operand signalled
 
       float alpha = 0.f;
       for (int l = 0; l < plan.n_layers; ++l) {
@@ -763,6 +800,14 @@ __global__ void __launch_bounds__(PP_THREADS, 1) nerf_mlp_tc_pp_kernel(const __g
         mbar_wait(my_acc, acc_phase);
         acc_phase ^= 1;
         tc_fence_after();
+        TRACE(tr, 0x500 + l);                            // accumulators of layer l visible
+#if SCADE_TC_TRACE
+        if (a.dbg & 32) {                                // timing ablation: no epilogue work at all
+          if (kind != 3) signal_a_ready();
+          TRACE(tr, 0x700 + l);
+          continue;
+        }
+#endif
         if (kind != 3) {
           // hidden / feature layer: this thread's 128 accumulator columns -> A chunks 2*half, 2*half+1
           uint32_t rbuf[2][32];
@@ -801,6 +846,7 @@ __global__ void __launch_bounds__(PP_THREADS, 1) nerf_mlp_tc_pp_kernel(const __g
               *reinterpret_cast<uint4*>(chunk + sw128_offset(row, (c4 & 1) * 4 + pc)) = q;
             }
           }
+          TRACE(tr, 0x600 + l);                          // operand chunks written
           if (kind == 1 && half == 0) {
             // alpha_linear on the un-rounded fp32 activations of the last hidden layer (H:233): the half-0 thread of
             // each row walks all 256 columns once more
@@ -815,6 +861,7 @@ __global__ void __launch_bounds__(PP_THREADS, 1) nerf_mlp_tc_pp_kernel(const __g
             }
           }
           signal_a_ready();
+          TRACE(tr, 0x700 + l);                          // signalled
           if (kStash) {
             if (relu && !(a.dbg & 8))
               *reinterpret_cast<uint4*>(sa.ws + sa.L.maskh[l] + ((size_t)(tile_g * 2 + half) * TILE_M + row) * 16) =
@@ -885,6 +932,7 @@ __global__ void __launch_bounds__(PP_THREADS, 1) nerf_mlp_tc_pp_kernel(const __g
             }
           }
           tc_fence_before();
+          TRACE(tr, 0x700 + l);                          // views epilogue done
         }
       }
     }
@@ -1344,3 +1392,10 @@ int mlp_tc_backward(const scade_net& net, const float* d_out, int64_t P, float* 
 }
 
 }  // namespace scade
+
+#if SCADE_TC_TRACE
+// trace library only (python -m scade_b200.build --trace): register the device buffer the traced warps append to
+extern "C" int scade_debug_tc_trace(void* device_buf) {
+  return (int)cudaMemcpyToSymbol(scade::tc::g_trace_buf, &device_buf, sizeof(device_buf));
+}
+#endif
