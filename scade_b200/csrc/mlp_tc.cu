@@ -52,27 +52,32 @@ constexpr int CHUNK_BYTES = TILE_M * KCHUNK * 2;    // 16 KB
 constexpr int NUM_STAGES = 4;
 constexpr int MAX_LAYERS = 12;           // D (<= 8) + feature + views
 constexpr int MAX_STAGE_DESCS = 96;
-constexpr int EPI_WARPS = 8;
-constexpr int THREADS = 128 + EPI_WARPS * 32;   // warpgroup 0: producer, MMA issuer, 2 idle warps; warpgroups 1-2: epilogue
 
 // shared-memory map (relative to a 1024-byte aligned base)
 constexpr int OFF_A = 0;                                 // [TILES][4 chunks]
 constexpr int OFF_EMB = OFF_A + TILES * 4 * CHUNK_BYTES;  // [TILES]
 constexpr int OFF_STAGE = OFF_EMB + TILES * CHUNK_BYTES;  // [NUM_STAGES]
 constexpr int OFF_BAR = OFF_STAGE + NUM_STAGES * STAGE_BYTES;
-constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;         // barriers + alignment slack
+constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;         // barriers + alignment slack (dgrad kernel)
+// forward kernel: + one 256-float staging row per tile for the current layer's fp32 bias; no slack -- the dynamic shared
+// memory base is 1024-byte aligned when the kernel has no static shared memory (checked at kernel start)
+constexpr int OFF_BIAS = OFF_BAR + 256;
+constexpr int FWD_SMEM_BYTES = OFF_BIAS + TILES * W * 4;
+static_assert(FWD_SMEM_BYTES <= 227 * 1024, "forward kernel shared memory exceeds the 227 KB per-CTA limit");
 
 enum ASrc : int { SRC_EMB = 4 };         // 0..3 = activation chunk c
 
 struct LayerDesc {
   int n_k;                // K chunks
   int a_src[5];           // source chunk of each K chunk
-  int n_halves;           // N / 128
   int relu;
   int kind;               // 0 = hidden, 1 = last hidden (also computes alpha), 2 = feature, 3 = views (final)
-  int bias_stage;         // 1: extra stages carry the bias (layer has no encoding K chunk)
+  int bias_epi;           // 1: the epilogue adds the fp32 bias (layer has no encoding K chunk whose 1.0 columns carry it)
   int n_out;              // output width (256, or 128 for the views layer)
-  int a_step;             // ping-pong issuer: K chunk i (after the encoding chunk) reads activation chunk a_step * i
+  int a_step;             // issuer: K chunk i (after the encoding chunk) reads activation chunk a_step * i
+  int kpack;              // K chunks per ring stage (2 when a CTA's N half is only 64 rows: views layer)
+  int bias_stage;         // 1: one extra ring stage carries the bias as a K=16 MMA step against the encoding chunk's 1.0 columns
+                          //    (last hidden layer: its shared-memory row is taken by the alpha_linear weights)
 };
 
 struct NetPlan {
@@ -85,20 +90,30 @@ struct NetPlan {
 
 // small fp32 table behind the stage images in the packed buffer
 struct PackedTail {
-  float4 w_rgb[W / 2];     // (r, g, b, 0) weights of rgb_linear per hidden column
+  float4 w_rgb[W / 2];     // (r, g, b, 0) weights of rgb_linear per hidden column (dgrad prologue)
   float w_alpha[W];
   float b_alpha, b_rgb[3];
+  float w_rgb_p[3][W / 2]; // the same weights, one row per colour channel (forward epilogue: 4 columns per 16-byte load)
+  float bias[MAX_LAYERS][W];   // fp32 biases of the layers whose epilogue adds them (bias_epi)
 };
 
+// One ring stage = up to two row blocks: block j fills stage rows [dst_row0, dst_row0 + nrows) with K chunk columns.
+struct StageBlock {
+  int col0; int ncols; int dst_col0; int dst_row0; int nrows;
+  int bias_mode;                      // 0 none; 1: cols 60/61 <- hi/lo fp16 halves of bias[row0 + n]; 2: bias stage (cols 12/13)
+};
 struct StageDesc {
-  const float* W; int ld; int col0; int ncols; int dst_col0; int row0; int nrows;
-  const float* bias; int bias_mode;   // 0 none; 1: cols 60/61 <- hi/lo of bias[row0+n]; 2: bias stage (both N halves)
-  int trans;                          // 1: stage element (n, k) = W[(col0 + k) * ld + row0 + n]  (dgrad: B = W^T)
+  const float* W; int ld; int row0;   // stage row (dst_row0 + n) of a block <- weight row row0 + n
+  const float* bias;
+  int trans;                          // 1: element (n, k) = W[(col0 + k) * ld + row0 + n]  (dgrad: B = W^T)
+  int n_blocks;
+  StageBlock blk[2];
 };
 struct PackPlan {
   int n_stages;
   StageDesc st[MAX_STAGE_DESCS];
   const float* w_alpha; const float* b_alpha; const float* w_rgb; const float* b_rgb;
+  const float* epi_bias[MAX_LAYERS];  // bias vector of layer l if its epilogue adds it, else nullptr
 };
 constexpr int ONES_COL = 60;      // encoding-chunk columns 60 and 61 hold 1.0 (bias hi / lo ride on them)
 
@@ -174,353 +189,6 @@ struct StashArgs {
   TrainLayout L;
 };
 
-// kPair == false: every CTA is independent (cta_group::1, M=128 MMAs, both N halves of every weight block).
-// kPair == true : clusters of 2 CTAs on an SM pair; the leader issues tcgen05.mma.cta_group::2 (M=256 = 128 rows of each
-//                 CTA, N=256); each CTA streams only ITS half (128 N rows) of every weight block, so the B operand read
-//                 per SM and the weight bytes per SM are halved (the single-CTA form is shared-memory-bandwidth bound:
-//                 4 KB of A + 4 KB of B per 64-cycle instruction = 128 B/cycle).
-// kPing == false: the two row tiles of a CTA run in lock-step and share every weight stage.
-// kPing == true : the two row tiles are independent pipelines that alternate on the tensor pipe: while tile 0's
-//                 accumulators are drained by its epilogue warps, tile 1's MMAs run (and vice versa), which hides the
-//                 epilogue and the per-layer barrier/pipeline latencies.  Each layer's weight stages are streamed twice
-//                 (once per tile); the pair form keeps that at 16 KB per 512 MMA cycles per SM.
-template <bool kPair, bool kPing>
-__global__ void __launch_bounds__(THREADS, 1) nerf_mlp_tc_kernel(const __grid_constant__ FwdArgs a,
-                                                                 const __grid_constant__ NetPlan plan) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  const uint32_t sbase = smem_u32(smem);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t cta_rank = kPair ? cluster_ctarank() : 0;
-  // work units: a cluster (or a lone CTA) walks `n_steps`; CTA `cta_rank` of the cluster takes pair 2*step + rank
-  const int64_t unit0 = kPair ? cluster_id_x() : blockIdx.x;
-  const int64_t n_units = kPair ? num_clusters_x() : gridDim.x;
-  const int64_t n_steps = kPair ? (a.n_pairs + 1) / 2 : a.n_pairs;
-  constexpr int kStreams = kPing ? 2 : 1;          // independent tile pipelines per CTA
-
-  // barriers: full[4], empty[4], peer_full[4] (leader: the peer's stage has landed), acc_full[2], a_ready[2], TMEM slot
-  const uint32_t bar_full = sbase + OFF_BAR, bar_empty = bar_full + 8 * NUM_STAGES;
-  const uint32_t bar_peer_full = bar_empty + 8 * NUM_STAGES;
-  const uint32_t bar_acc = bar_peer_full + 8 * NUM_STAGES, bar_aready = bar_acc + 16;
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + OFF_BAR + 8 * (3 * NUM_STAGES + 4));
-
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < NUM_STAGES; ++s) {
-      mbar_init(bar_full + 8 * s, 1);
-      mbar_init(bar_empty + 8 * s, 1);
-      mbar_init(bar_peer_full + 8 * s, 1);
-    }
-    for (int t = 0; t < 2; ++t) {
-      mbar_init(bar_acc + 8 * t, 1);
-      // arrivals: one per epilogue warp of the stream (pair form: the peer CTA's warps arrive remotely as well)
-      mbar_init(bar_aready + 8 * t, (kPair ? 2 : 1) * (EPI_WARPS / kStreams));
-    }
-    fence_barrier_init();
-  }
-  if (warp == 1) {
-    if (kPair) tmem_alloc_pair(smem_u32((const void*)tmem_slot), 512);
-    else tmem_alloc(smem_u32((const void*)tmem_slot), 512);
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (kPair) cluster_sync_all();           // peers' barriers are initialised before any remote arrive / multicast commit
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  // register budget: the control warpgroup gives registers to the two epilogue warpgroups.  The pool is what the CTA got
-  // at launch (384 threads x 168 = 64512 registers), so 128*96 + 256*200 = 63488 fits; asking for more blocks forever.
-  if (warp < 4) asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");
-  else asm volatile("setmaxnreg.inc.sync.aligned.u32 200;");
-
-  if (warp == 0 || (warp == 2 && kPair)) {
-    // ================= warp 0: TMA producer -- streams the packed weight stages =================
-    //   pair form: stages alternate (CTA 0's half, CTA 1's half); each CTA fetches only its own;
-    //   ping-pong : every layer's stage list is streamed once per tile stream.
-    // ================= warp 2 (pair form, non-leader CTA): relay -- tells the leader that this CTA's stage landed ====
-    const bool is_relay = warp == 2;
-    if (lane == 0 && (!is_relay || cta_rank != 0)) {
-      uint32_t stage = 0, phase = 0;
-      const int s0 = kPair ? (int)cta_rank : 0, ds = kPair ? 2 : 1;
-      const uint32_t leader_peer_full = kPair ? map_to_cta(bar_peer_full, 0) : 0;
-      for (int64_t step = unit0; step < n_steps; step += n_units) {
-        for (int l = 0; l < plan.n_layers; ++l) {
-          const int first = plan.first_stage[l], last = first + plan.n_stages[l];
-          for (int rep = 0; rep < kStreams; ++rep) {
-            for (int s = first + s0; s < last; s += ds) {
-              if (!is_relay) {
-                mbar_wait(bar_empty + 8 * stage, phase ^ 1);
-                mbar_expect_tx(bar_full + 8 * stage, STAGE_BYTES);
-                bulk_g2s(sbase + OFF_STAGE + stage * STAGE_BYTES, a.packed + (size_t)s * STAGE_BYTES, STAGE_BYTES,
-                         bar_full + 8 * stage);
-              } else {
-                mbar_wait(bar_full + 8 * stage, phase);
-                mbar_arrive_remote(leader_peer_full + 8 * stage);
-              }
-              if (++stage == NUM_STAGES) { stage = 0; phase ^= 1; }
-            }
-          }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    // ================= MMA issuer =================
-    // The whole warp walks the loops (warp-uniform control flow keeps descriptors in uniform registers);
-    // one elected lane issues the tcgen05 instructions.  In pair form only the leader CTA issues.
-    uint32_t stage = 0, phase = 0, a_phase0 = 0, a_phase1 = 0;
-    constexpr uint64_t desc_hi = ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61) | ((uint64_t)1 << 16);
-    auto wait_stage = [&]() {
-      mbar_wait(bar_full + 8 * stage, phase);
-      if (kPair) mbar_wait_cluster(bar_peer_full + 8 * stage, phase);
-      tc_fence_after();
-    };
-    auto release_stage = [&]() {                        // (elected lane) frees the slot once the MMAs issued so far retire
-      if (kPair) mma_commit_pair(bar_empty + 8 * stage, (uint16_t)3);
-      else mma_commit(bar_empty + 8 * stage);
-    };
-    auto next_stage = [&]() {
-      __syncwarp();
-      if (++stage == NUM_STAGES) { stage = 0; phase ^= 1; }
-    };
-    if (!kPair || cta_rank == 0) {
-      for (int64_t step = unit0; step < n_steps; step += n_units) {
-        for (int l = 0; l < plan.n_layers; ++l) {
-          const int n_k = plan.layers[l].n_k, n_halves = plan.layers[l].n_halves, bias_stage = plan.layers[l].bias_stage;
-          const uint32_t idesc = kPair ? make_idesc(2 * TILE_M, plan.layers[l].n_out) : make_idesc(TILE_M, STAGE_N);
-          int a_src[5];
-#pragma unroll
-          for (int i = 0; i < 5; ++i) a_src[i] = plan.layers[l].a_src[i];
-#pragma unroll 1
-          for (int sidx = 0; sidx < kStreams; ++sidx) {
-            const int t_lo = kPing ? sidx : 0, t_hi = kPing ? sidx + 1 : TILES;
-            {
-              const uint32_t ph = sidx == 0 ? a_phase0 : a_phase1;
-              if (kPair) mbar_wait_cluster(bar_aready + 8 * sidx, ph); else mbar_wait(bar_aready + 8 * sidx, ph);
-              if (sidx == 0) a_phase0 ^= 1; else a_phase1 ^= 1;
-              tc_fence_after();
-            }
-#pragma unroll 1
-            for (int kc = 0; kc < n_k; ++kc) {
-              int src = a_src[0];
-#pragma unroll
-              for (int i = 1; i < 5; ++i) src = (kc == i) ? a_src[i] : src;
-              const uint32_t a_off = (src == SRC_EMB) ? OFF_EMB : OFF_A + src * CHUNK_BYTES;
-              const uint32_t a_stride = (src == SRC_EMB) ? CHUNK_BYTES : 4 * CHUNK_BYTES;
-              const int n_parts = kPair ? 1 : n_halves;          // pair form: one M=256, N=n_out instruction series per K chunk
-#pragma unroll 1
-              for (int nh = 0; nh < n_parts; ++nh) {
-                wait_stage();
-                if (elect_one()) {
-                  const uint64_t b_desc = desc_hi | (uint64_t)(((sbase + OFF_STAGE + stage * STAGE_BYTES) & 0x3FFFF) >> 4);
-#pragma unroll 1
-                  for (int t = t_lo; t < t_hi; ++t) {
-                    const uint64_t a_desc = desc_hi | (uint64_t)(((sbase + a_off + t * a_stride) & 0x3FFFF) >> 4);
-                    const uint32_t d_addr = tmem_base + t * W + nh * STAGE_N;
-#pragma unroll
-                    for (int ks = 0; ks < KCHUNK / 16; ++ks) {
-                      if (kPair) mma_f16_ss_pair(d_addr, a_desc + 2 * ks, b_desc + 2 * ks, idesc, (kc | ks) != 0 ? 1u : 0u);
-                      else mma_f16_ss(d_addr, a_desc + 2 * ks, b_desc + 2 * ks, idesc, (kc | ks) != 0 ? 1u : 0u);
-                    }
-                  }
-                  release_stage();
-                }
-                next_stage();
-              }
-            }
-            if (bias_stage) {
-              // bias: A = K-step 3 of the encoding chunk (columns 48..63: zero-weighted encoding + the two 1.0 columns),
-              // B = K-step 0 of a bias stage (hi/lo fp16 halves of the bias at K positions 12/13); one stage per N half
-              const int n_b = kPair ? 1 : 2;
-#pragma unroll 1
-              for (int nh = 0; nh < n_b; ++nh) {
-                wait_stage();
-                if (elect_one()) {
-                  const uint64_t b_desc = desc_hi | (uint64_t)(((sbase + OFF_STAGE + stage * STAGE_BYTES) & 0x3FFFF) >> 4);
-#pragma unroll 1
-                  for (int t = t_lo; t < t_hi; ++t) {
-                    const uint64_t a_desc = desc_hi | (uint64_t)(((sbase + OFF_EMB + t * CHUNK_BYTES + 3 * 32) & 0x3FFFF) >> 4);
-                    if (kPair) mma_f16_ss_pair(tmem_base + t * W, a_desc, b_desc, idesc, 1u);
-                    else mma_f16_ss(tmem_base + t * W + nh * STAGE_N, a_desc, b_desc, idesc, 1u);
-                  }
-                  release_stage();
-                }
-                next_stage();
-              }
-            }
-            if (elect_one()) {                                           // accumulators of this stream's layer complete
-              if (kPair) mma_commit_pair(bar_acc + 8 * sidx, (uint16_t)3);
-              else mma_commit(bar_acc + 8 * sidx);
-            }
-            __syncwarp();
-          }
-        }
-      }
-    }
-  } else if (warp >= 4) {
-    // ================= prologue / epilogue warps: thread == point row =================
-    const int ew = warp - 4;
-    const int tile = ew >> 2;
-    const int quarter = warp & 3;                       // TMEM lane quarter this warp may access
-    const int row = quarter * 32 + lane;
-    uint8_t* a_tile = smem + OFF_A + tile * 4 * CHUNK_BYTES;
-    uint8_t* emb_tile = smem + OFF_EMB + tile * CHUNK_BYTES;
-    const uint32_t t_lane = tmem_base + ((uint32_t)(quarter * 32) << 16) + tile * W;
-    const PackedTail* tail = reinterpret_cast<const PackedTail*>(a.packed + (size_t)plan.stages_per_pass * STAGE_BYTES);
-    uint32_t acc_phase = 0;
-    const int sidx = kPing ? tile : 0;                  // which stream's barriers this warp uses
-    const uint32_t my_acc = bar_acc + 8 * sidx, my_aready = bar_aready + 8 * sidx;
-    const uint32_t aready_target = (kPair && cta_rank != 0) ? map_to_cta(my_aready, 0) : 0;
-    auto signal_a_ready = [&]() {
-      if (kPair) fence_proxy_async_all(); else fence_proxy_async();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) {
-        if (kPair && cta_rank != 0) mbar_arrive_remote(aready_target);
-        else mbar_arrive(my_aready);
-      }
-    };
-
-    for (int64_t step = unit0; step < n_steps; step += n_units) {
-      const int64_t pair = kPair ? 2 * step + cta_rank : step;
-      const int64_t p_raw = pair * (TILES * TILE_M) + tile * TILE_M + row;
-      const bool live = p_raw < a.P;
-      const int64_t p = live ? p_raw : a.P - 1;
-
-      // ---- positional encoding -> fp16 encoding chunk (columns: gamma(x), view dir, zeros, 1, 1, 0, 0) ----
-      {
-        float v[64];
-#pragma unroll
-        for (int i = 0; i < 64; ++i) v[i] = 0.f;
-        float vd[3] = {0.f, 0.f, 0.f};
-        if (a.rays != nullptr) {
-          const int64_t r = p / a.S;
-          const float* ray = a.rays + r * a.ray_stride;
-          const float zz = a.z[p];
-          const float cen[3] = {a.cx, a.cy, a.cz};
-#pragma unroll
-          for (int d = 0; d < 3; ++d) {
-            float pt = __fadd_rn(ray[d], __fmul_rn(ray[3 + d], zz));            // RS:657
-            float x = __fmul_rn(__fsub_rn(pt, cen[d]), a.bb_scale);             // RS:52
-            v[d] = x;
-            float xp = __fmul_rn(x, 3.14159274101257324f);                      // H:165
-#pragma unroll
-            for (int k = 0; k < 9; ++k) {
-              if (k < a.multires) {
-                float s, c;
-                sincos_reduced(__fmul_rn(xp, (float)(1 << k)), &s, &c);
-                v[3 + 6 * k + d] = s;
-                v[6 + 6 * k + d] = c;
-              }
-            }
-            vd[d] = ray[8 + d];                                                 // RS:632
-          }
-        } else {
-          const float* x = a.x_embedded + p * a.in_all;
-#pragma unroll
-          for (int i = 0; i < ONES_COL; ++i)
-            if (i < a.in_all) v[i] = x[i];
-        }
-        v[ONES_COL] = 1.0f;
-        v[ONES_COL + 1] = 1.0f;
-#pragma unroll
-        for (int piece = 0; piece < 8; ++piece) {
-          uint4 q;
-          q.x = pack_f16x2(v[piece * 8 + 0], v[piece * 8 + 1]);
-          q.y = pack_f16x2(v[piece * 8 + 2], v[piece * 8 + 3]);
-          q.z = pack_f16x2(v[piece * 8 + 4], v[piece * 8 + 5]);
-          q.w = pack_f16x2(v[piece * 8 + 6], v[piece * 8 + 7]);
-          *reinterpret_cast<uint4*>(emb_tile + sw128_offset(row, piece)) = q;
-        }
-        if (a.rays != nullptr) {
-          // the (un-encoded, multires_views == 0) view direction sits right after gamma(x): columns in_ch..in_ch+2
-          const int in_ch = 3 + 6 * a.multires;
-#pragma unroll
-          for (int d = 0; d < 3; ++d) {
-            const int col = in_ch + d;
-            *reinterpret_cast<__half*>(emb_tile + sw128_offset(row, col >> 3) + (col & 7) * 2) = __float2half_rn(vd[d]);
-          }
-        }
-      }
-      signal_a_ready();
-
-      float alpha = 0.f;
-      for (int l = 0; l < plan.n_layers; ++l) {
-        const int kind = plan.layers[l].kind, relu = plan.layers[l].relu;
-        mbar_wait(my_acc, acc_phase);
-        acc_phase ^= 1;
-        tc_fence_after();
-        if (kind != 3) {
-          // hidden / feature layer: 256 accumulator columns (bias already inside) -> next layer's A chunks.
-          // 32-column TMEM loads are double-buffered: the load of chunk c+1 is in flight while chunk c is packed.
-          uint32_t rbuf[2][32];
-          tmem_ld32(t_lane, rbuf[0]);
-#pragma unroll
-          for (int c8 = 0; c8 < W / 32; ++c8) {
-            uint32_t* r = rbuf[c8 & 1];
-            tmem_ld_wait();
-            if (c8 + 1 < W / 32) tmem_ld32(t_lane + (c8 + 1) * 32, rbuf[(c8 + 1) & 1]);
-            if (kind == 1) {
-              const float* wa = tail->w_alpha + c8 * 32;
-#pragma unroll
-              for (int j = 0; j < 32; ++j) alpha = fmaf(fmaxf(__uint_as_float(r[j]), 0.f), __ldg(wa + j), alpha);   // H:233
-            }
-            uint8_t* chunk = a_tile + (c8 >> 1) * CHUNK_BYTES;
-#pragma unroll
-            for (int pc = 0; pc < 4; ++pc) {
-              uint4 q;
-              if (relu) {
-                q.x = pack_relu_f16x2(r[pc * 8 + 0], r[pc * 8 + 1]);
-                q.y = pack_relu_f16x2(r[pc * 8 + 2], r[pc * 8 + 3]);
-                q.z = pack_relu_f16x2(r[pc * 8 + 4], r[pc * 8 + 5]);
-                q.w = pack_relu_f16x2(r[pc * 8 + 6], r[pc * 8 + 7]);
-              } else {
-                q.x = pack_plain_f16x2(r[pc * 8 + 0], r[pc * 8 + 1]);
-                q.y = pack_plain_f16x2(r[pc * 8 + 2], r[pc * 8 + 3]);
-                q.z = pack_plain_f16x2(r[pc * 8 + 4], r[pc * 8 + 5]);
-                q.w = pack_plain_f16x2(r[pc * 8 + 6], r[pc * 8 + 7]);
-              }
-              *reinterpret_cast<uint4*>(chunk + sw128_offset(row, (c8 & 1) * 4 + pc)) = q;
-            }
-          }
-          signal_a_ready();
-        } else {
-          // views layer (N = 128) + rgb_linear + output                          H:238-242
-          float cr = 0.f, cg = 0.f, cb = 0.f;
-#pragma unroll 1
-          for (int c = 0; c < 2; ++c) {
-            uint32_t r[64];
-            tmem_ld32(t_lane + c * 64, r);
-            tmem_ld32(t_lane + c * 64 + 32, r + 32);
-            tmem_ld_wait();
-#pragma unroll
-            for (int j = 0; j < 64; ++j) {
-              float h = fmaxf(__uint_as_float(r[j]), 0.f);
-              float4 w = __ldg(tail->w_rgb + c * 64 + j);
-              cr = fmaf(h, w.x, cr);
-              cg = fmaf(h, w.y, cg);
-              cb = fmaf(h, w.z, cb);
-            }
-          }
-          tc_fence_before();
-          if (live) {
-            float al = alpha + __ldg(&tail->b_alpha);
-            a.out[p_raw] = make_float4(cr + __ldg(&tail->b_rgb[0]), cg + __ldg(&tail->b_rgb[1]),
-                                       cb + __ldg(&tail->b_rgb[2]), softplus_beta10(al));
-          }
-        }
-      }
-    }
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (kPair) cluster_sync_all();           // no CTA leaves (or frees TMEM) while the pair's MMAs / arrivals are in flight
-  if (warp == 1) {
-    tc_fence_after();
-    if (kPair) tmem_dealloc_pair(tmem_base, 512);
-    else tmem_dealloc(tmem_base, 512);
-  }
-}
-
 // =====================================================================================================
 // v6: SM-pair kernel with the two row tiles ping-ponging on ONE shared weight ring
 // =====================================================================================================
@@ -532,7 +200,12 @@ __global__ void __launch_bounds__(THREADS, 1) nerf_mlp_tc_kernel(const __grid_co
 // fill/drain of one tile hide under the other tile's MMAs, with no extra weight traffic and no extra shared memory.
 // 16 epilogue warps (8 per tile: thread = one row x 128 columns) keep a tile's epilogue shorter than a layer of MMAs.
 constexpr int PP_EPI_WARPS = 16;
-constexpr int PP_THREADS = 128 + PP_EPI_WARPS * 32;
+constexpr int PP_EPI_WARP0 = 4;                        // warpgroup 0: TMA producer, MMA issuer, 2 idle warps; warps 4..19: prologue / epilogue
+constexpr int PP_THREADS = (PP_EPI_WARP0 + PP_EPI_WARPS) * 32;
+// register hand-over: the control warpgroup shrinks to 32 registers per thread, the four epilogue warpgroups grow from the
+// launch allocation (96) to 112  (128 x 32 + 512 x 112 = 61,440 = the 640 x 96 the CTA owns; asking for more would block forever)
+__device__ __forceinline__ void regs_control() { asm volatile("setmaxnreg.dec.sync.aligned.u32 32;"); }
+__device__ __forceinline__ void regs_epilogue() { asm volatile("setmaxnreg.inc.sync.aligned.u32 112;"); }
 
 // ---- roles shared by the ping-pong forward kernel and the dgrad kernel ---------------------------------------------
 // TMA producer of this CTA's half stages (every stage once per layer).  The packed stream is addressed through a 2D
@@ -554,8 +227,12 @@ __device__ __forceinline__ void pp_weight_producer(const NetPlan& plan, const CU
   }
 }
 
-// MMA issuer of the leader CTA (whole warp walks the loops, one elected lane issues).  Super-tile 0 runs up to
-// NUM_STAGES ring slots ahead of super-tile 1, whose MMAs release the slots.
+// MMA issuer of the leader CTA (whole warp walks the loops, one elected lane issues).  Ring stage i of a layer holds
+// `kpack` consecutive K chunks of this CTA's N half (kpack = 2 for the views layer, whose half is only 64 rows).
+// Layers of <= NUM_STAGES stages: super-tile 0 consumes the whole layer, then super-tile 1 does, releasing the slots as it
+// goes -- by then the next layer's stages are already in flight, so the ring never blocks.  The one 5-stage layer (skip
+// layer: encoding chunk + 4 activation chunks) interleaves the tiles so that the 5th stage is requested two stages before
+// it is needed (trace-measured commit -> reload -> full latency is ~1600 cycles = 12 MMAs).
 __device__ __forceinline__ void pp_mma_issuer(const NetPlan& plan, uint32_t sbase, uint32_t tmem_base, uint32_t bar_full,
                                               uint32_t bar_empty, uint32_t bar_acc, uint32_t bar_aready, int64_t unit0,
                                               int64_t n_steps, int64_t n_units, int dbg = 0) {
@@ -565,8 +242,9 @@ __device__ __forceinline__ void pp_mma_issuer(const NetPlan& plan, uint32_t sbas
   [[maybe_unused]] Tracer tr;
   for (int64_t step = unit0; step < n_steps; step += n_units) {
     for (int l = 0; l < plan.n_layers; ++l) {
-      const int n_k = plan.layers[l].n_k, bias_stage = plan.layers[l].bias_stage;
-      const int n_own = n_k + bias_stage;                      // this layer's stages per CTA (<= 5)
+      const int n_k = plan.layers[l].n_k, kpack = plan.layers[l].kpack;
+      const int n_kst = (n_k + kpack - 1) / kpack;             // stages holding K chunks
+      const int n_own = n_kst + plan.layers[l].bias_stage;     // this layer's stages per CTA (<= 5)
       const int has_emb = plan.layers[l].a_src[0] == SRC_EMB;
       const int a_step = plan.layers[l].a_step;                // A chunk of K chunk i (after the encoding chunk) = a_step * i
       const uint32_t idesc = make_idesc(2 * TILE_M, plan.layers[l].n_out);
@@ -579,20 +257,24 @@ __device__ __forceinline__ void pp_mma_issuer(const NetPlan& plan, uint32_t sbas
         mbar_wait(bar_full + 8 * sl, p);                 // both CTAs' halves of the stage have landed
         tc_fence_after();
         if (elect_one()) {
-          const uint64_t b_desc = desc_hi | (uint64_t)(((sbase + OFF_STAGE + sl * STAGE_BYTES) & 0x3FFFF) >> 4);
           const uint32_t d_addr = tmem_base + t * W;
-          if (i < n_k) {
-            const bool emb = has_emb && i == 0;
+          if (i == n_kst) {
+            // bias stage: A = K-step 3 of the encoding chunk (the two 1.0 columns), B = K-step 0 (bias hi/lo at k = 12, 13)
+            const uint64_t a_desc = desc_hi | (uint64_t)(((sbase + OFF_EMB + t * CHUNK_BYTES + 3 * 32) & 0x3FFFF) >> 4);
+            const uint64_t b_desc = desc_hi | (uint64_t)(((sbase + OFF_STAGE + sl * STAGE_BYTES) & 0x3FFFF) >> 4);
+            mma_f16_ss_pair(d_addr, a_desc, b_desc, idesc, 1u);
+          }
+          for (int j = 0; j < kpack && i < n_kst; ++j) {
+            const int kc = i * kpack + j;
+            if (kc >= n_k) break;
+            const bool emb = has_emb && kc == 0;
             const uint32_t a_addr = emb ? sbase + OFF_EMB + t * CHUNK_BYTES
-                                        : sbase + OFF_A + (t * 4 + (i - has_emb) * a_step) * CHUNK_BYTES;
+                                        : sbase + OFF_A + (t * 4 + (kc - has_emb) * a_step) * CHUNK_BYTES;
             const uint64_t a_desc = desc_hi | (uint64_t)((a_addr & 0x3FFFF) >> 4);
+            const uint64_t b_desc = desc_hi | (uint64_t)(((sbase + OFF_STAGE + sl * STAGE_BYTES + j * (STAGE_BYTES / 2)) & 0x3FFFF) >> 4);
 #pragma unroll
             for (int ks = 0; ks < KCHUNK / 16; ++ks)
-              mma_f16_ss_pair(d_addr, a_desc + 2 * ks, b_desc + 2 * ks, idesc, (i | ks) != 0 ? 1u : 0u);
-          } else {
-            // bias stage: A = K-step 3 of the encoding chunk (the two 1.0 columns), B = K-step 0 (bias hi/lo)
-            const uint64_t a_desc = desc_hi | (uint64_t)(((sbase + OFF_EMB + t * CHUNK_BYTES + 3 * 32) & 0x3FFFF) >> 4);
-            mma_f16_ss_pair(d_addr, a_desc, b_desc, idesc, 1u);
+              mma_f16_ss_pair(d_addr, a_desc + 2 * ks, b_desc + 2 * ks, idesc, (kc | ks) != 0 ? 1u : 0u);
           }
           if (release) mma_commit_pair(bar_empty + 8 * sl, (uint16_t)3);
         }
@@ -618,24 +300,100 @@ __device__ __forceinline__ void pp_mma_issuer(const NetPlan& plan, uint32_t sbas
         __syncwarp();
         TRACE(tr, 0x300 + 2 * l + t);                    // issuer: all MMAs of (layer l, tile t) issued + commit
       };
-      // tile 0 first (at most NUM_STAGES ahead of tile 1), then tile 1, which releases the slots
       wait_a(0);
-      const int lead = n_own < NUM_STAGES ? n_own : NUM_STAGES;
-      for (int i = 0; i < lead; ++i) consume(0, i, false);
-      int i1 = 0;
-      if (n_own > NUM_STAGES) {                                // 5-stage layer: tile 1 must free a slot first
+      if (n_own <= NUM_STAGES) {
+        for (int i = 0; i < n_own; ++i) consume(0, i, false);
+        publish(0);
+        wait_a(1);
+        for (int i = 0; i < n_own; ++i) consume(1, i, true);
+        publish(1);
+      } else {
+        // 5 stages on a 4-slot ring: a0 a1 a2 | b0 | a3 | b1 | a4 | b2 b3 b4   (a = tile 0, b = tile 1)
+        consume(0, 0, false); consume(0, 1, false); consume(0, 2, false);
         wait_a(1);
         consume(1, 0, true);
-        i1 = 1;
-        consume(0, NUM_STAGES, false);
+        consume(0, 3, false);
+        consume(1, 1, true);
+        consume(0, 4, false);
+        publish(0);
+        consume(1, 2, true); consume(1, 3, true); consume(1, 4, true);
+        publish(1);
       }
-      publish(0);
-      if (i1 == 0) wait_a(1);
-      for (int i = i1; i < n_own; ++i) consume(1, i, true);
-      publish(1);
     }
   }
 }
+
+// One thread's share of a hidden / feature layer epilogue: 128 fp32 accumulator columns (TMEM, 32 at a time, double
+// buffered) -> (+ bias row from shared memory) -> (ReLU) -> fp16 -> the two swizzled A chunks at `dst` (row offset applied;
+// rx4 = (row & 7) << 4 is the row's swizzle term).  kAlpha: also the dot product of the un-rounded ReLU'd activations with
+// the 128 alpha_linear weights at `srow` (H:233).  kMask: sign masks of the pre-activations for the training stash.
+// Branch-free inside; the caller dispatches on the layer's flags.
+template <bool kBias, bool kRelu, bool kAlpha, bool kMask>
+__device__ __forceinline__ float hidden_epilogue(uint32_t t_col, uint8_t* dst, uint32_t rx4, const float* srow, const float* walpha,
+                                                 uint32_t* sgn) {
+  uint32_t rb[2][32];
+  float al0 = 0.f, al1 = 0.f, al2 = 0.f, al3 = 0.f;
+  tmem_ld32(t_col, rb[0]);
+#pragma unroll
+  for (int c4 = 0; c4 < 4; ++c4) {
+    uint32_t* r = rb[c4 & 1];
+    float4 w[4];
+    if (kAlpha) {                                          // global (L1-resident, warp-uniform) loads issued ahead of the TMEM wait
+#pragma unroll
+      for (int i = 0; i < 4; ++i) w[i] = __ldg(reinterpret_cast<const float4*>(walpha + c4 * 32) + i);
+    }
+    tmem_ld_wait();
+    if (c4 + 1 < 4) tmem_ld32(t_col + (c4 + 1) * 32, rb[(c4 + 1) & 1]);
+#pragma unroll
+    for (int g = 0; g < 2; ++g) {
+      if (kBias) {                                         // 4 broadcast LDS.128 in flight, then their 16 columns
+        const float4* p4 = reinterpret_cast<const float4*>(srow + c4 * 32 + g * 16);
+        const float4 v0 = p4[0], v1 = p4[1], v2 = p4[2], v3 = p4[3];
+        const float v[16] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, v2.y, v2.z, v2.w, v3.x, v3.y, v3.z, v3.w};
+#pragma unroll
+        for (int i = 0; i < 16; ++i) r[g * 16 + i] = __float_as_uint(__uint_as_float(r[g * 16 + i]) + v[i]);
+      }
+      if (kAlpha) {
+        const float v[16] = {w[0].x, w[0].y, w[0].z, w[0].w, w[1].x, w[1].y, w[1].z, w[1].w,
+                             w[2].x, w[2].y, w[2].z, w[2].w, w[3].x, w[3].y, w[3].z, w[3].w};
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float hx = fmaxf(__uint_as_float(r[g * 16 + i]), 0.f);
+          if ((i & 3) == 0) al0 = fmaf(hx, v[i], al0);
+          else if ((i & 3) == 1) al1 = fmaf(hx, v[i], al1);
+          else if ((i & 3) == 2) al2 = fmaf(hx, v[i], al2);
+          else al3 = fmaf(hx, v[i], al3);
+        }
+        if (g == 0) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) w[i] = __ldg(reinterpret_cast<const float4*>(walpha + c4 * 32 + 16) + i);
+        }
+      }
+    }
+    if (kMask) sgn[c4] = sign_mask32(r);
+    uint8_t* chunk = dst + (c4 >> 1) * CHUNK_BYTES;
+#pragma unroll
+    for (int pc = 0; pc < 4; ++pc) {
+      uint4 q;
+      if (kRelu) {
+        q.x = pack_relu_f16x2(r[pc * 8 + 0], r[pc * 8 + 1]);
+        q.y = pack_relu_f16x2(r[pc * 8 + 2], r[pc * 8 + 3]);
+        q.z = pack_relu_f16x2(r[pc * 8 + 4], r[pc * 8 + 5]);
+        q.w = pack_relu_f16x2(r[pc * 8 + 6], r[pc * 8 + 7]);
+      } else {
+        q.x = pack_plain_f16x2(r[pc * 8 + 0], r[pc * 8 + 1]);
+        q.y = pack_plain_f16x2(r[pc * 8 + 2], r[pc * 8 + 3]);
+        q.z = pack_plain_f16x2(r[pc * 8 + 4], r[pc * 8 + 5]);
+        q.w = pack_plain_f16x2(r[pc * 8 + 6], r[pc * 8 + 7]);
+      }
+      *reinterpret_cast<uint4*>(chunk + ((uint32_t)((((c4 & 1) * 4 + pc) << 4)) ^ rx4)) = q;
+    }
+  }
+  return (al0 + al1) + (al2 + al3);
+}
+
+__device__ __forceinline__ void named_bar_sync(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
+__device__ __forceinline__ void named_bar_arrive(int id, int threads) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
 
 // kStash: additionally write every layer's fp16 output chunk (TMA bulk store of the shared-memory image the next layer's
 // MMAs read anyway), the ReLU sign masks and the alpha pre-activation to the training stash.
@@ -644,9 +402,10 @@ __global__ void __launch_bounds__(PP_THREADS, 1) nerf_mlp_tc_pp_kernel(const __g
                                                                        const __grid_constant__ NetPlan plan,
                                                                        const __grid_constant__ CUtensorMap tmap,
                                                                        const __grid_constant__ StashArgs sa) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  extern __shared__ __align__(1024) uint8_t smem_fwd[];
+  uint8_t* smem = smem_fwd;
   const uint32_t sbase = smem_u32(smem);
+  if ((sbase & 1023u) != 0u) __trap();                  // SWIZZLE_128B operand tiles need 1024-byte alignment
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t cta_rank = cluster_ctarank();
   const int64_t unit0 = cluster_id_x(), n_units = num_clusters_x();
@@ -661,7 +420,6 @@ __global__ void __launch_bounds__(PP_THREADS, 1) nerf_mlp_tc_pp_kernel(const __g
     for (int s = 0; s < NUM_STAGES; ++s) {
       mbar_init(bar_full + 8 * s, 1);
       mbar_init(bar_empty + 8 * s, 1);
-      mbar_init(bar_peer_full + 8 * s, 1);
     }
     for (int t = 0; t < 2; ++t) {
       mbar_init(bar_acc + 8 * t, 1);
@@ -676,13 +434,17 @@ __global__ void __launch_bounds__(PP_THREADS, 1) nerf_mlp_tc_pp_kernel(const __g
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0) {
-    if (lane == 0) pp_weight_producer(plan, &tmap, sbase, bar_full, bar_empty, cta_rank, unit0, n_steps, n_units);
-  } else if (warp == 1) {
-    if (cta_rank == 0) pp_mma_issuer(plan, sbase, tmem_base, bar_full, bar_empty, bar_acc, bar_aready, unit0, n_steps, n_units, a.dbg);
-  } else if (warp >= 4) {
+  if (warp < PP_EPI_WARP0) {
+    regs_control();
+    if (warp == 0) {
+      if (lane == 0) pp_weight_producer(plan, &tmap, sbase, bar_full, bar_empty, cta_rank, unit0, n_steps, n_units);
+    } else if (warp == 1) {
+      if (cta_rank == 0) pp_mma_issuer(plan, sbase, tmem_base, bar_full, bar_empty, bar_acc, bar_aready, unit0, n_steps, n_units, a.dbg);
+    }
+  } else {
     // ================= prologue / epilogue warps: thread == one row x 128 columns =================
-    const int ew = warp - 4;
+    regs_epilogue();
+    const int ew = warp - PP_EPI_WARP0;
     const int tile = ew >> 3;
     const int quarter = warp & 3;                       // TMEM lane quarter this warp may access
     const int half = (ew >> 2) & 1;                     // which 128 accumulator columns
@@ -693,6 +455,11 @@ __global__ void __launch_bounds__(PP_THREADS, 1) nerf_mlp_tc_pp_kernel(const __g
     const PackedTail* tail = reinterpret_cast<const PackedTail*>(a.packed + (size_t)plan.stages_per_pass * STAGE_BYTES);
     const uint32_t my_acc = bar_acc + 8 * tile, my_aready = bar_aready + 8 * tile;
     const uint32_t aready_target = cta_rank != 0 ? map_to_cta(my_aready, 0) : my_aready;
+    const int pair_bar = 1 + tile * 4 + quarter;         // named barrier shared by the two column-half warps of this row quarter
+    const int tile_bar = 9 + tile;                       // named barrier of the tile's 8 epilogue warps
+    const int tid_tile = half * 128 + row;               // 0..255 within the tile's epilogue threads
+    float* sbias = reinterpret_cast<float*>(smem + OFF_BIAS) + tile * W;
+    const uint32_t row_off = (uint32_t)((row >> 3) * 1024 + (row & 7) * 128), rx4 = (uint32_t)((row & 7) << 4);
     uint32_t acc_phase = 0;
     [[maybe_unused]] Tracer tr;
     auto signal_a_ready = [&]() {
@@ -704,241 +471,273 @@ __global__ void __launch_bounds__(PP_THREADS, 1) nerf_mlp_tc_pp_kernel(const __g
         else mbar_arrive(my_aready);
       }
     };
+    // global point index of this thread's row in step `step`
+    auto point_of = [&](int64_t step) { return (2 * step + cta_rank) * (int64_t)(TILES * TILE_M) + tile * TILE_M + row; };
 
-    for (int64_t step = unit0; step < n_steps; step += n_units) {
-      const int64_t pair = 2 * step + cta_rank;
-      const int64_t p_raw = pair * (TILES * TILE_M) + tile * TILE_M + row;
-      const bool live = p_raw < a.P;
-      const int64_t p = live ? p_raw : a.P - 1;
-      const int64_t tile_g = 2 * pair + tile;            // 128-point tile index in the stash
-
-      // ---- positional encoding: this thread writes encoding-chunk columns [32*half, 32*half + 32) of its row ----
-      TRACE(tr, 0x400);                                  // epilogue warp: prologue begins
-      {
-        float v[32];
+    // ---- positional encoding of this thread's 32 encoding-chunk columns [32*half, 32*half + 32) for step `step`, as 16 packed
+    //      fp16 pairs.  Computed one layer early (while the views layer's MMAs run) and stored once those MMAs have retired.
+    auto encode = [&](int64_t step, uint32_t (&pk)[16], float (&vd)[3]) {
+      const int64_t p_raw = point_of(step);
+      const int64_t p = p_raw < a.P ? p_raw : a.P - 1;
+      float v[32];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = 0.f;
-        if (a.rays != nullptr) {
-          const int64_t r = p / a.S;
-          const float* ray = a.rays + r * a.ray_stride;
-          const float zz = a.z[p];
-          const float cen[3] = {a.cx, a.cy, a.cz};
-          const int in_ch = 3 + 6 * a.multires;
+      for (int i = 0; i < 32; ++i) v[i] = 0.f;
+      if (a.rays != nullptr) {
+        const int64_t r = a.P < (int64_t)0x7fffffff ? (int64_t)((uint32_t)p / (uint32_t)a.S) : p / a.S;
+        const float* ray = a.rays + r * a.ray_stride;
+        const float zz = a.z[p];
+        const float cen[3] = {a.cx, a.cy, a.cz};
 #pragma unroll
-          for (int d = 0; d < 3; ++d) {
-            float pt = __fadd_rn(ray[d], __fmul_rn(ray[3 + d], zz));            // RS:657
-            float x = __fmul_rn(__fsub_rn(pt, cen[d]), a.bb_scale);             // RS:52
-            float xp = __fmul_rn(x, 3.14159274101257324f);                      // H:165
-            if (half == 0) {
-              v[d] = x;                                                         // columns 0..2
+        for (int d = 0; d < 3; ++d) {
+          float pt = __fadd_rn(ray[d], __fmul_rn(ray[3 + d], zz));            // RS:657
+          float x = __fmul_rn(__fsub_rn(pt, cen[d]), a.bb_scale);             // RS:52
+          float xp = __fmul_rn(x, 3.14159274101257324f);                      // H:165
+          if (half == 0) {
+            v[d] = x;                                                         // columns 0..2
 #pragma unroll
-              for (int k = 0; k < 5; ++k) {
-                if (k < a.multires) {
-                  float s, c;
-                  sincos_reduced(__fmul_rn(xp, (float)(1 << k)), &s, &c);
-                  if (3 + 6 * k + d < 32) v[3 + 6 * k + d] = s;                 // sin block of octave k
-                  if (6 + 6 * k + d < 32) v[6 + 6 * k + d] = c;                 // cos block
-                }
+            for (int k = 0; k < 5; ++k) {
+              if (k < a.multires) {
+                float s, c;
+                sincos_reduced(__fmul_rn(xp, (float)(1 << k)), &s, &c);
+                if (3 + 6 * k + d < 32) v[3 + 6 * k + d] = s;                 // sin block of octave k
+                if (6 + 6 * k + d < 32) v[6 + 6 * k + d] = c;                 // cos block
               }
-            } else {
+            }
+          } else {
 #pragma unroll
-              for (int k = 4; k < 9; ++k) {
-                if (k < a.multires) {
-                  float s, c;
-                  sincos_reduced(__fmul_rn(xp, (float)(1 << k)), &s, &c);
-                  if (3 + 6 * k + d >= 32) v[3 + 6 * k + d - 32] = s;
-                  if (6 + 6 * k + d >= 32) v[6 + 6 * k + d - 32] = c;
-                }
+            for (int k = 4; k < 9; ++k) {
+              if (k < a.multires) {
+                float s, c;
+                sincos_reduced(__fmul_rn(xp, (float)(1 << k)), &s, &c);
+                if (3 + 6 * k + d >= 32) v[3 + 6 * k + d - 32] = s;
+                if (6 + 6 * k + d >= 32) v[6 + 6 * k + d - 32] = c;
               }
             }
           }
-          if (half == 1) {
-            v[ONES_COL - 32] = 1.0f;
-            v[ONES_COL + 1 - 32] = 1.0f;
-          }
+        }
 #pragma unroll
-          for (int pc = 0; pc < 4; ++pc) {
-            uint4 q;
-            q.x = pack_f16x2(v[pc * 8 + 0], v[pc * 8 + 1]);
-            q.y = pack_f16x2(v[pc * 8 + 2], v[pc * 8 + 3]);
-            q.z = pack_f16x2(v[pc * 8 + 4], v[pc * 8 + 5]);
-            q.w = pack_f16x2(v[pc * 8 + 6], v[pc * 8 + 7]);
-            *reinterpret_cast<uint4*>(emb_tile + sw128_offset(row, half * 4 + pc)) = q;
-          }
-          // view direction (multires_views == 0): columns in_ch .. in_ch+2, written by the thread that owns them
+        for (int d = 0; d < 3; ++d) vd[d] = ray[8 + d];
+      } else {
+        vd[0] = vd[1] = vd[2] = 0.f;
+        const float* x = a.x_embedded + p * a.in_all;
 #pragma unroll
-          for (int d = 0; d < 3; ++d) {
-            const int col = in_ch + d;
-            if ((col >> 5) == half)
-              *reinterpret_cast<__half*>(emb_tile + sw128_offset(row, col >> 3) + (col & 7) * 2) = __float2half_rn(ray[8 + d]);
-          }
-        } else {
-          const float* x = a.x_embedded + p * a.in_all;
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const int col = 32 * half + i;
-            if (col < a.in_all) v[i] = x[col];
-            if (col == ONES_COL || col == ONES_COL + 1) v[i] = 1.0f;
-          }
-#pragma unroll
-          for (int pc = 0; pc < 4; ++pc) {
-            uint4 q;
-            q.x = pack_f16x2(v[pc * 8 + 0], v[pc * 8 + 1]);
-            q.y = pack_f16x2(v[pc * 8 + 2], v[pc * 8 + 3]);
-            q.z = pack_f16x2(v[pc * 8 + 4], v[pc * 8 + 5]);
-            q.w = pack_f16x2(v[pc * 8 + 6], v[pc * 8 + 7]);
-            *reinterpret_cast<uint4*>(emb_tile + sw128_offset(row, half * 4 + pc)) = q;
-          }
+        for (int i = 0; i < 32; ++i) {
+          const int col = 32 * half + i;
+          if (col < a.in_all) v[i] = x[col];
         }
       }
+      if (half == 1) {
+        v[ONES_COL - 32] = 1.0f;
+        v[ONES_COL + 1 - 32] = 1.0f;
+      }
+#pragma unroll
+      for (int i = 0; i < 16; ++i) pk[i] = pack_f16x2(v[2 * i], v[2 * i + 1]);
+    };
+    auto store_emb = [&](const uint32_t (&pk)[16], const float (&vd)[3]) {
+#pragma unroll
+      for (int pc = 0; pc < 4; ++pc)
+        *reinterpret_cast<uint4*>(emb_tile + sw128_offset(row, half * 4 + pc)) = make_uint4(pk[4 * pc], pk[4 * pc + 1], pk[4 * pc + 2], pk[4 * pc + 3]);
+      if (a.rays != nullptr) {
+        // view direction (multires_views == 0): columns in_ch .. in_ch+2, written by the thread that owns them
+        const int in_ch = 3 + 6 * a.multires;
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+          const int col = in_ch + d;
+          if ((col >> 5) == half)
+            *reinterpret_cast<__half*>(emb_tile + sw128_offset(row, col >> 3) + (col & 7) * 2) = __float2half_rn(vd[d]);
+        }
+      }
+    };
+
+    if (unit0 < n_steps) {
+      TRACE(tr, 0x400);                                  // epilogue warp: first prologue begins
+      uint32_t pk[16];
+      float vd[3];
+      encode(unit0, pk, vd);
+      store_emb(pk, vd);
       signal_a_ready();
       TRACE(tr, 0x401);                                  // prologue done, operand signalled
+    }
 
-      float alpha = 0.f;
+    for (int64_t step = unit0; step < n_steps; step += n_units) {
+      const int64_t p_raw = point_of(step);
+      const bool live = p_raw < a.P;
+      const int64_t tile_g = 2 * (2 * step + cta_rank) + tile;            // 128-point tile index in the stash
+
+      float alpha = 0.f;                                  // this thread's share of alpha_linear (its 128 columns)
       for (int l = 0; l < plan.n_layers; ++l) {
-        const int kind = plan.layers[l].kind, relu = plan.layers[l].relu;
-        mbar_wait(my_acc, acc_phase);
-        acc_phase ^= 1;
-        tc_fence_after();
-        TRACE(tr, 0x500 + l);                            // accumulators of layer l visible
-#if SCADE_TC_TRACE
-        if (a.dbg & 32) {                                // timing ablation: no epilogue work at all
-          if (kind != 3) signal_a_ready();
-          TRACE(tr, 0x700 + l);
-          continue;
-        }
-#endif
+        const int kind = plan.layers[l].kind, relu = plan.layers[l].relu, bias_epi = plan.layers[l].bias_epi;
         if (kind != 3) {
+          // fetched while the layer's MMAs run: this thread's element of the bias row that goes through shared memory
+          float s_mine = 0.f;
+          if (bias_epi) s_mine = __ldg(tail->bias[l] + tid_tile);
+          mbar_wait(my_acc, acc_phase);
+          acc_phase ^= 1;
+          tc_fence_after();
+          TRACE(tr, 0x500 + l);                            // accumulators of layer l visible
+#if SCADE_TC_TRACE
+          if (a.dbg & 32) {                                // timing ablation: no epilogue work at all
+            signal_a_ready();
+            TRACE(tr, 0x700 + l);
+            continue;
+          }
+#endif
           // hidden / feature layer: this thread's 128 accumulator columns -> A chunks 2*half, 2*half+1
-          uint32_t rbuf[2][32];
           uint32_t sgn[4];
           const uint32_t t_col = t_lane + half * 128;
-          tmem_ld32(t_col, rbuf[0]);
           if (kStash) {
             if (l == 0 && half == 0 && lane == 0) {       // the encoding chunk of this tile is complete: stash this warp's 32 rows
-              if (!(a.dbg & 4)) bulk_s2g(sa.ws + sa.L.emb + (size_t)tile_g * CHUNK_BYTES + quarter * 4096, smem_u32(emb_tile) + quarter * 4096, 4096);
+              bulk_s2g(sa.ws + sa.L.emb + (size_t)tile_g * CHUNK_BYTES + quarter * 4096, smem_u32(emb_tile) + quarter * 4096, 4096);
               bulk_commit();
             }
-            if (lane == 0 && !(a.dbg & 16)) bulk_wait_read0();             // earlier stash stores no longer read the rows overwritten below
+            if (lane == 0) bulk_wait_read0();             // earlier stash stores no longer read the rows overwritten below
             __syncwarp();
           }
-#pragma unroll
-          for (int c4 = 0; c4 < 4; ++c4) {
-            uint32_t* r = rbuf[c4 & 1];
-            tmem_ld_wait();
-            if (c4 + 1 < 4) tmem_ld32(t_col + (c4 + 1) * 32, rbuf[(c4 + 1) & 1]);
-            if (kStash) sgn[c4] = sign_mask32(r);
-            uint8_t* chunk = a_tile + (2 * half + (c4 >> 1)) * CHUNK_BYTES;
-#pragma unroll
-            for (int pc = 0; pc < 4; ++pc) {
-              uint4 q;
-              if (relu) {
-                q.x = pack_relu_f16x2(r[pc * 8 + 0], r[pc * 8 + 1]);
-                q.y = pack_relu_f16x2(r[pc * 8 + 2], r[pc * 8 + 3]);
-                q.z = pack_relu_f16x2(r[pc * 8 + 4], r[pc * 8 + 5]);
-                q.w = pack_relu_f16x2(r[pc * 8 + 6], r[pc * 8 + 7]);
-              } else {
-                q.x = pack_plain_f16x2(r[pc * 8 + 0], r[pc * 8 + 1]);
-                q.y = pack_plain_f16x2(r[pc * 8 + 2], r[pc * 8 + 3]);
-                q.z = pack_plain_f16x2(r[pc * 8 + 4], r[pc * 8 + 5]);
-                q.w = pack_plain_f16x2(r[pc * 8 + 6], r[pc * 8 + 7]);
-              }
-              *reinterpret_cast<uint4*>(chunk + sw128_offset(row, (c4 & 1) * 4 + pc)) = q;
-            }
+          if (bias_epi) {
+            // the tile's row goes through shared memory (broadcast LDS.128 in the epilogue).  No thread of the tile can still
+            // be reading the previous layer's row: every warp signalled its operand before these MMAs were issued.
+            sbias[tid_tile] = s_mine;
+            named_bar_sync(tile_bar, 256);
           }
+          uint8_t* dst = a_tile + 2 * half * CHUNK_BYTES + row_off;
+          const float* srow = sbias + half * 128;
+          const float* walpha = tail->w_alpha + half * 128;
+          if (kind == 1) {
+            if (bias_epi) alpha = hidden_epilogue<true, true, true, kStash>(t_col, dst, rx4, srow, walpha, sgn);
+            else alpha = hidden_epilogue<false, true, true, kStash>(t_col, dst, rx4, srow, walpha, sgn);
+          } else if (kind == 2) hidden_epilogue<true, false, false, false>(t_col, dst, rx4, srow, walpha, sgn);
+          else if (bias_epi) hidden_epilogue<true, true, false, kStash>(t_col, dst, rx4, srow, walpha, sgn);
+          else hidden_epilogue<false, true, false, kStash>(t_col, dst, rx4, srow, walpha, sgn);
           TRACE(tr, 0x600 + l);                          // operand chunks written
-          if (kind == 1 && half == 0) {
-            // alpha_linear on the un-rounded fp32 activations of the last hidden layer (H:233): the half-0 thread of
-            // each row walks all 256 columns once more
-#pragma unroll 1
-            for (int c8 = 0; c8 < W / 32; ++c8) {
-              uint32_t r[32];
-              tmem_ld32(t_lane + c8 * 32, r);
-              tmem_ld_wait();
-              const float* wa = tail->w_alpha + c8 * 32;
-#pragma unroll
-              for (int j = 0; j < 32; ++j) alpha = fmaf(fmaxf(__uint_as_float(r[j]), 0.f), __ldg(wa + j), alpha);
-            }
-          }
           signal_a_ready();
           TRACE(tr, 0x700 + l);                          // signalled
           if (kStash) {
-            if (relu && !(a.dbg & 8))
+            if (relu)
               *reinterpret_cast<uint4*>(sa.ws + sa.L.maskh[l] + ((size_t)(tile_g * 2 + half) * TILE_M + row) * 16) =
                   make_uint4(sgn[0], sgn[1], sgn[2], sgn[3]);
             if (lane == 0) {
               uint8_t* dst = sa.ws + (kind == 2 ? sa.L.feat : sa.L.h[l]) + (size_t)(tile_g * 4 + 2 * half) * CHUNK_BYTES + quarter * 4096;
               const uint32_t src = smem_u32(a_tile) + 2 * half * CHUNK_BYTES + quarter * 4096;
-              if (!(a.dbg & 4)) bulk_s2g(dst, src, 4096);
-              if (!(a.dbg & 4)) bulk_s2g(dst + CHUNK_BYTES, src + CHUNK_BYTES, 4096);
+              bulk_s2g(dst, src, 4096);
+              bulk_s2g(dst + CHUNK_BYTES, src + CHUNK_BYTES, 4096);
               bulk_commit();
             }
           }
         } else {
-          // views layer (N = 128) + rgb_linear + output, done by the half-0 thread of each row      H:238-242
-          if (half == 0) {
-            float cr = 0.f, cg = 0.f, cb = 0.f;
-            uint32_t sgn[4];
-            if (kStash) {
-              if (lane == 0 && !(a.dbg & 16)) bulk_wait_read0();           // A chunks 0/1 (feature, fully consumed by now) become the h_v staging area
-              __syncwarp();
-            }
-#pragma unroll 1
-            for (int c4 = 0; c4 < 4; ++c4) {
-              uint32_t r[32];
-              tmem_ld32(t_lane + c4 * 32, r);
-              tmem_ld_wait();
+          // views layer (N = 128) + rgb_linear + output (H:238-242).  The two column-half threads of a row take 64 hidden
+          // columns each; half 1 hands its partial sums (and its share of alpha) to half 0 through shared memory.
+          // The next step's encoding is computed BEFORE waiting for this layer's MMAs and stored right after them.
+          const int64_t next = step + n_units;
+          const bool has_next = next < n_steps;
+          uint32_t pk[16];
+          float vd[3];
+          if (has_next) encode(next, pk, vd);
+          // rgb_linear's weights (3 x 128 fp32) are staged by one warp of the tile in activation chunk 3, which is dead once
+          // this layer's MMAs have retired
+          const bool stager = (half == 1 && quarter == 0);
+          float4 wst[3];
+          if (stager) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                float h = fmaxf(__uint_as_float(r[j]), 0.f);
-                float4 w = __ldg(tail->w_rgb + c4 * 32 + j);
-                cr = fmaf(h, w.x, cr);
-                cg = fmaf(h, w.y, cg);
-                cb = fmaf(h, w.z, cb);
-              }
-              if (kStash) {
-                const uint32_t sg = sign_mask32(r);
-                sgn[0] = c4 == 0 ? sg : sgn[0]; sgn[1] = c4 == 1 ? sg : sgn[1];
-                sgn[2] = c4 == 2 ? sg : sgn[2]; sgn[3] = c4 == 3 ? sg : sgn[3];
-                uint8_t* chunk = a_tile + (c4 >> 1) * CHUNK_BYTES;
+            for (int i = 0; i < 3; ++i) wst[i] = __ldg(reinterpret_cast<const float4*>(&tail->w_rgb_p[0][0]) + i * 32 + lane);
+          }
+          mbar_wait(my_acc, acc_phase);
+          acc_phase ^= 1;
+          tc_fence_after();
+          TRACE(tr, 0x500 + l);
+#if SCADE_TC_TRACE
+          if (a.dbg & 32) {
+            tc_fence_before();
+            if (has_next) { store_emb(pk, vd); signal_a_ready(); }
+            TRACE(tr, 0x700 + l);
+            continue;
+          }
+#endif
+          float cr[2] = {0.f, 0.f}, cg[2] = {0.f, 0.f}, cb[2] = {0.f, 0.f};
+          uint32_t sgn[2];
+          uint8_t* hv_chunk = a_tile + 2 * half * CHUNK_BYTES;      // stash staging of this half's 64 h_v columns (own chunk)
+          float4* scratch = reinterpret_cast<float4*>(a_tile + 3 * CHUNK_BYTES + quarter * 4096) + lane;   // half 1's own, dead chunk
+          if (kStash) {
+            if (lane == 0) bulk_wait_read0();              // this warp's feature-chunk stash stores have read their source
+            __syncwarp();
+          }
+          float* srgb = reinterpret_cast<float*>(a_tile + 3 * CHUNK_BYTES + 1024);     // [3][128], clear of the scratch rows
+          if (stager) {
 #pragma unroll
-                for (int pc = 0; pc < 4; ++pc) {
-                  uint4 q;
-                  q.x = pack_relu_f16x2(r[pc * 8 + 0], r[pc * 8 + 1]);
-                  q.y = pack_relu_f16x2(r[pc * 8 + 2], r[pc * 8 + 3]);
-                  q.z = pack_relu_f16x2(r[pc * 8 + 4], r[pc * 8 + 5]);
-                  q.w = pack_relu_f16x2(r[pc * 8 + 6], r[pc * 8 + 7]);
-                  *reinterpret_cast<uint4*>(chunk + sw128_offset(row, (c4 & 1) * 4 + pc)) = q;
-                }
-              }
-            }
-            const float al = alpha + __ldg(&tail->b_alpha);
-            if (live) {
-              a.out[p_raw] = make_float4(cr + __ldg(&tail->b_rgb[0]), cg + __ldg(&tail->b_rgb[1]),
-                                         cb + __ldg(&tail->b_rgb[2]), softplus_beta10(al));
+            for (int i = 0; i < 3; ++i) reinterpret_cast<float4*>(srgb)[i * 32 + lane] = wst[i];
+          }
+          named_bar_sync(tile_bar, 256);
+          const float4* wr4 = reinterpret_cast<const float4*>(srgb + half * 64);
+          const float4* wg4 = reinterpret_cast<const float4*>(srgb + 128 + half * 64);
+          const float4* wb4 = reinterpret_cast<const float4*>(srgb + 256 + half * 64);
+#pragma unroll
+          for (int c2 = 0; c2 < 2; ++c2) {
+            uint32_t r[32];
+            tmem_ld32(t_lane + half * 64 + c2 * 32, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const float4 wr = wr4[c2 * 8 + q], wg = wg4[c2 * 8 + q], wb = wb4[c2 * 8 + q];
+              const float h0 = fmaxf(__uint_as_float(r[4 * q + 0]), 0.f), h1 = fmaxf(__uint_as_float(r[4 * q + 1]), 0.f);
+              const float h2 = fmaxf(__uint_as_float(r[4 * q + 2]), 0.f), h3 = fmaxf(__uint_as_float(r[4 * q + 3]), 0.f);
+              cr[0] = fmaf(h0, wr.x, cr[0]); cg[0] = fmaf(h0, wg.x, cg[0]); cb[0] = fmaf(h0, wb.x, cb[0]);
+              cr[1] = fmaf(h1, wr.y, cr[1]); cg[1] = fmaf(h1, wg.y, cg[1]); cb[1] = fmaf(h1, wb.y, cb[1]);
+              cr[0] = fmaf(h2, wr.z, cr[0]); cg[0] = fmaf(h2, wg.z, cg[0]); cb[0] = fmaf(h2, wb.z, cb[0]);
+              cr[1] = fmaf(h3, wr.w, cr[1]); cg[1] = fmaf(h3, wg.w, cg[1]); cb[1] = fmaf(h3, wb.w, cb[1]);
             }
             if (kStash) {
-              *reinterpret_cast<uint4*>(sa.ws + sa.L.maskv + (size_t)(tile_g * TILE_M + row) * 16) = make_uint4(sgn[0], sgn[1], sgn[2], sgn[3]);
-              reinterpret_cast<float*>(sa.ws + sa.L.alpha)[tile_g * TILE_M + row] = al;
-              fence_proxy_async();
-              __syncwarp();
-              if (lane == 0) {
-                uint8_t* dst = sa.ws + sa.L.hv + (size_t)(tile_g * 2) * CHUNK_BYTES + quarter * 4096;
-                const uint32_t src = smem_u32(a_tile) + quarter * 4096;
-                if (!(a.dbg & 4)) bulk_s2g(dst, src, 4096);
-                if (!(a.dbg & 4)) bulk_s2g(dst + CHUNK_BYTES, src + CHUNK_BYTES, 4096);
-                bulk_commit();
+              sgn[c2] = sign_mask32(r);
+#pragma unroll
+              for (int pc = 0; pc < 4; ++pc) {
+                uint4 q;
+                q.x = pack_relu_f16x2(r[pc * 8 + 0], r[pc * 8 + 1]);
+                q.y = pack_relu_f16x2(r[pc * 8 + 2], r[pc * 8 + 3]);
+                q.z = pack_relu_f16x2(r[pc * 8 + 4], r[pc * 8 + 5]);
+                q.w = pack_relu_f16x2(r[pc * 8 + 6], r[pc * 8 + 7]);
+                *reinterpret_cast<uint4*>(hv_chunk + sw128_offset(row, c2 * 4 + pc)) = q;
               }
             }
           }
+          // accumulators are in registers: the next step's layer 0 may overwrite them.  Half 1 publishes its partial sums,
+          // half 0 picks them up BEFORE either signals (the scratch rows are overwritten by the next step's layer-0 epilogue).
           tc_fence_before();
+          const float pr = cr[0] + cr[1], pg = cg[0] + cg[1], pb = cb[0] + cb[1];
+          float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (half == 1) {
+            *scratch = make_float4(pr, pg, pb, alpha);
+            __threadfence_block();
+            named_bar_arrive(pair_bar, 64);
+          }
+          if (has_next) store_emb(pk, vd);
+          if (half == 0) {
+            named_bar_sync(pair_bar, 64);
+            o = *scratch;
+          }
+          if (has_next) signal_a_ready();
+          TRACE(tr, 0x600 + l);
+          if (half == 0) {
+            const float al = (alpha + o.w) + __ldg(&tail->b_alpha);
+            if (live) {
+              a.out[p_raw] = make_float4((pr + o.x) + __ldg(&tail->b_rgb[0]), (pg + o.y) + __ldg(&tail->b_rgb[1]),
+                                         (pb + o.z) + __ldg(&tail->b_rgb[2]), softplus_beta10(al));
+            }
+            if (kStash) reinterpret_cast<float*>(sa.ws + sa.L.alpha)[tile_g * TILE_M + row] = al;
+          }
+          if (kStash) {
+            *reinterpret_cast<uint2*>(sa.ws + sa.L.maskv + (size_t)(tile_g * TILE_M + row) * 16 + half * 8) = make_uint2(sgn[0], sgn[1]);
+            if (!has_next) fence_proxy_async();            // (signal_a_ready already fenced the generic-proxy writes otherwise)
+            __syncwarp();
+            if (lane == 0) {
+              bulk_s2g(sa.ws + sa.L.hv + (size_t)(tile_g * 2 + half) * CHUNK_BYTES + quarter * 4096, smem_u32(hv_chunk) + quarter * 4096, 4096);
+              bulk_commit();
+            }
+          }
           TRACE(tr, 0x700 + l);                          // views epilogue done
         }
       }
     }
   }
 
-  if (kStash && warp >= 4 && lane == 0) bulk_wait_all0();     // stash stores are complete before the CTA retires
+  if (kStash && warp >= PP_EPI_WARP0 && lane == 0) bulk_wait_all0();     // stash stores are complete before the CTA retires
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();
@@ -956,12 +755,18 @@ __device__ __forceinline__ void split_f16(float b, __half* hi, __half* lo) {
 
 __global__ void pack_kernel(const __grid_constant__ PackPlan plan, uint8_t* __restrict__ out) {
   if ((int)blockIdx.x == plan.n_stages) {
-    // fp32 tail: rgb_linear as (r,g,b,0) per hidden column, alpha_linear, head biases
+    // fp32 tail: rgb_linear (two layouts), alpha_linear, head biases, epilogue biases
     if (plan.w_alpha == nullptr) return;
     PackedTail* tail = reinterpret_cast<PackedTail*>(out + (size_t)plan.n_stages * STAGE_BYTES);
-    for (int k = threadIdx.x; k < W / 2; k += blockDim.x)
+    for (int k = threadIdx.x; k < W / 2; k += blockDim.x) {
       tail->w_rgb[k] = make_float4(plan.w_rgb[k], plan.w_rgb[W / 2 + k], plan.w_rgb[W + k], 0.f);
+      tail->w_rgb_p[0][k] = plan.w_rgb[k];
+      tail->w_rgb_p[1][k] = plan.w_rgb[W / 2 + k];
+      tail->w_rgb_p[2][k] = plan.w_rgb[W + k];
+    }
     for (int k = threadIdx.x; k < W; k += blockDim.x) tail->w_alpha[k] = plan.w_alpha[k];
+    for (int l = 0; l < MAX_LAYERS; ++l)
+      for (int k = threadIdx.x; k < W; k += blockDim.x) tail->bias[l][k] = plan.epi_bias[l] ? plan.epi_bias[l][k] : 0.f;
     if (threadIdx.x == 0) {
       tail->b_alpha = plan.b_alpha[0];
       tail->b_rgb[0] = plan.b_rgb[0]; tail->b_rgb[1] = plan.b_rgb[1]; tail->b_rgb[2] = plan.b_rgb[2];
@@ -971,23 +776,28 @@ __global__ void pack_kernel(const __grid_constant__ PackPlan plan, uint8_t* __re
   const StageDesc& sd = plan.st[blockIdx.x];
   __half* dst = reinterpret_cast<__half*>(out + (size_t)blockIdx.x * STAGE_BYTES);
   for (int idx = threadIdx.x; idx < STAGE_N * KCHUNK; idx += blockDim.x) {
-    int n = idx / KCHUNK, k = idx % KCHUNK;
+    const int n = idx / KCHUNK, k = idx % KCHUNK;
     __half hv = __float2half_rn(0.f);
-    if (sd.bias_mode == 2) {
-      // bias stage of one N half: K-step 0 only; positions 12/13 meet the encoding chunk's 1.0 columns (60/61 = 48+12/13)
-      if (k == 12 || k == 13) {
-        __half hi, lo;
-        split_f16(sd.bias[sd.row0 + n], &hi, &lo);
-        hv = (k == 12) ? hi : lo;
+    for (int j = 0; j < sd.n_blocks; ++j) {
+      const StageBlock& b = sd.blk[j];
+      const int bn = n - b.dst_row0;
+      if (bn < 0 || bn >= b.nrows) continue;
+      if (b.bias_mode == 2) {
+        // bias stage: K-step 0 only; positions 12/13 meet the encoding chunk's 1.0 columns (60/61 = 48 + 12/13)
+        if (k == 12 || k == 13) {
+          __half hi, lo;
+          split_f16(sd.bias[sd.row0 + bn], &hi, &lo);
+          hv = (k == 12) ? hi : lo;
+        }
+        continue;
       }
-    } else {
-      int sc = k - sd.dst_col0;
-      if (n < sd.nrows && sc >= 0 && sc < sd.ncols)
-        hv = __float2half_rn(sd.trans ? sd.W[(int64_t)(sd.col0 + sc) * sd.ld + sd.row0 + n]
-                                      : sd.W[(int64_t)(sd.row0 + n) * sd.ld + sd.col0 + sc]);
-      if (sd.bias_mode == 1 && n < sd.nrows && (k == ONES_COL || k == ONES_COL + 1)) {
+      const int sc = k - b.dst_col0;
+      if (sc >= 0 && sc < b.ncols)
+        hv = __float2half_rn(sd.trans ? sd.W[(int64_t)(b.col0 + sc) * sd.ld + sd.row0 + bn]
+                                      : sd.W[(int64_t)(sd.row0 + bn) * sd.ld + b.col0 + sc]);
+      if (b.bias_mode == 1 && (k == ONES_COL || k == ONES_COL + 1)) {
         __half hi, lo;
-        split_f16(sd.bias[sd.row0 + n], &hi, &lo);
+        split_f16(sd.bias[sd.row0 + bn], &hi, &lo);
         hv = (k == ONES_COL) ? hi : lo;
       }
     }
@@ -996,49 +806,53 @@ __global__ void pack_kernel(const __grid_constant__ PackPlan plan, uint8_t* __re
   }
 }
 
-// Process-wide choice of the kernel form (SCADE_TC_PAIR=0 selects the single-CTA form).
-static bool use_pair() {
-  static const bool v = []() {
-    const char* e = getenv("SCADE_TC_PAIR");
-    return !(e && e[0] == '0');
-  }();
-  return v;
-}
-
 // Build the layer table and the stage list for a network description.  Stage order = consumption order:
-// layer -> K chunk -> N half (pair mode: CTA 0's half, CTA 1's half), then the layer's two bias stages.
-static void build_plans(const scade_net& net, bool pair, NetPlan* np, PackPlan* pp) {
+// layer -> ring stage -> CTA (CTA 0's N half, CTA 1's N half).  A ring stage holds `kpack` K chunks of one CTA's N half.
+static void build_plans(const scade_net& net, NetPlan* np, PackPlan* pp) {
   const scade_net_desc& d = net.desc;
   NetDims nd(d);
   NetPlan P{};
   PackPlan Q{};
-  auto add_stage = [&](const float* Wt, int ld, int col0, int ncols, int dst_col0, int row0, int nrows,
-                       const float* bias, int bias_mode) {
-    StageDesc s{Wt, ld, col0, ncols, dst_col0, row0, nrows, bias, bias_mode, 0};
-    Q.st[Q.n_stages++] = s;
-  };
+  // K chunk kc of a layer: the encoding chunk (columns emb_col0.. of the weight matrix land at stage columns emb_dst..,
+  // bias on the 1.0 columns) or activation chunk c (weight columns h_col0 + 64 c ..)
   auto add_layer = [&](const float* Wt, int fan_in, bool with_emb, int emb_col0, int emb_ncols, int emb_dst, int h_col0,
                        bool with_h, int n_out, int relu, int kind, const float* bias) {
     LayerDesc L{};
-    P.first_stage[P.n_layers] = Q.n_stages;
-    L.n_halves = n_out / STAGE_N;
+    const int li = P.n_layers;
+    P.first_stage[li] = Q.n_stages;
     L.relu = relu; L.kind = kind; L.n_out = n_out; L.a_step = 1;
-    L.bias_stage = with_emb ? 0 : 1;
+    L.bias_stage = 0;                                          // (kept in the format: a K=16 bias MMA step for layers that want it)
+    L.bias_epi = (with_emb || L.bias_stage) ? 0 : 1;
+    Q.epi_bias[li] = L.bias_epi ? bias : nullptr;
     int nk = 0;
     if (with_emb) L.a_src[nk++] = SRC_EMB;
     if (with_h) for (int c = 0; c < 4; ++c) L.a_src[nk++] = c;
     L.n_k = nk;
-    // pair mode always splits N over the two CTAs (N/2 rows each); single mode walks 128-row halves
-    const int parts = pair ? 2 : L.n_halves;
-    const int rows = n_out / parts;
-    for (int kc = 0; kc < nk; ++kc)
-      for (int h = 0; h < parts; ++h) {
-        if (L.a_src[kc] == SRC_EMB) add_stage(Wt, fan_in, emb_col0, emb_ncols, emb_dst, h * rows, rows, bias, 1);
-        else add_stage(Wt, fan_in, h_col0 + 64 * L.a_src[kc], 64, 0, h * rows, rows, nullptr, 0);
+    const int rows = n_out / 2;                                // N rows per CTA
+    L.kpack = STAGE_N / rows;                                  // 1 (N = 256) or 2 (N = 128)
+    const int n_own = (nk + L.kpack - 1) / L.kpack;
+    for (int i = 0; i < n_own; ++i)
+      for (int h = 0; h < 2; ++h) {
+        StageDesc s{};
+        s.W = Wt; s.ld = fan_in; s.row0 = h * rows; s.bias = bias; s.trans = 0;
+        for (int j = 0; j < L.kpack; ++j) {
+          const int kc = i * L.kpack + j;
+          if (kc >= nk) break;
+          StageBlock& b = s.blk[s.n_blocks++];
+          b.dst_row0 = j * rows; b.nrows = rows;
+          if (L.a_src[kc] == SRC_EMB) { b.col0 = emb_col0; b.ncols = emb_ncols; b.dst_col0 = emb_dst; b.bias_mode = 1; }
+          else { b.col0 = h_col0 + 64 * L.a_src[kc]; b.ncols = 64; b.dst_col0 = 0; b.bias_mode = 0; }
+        }
+        Q.st[Q.n_stages++] = s;
       }
     if (L.bias_stage)
-      for (int h = 0; h < 2; ++h) add_stage(nullptr, 0, 0, 0, 0, h * STAGE_N, STAGE_N, bias, 2);
-    P.n_stages[P.n_layers] = Q.n_stages - P.first_stage[P.n_layers];
+      for (int h = 0; h < 2; ++h) {
+        StageDesc s{};
+        s.W = nullptr; s.ld = 0; s.row0 = h * rows; s.bias = bias; s.trans = 0; s.n_blocks = 1;
+        s.blk[0].dst_row0 = 0; s.blk[0].nrows = rows; s.blk[0].bias_mode = 2;
+        Q.st[Q.n_stages++] = s;
+      }
+    P.n_stages[li] = Q.n_stages - P.first_stage[li];
     P.layers[P.n_layers++] = L;
   };
   for (int i = 0; i < d.D; ++i) {
@@ -1059,11 +873,11 @@ static void build_plans(const scade_net& net, bool pair, NetPlan* np, PackPlan* 
   if (pp) *pp = Q;
 }
 
-static int count_stages(const scade_net_desc& d, bool pair) {
-  int n = 2;                                   // layer 0: 1 K chunk x 2 halves (bias inside)
-  for (int i = 1; i < d.D; ++i) n += 10;       // 4 K chunks x 2 halves + 2 bias stages, or (skip layer) 5 x 2
-  n += 10;                                     // feature + 2 bias stages
-  n += pair ? 10 : 5;                          // views (N = 128): 5 K chunks, split over the pair or not
+static int count_stages(const scade_net_desc& d) {
+  int n = 2;                                   // layer 0: the encoding chunk x 2 CTAs (bias inside)
+  for (int i = 1; i < d.D; ++i) n += (i - 1 == d.skip) ? 10 : 8;      // 4 activation chunks (+ encoding chunk after the skip) x 2 CTAs
+  n += 8;                                      // feature_linear
+  n += 6;                                      // views (N = 128): 5 K chunks, two per stage, x 2 CTAs
   return n;
 }
 
@@ -1083,12 +897,14 @@ static void build_bwd_plans(const scade_net& net, NetPlan* np, PackPlan* pp) {
   auto add_layer = [&](const float* Wt, int ld, int n_out_fwd, int col0, int a_step) {
     LayerDesc L{};
     P.first_stage[P.n_layers] = Q.n_stages;
-    L.n_halves = 2; L.relu = 0; L.kind = 0; L.n_out = W; L.a_step = a_step; L.bias_stage = 0;
+    L.relu = 0; L.kind = 0; L.n_out = W; L.a_step = a_step; L.bias_epi = 0; L.kpack = 1; L.bias_stage = 0;
     L.n_k = n_out_fwd / KCHUNK;
     for (int kc = 0; kc < L.n_k; ++kc) {
       L.a_src[kc] = kc * a_step;
       for (int h = 0; h < 2; ++h) {
-        StageDesc sd{Wt, ld, 64 * kc, 64, 0, col0 + STAGE_N * h, STAGE_N, nullptr, 0, 1};
+        StageDesc sd{};
+        sd.W = Wt; sd.ld = ld; sd.row0 = col0 + STAGE_N * h; sd.bias = nullptr; sd.trans = 1; sd.n_blocks = 1;
+        sd.blk[0].col0 = 64 * kc; sd.blk[0].ncols = 64; sd.blk[0].dst_col0 = 0; sd.blk[0].dst_row0 = 0; sd.blk[0].nrows = STAGE_N;
         Q.st[Q.n_stages++] = sd;
       }
     }
@@ -1108,7 +924,7 @@ static void build_bwd_plans(const scade_net& net, NetPlan* np, PackPlan* pp) {
 }
 
 static size_t fwd_stream_bytes(const scade_net_desc& d) {
-  return (size_t)count_stages(d, true) * STAGE_BYTES + align_up(sizeof(PackedTail), 1024);
+  return (size_t)count_stages(d) * STAGE_BYTES + align_up(sizeof(PackedTail), 1024);
 }
 
 static TrainLayout train_layout(const scade_net_desc& d, int64_t P) {
@@ -1182,24 +998,21 @@ static int launch_pair(const void* kern, int clusters, int threads, int smem, cu
 bool mlp_tc_supported(const scade_net_desc& d) {
   NetDims nd(d);
   return d.W == tc::W && d.D >= 2 && d.D <= 8 && nd.in_all <= tc::ONES_COL && d.multires <= 9 && d.multires_views == 0 &&
-         d.skip != d.D - 1 && tc::count_stages(d, true) <= tc::MAX_STAGE_DESCS;
+         d.skip != d.D - 1 && tc::count_stages(d) <= tc::MAX_STAGE_DESCS;
 }
 
 size_t mlp_tc_packed_bytes(const scade_net_desc& d) {
-  if (!tc::use_pair()) return (size_t)tc::count_stages(d, false) * tc::STAGE_BYTES + align_up(sizeof(tc::PackedTail));
   return tc::fwd_stream_bytes(d) + (size_t)tc::count_bwd_stages(d) * tc::STAGE_BYTES;      // forward stream + tail | dgrad stream
 }
 
 int mlp_tc_pack(const scade_net& net, void* packed_out, cudaStream_t st) {
   tc::PackPlan pp;
-  tc::build_plans(net, tc::use_pair(), nullptr, &pp);
+  tc::build_plans(net, nullptr, &pp);
   tc::pack_kernel<<<pp.n_stages + 1, 256, 0, st>>>(pp, reinterpret_cast<uint8_t*>(packed_out));
   SCADE_LAUNCH_CHECK();
-  if (tc::use_pair()) {
-    tc::build_bwd_plans(net, nullptr, &pp);
-    tc::pack_kernel<<<pp.n_stages, 256, 0, st>>>(pp, reinterpret_cast<uint8_t*>(packed_out) + tc::fwd_stream_bytes(net.desc));
-    SCADE_LAUNCH_CHECK();
-  }
+  tc::build_bwd_plans(net, nullptr, &pp);
+  tc::pack_kernel<<<pp.n_stages, 256, 0, st>>>(pp, reinterpret_cast<uint8_t*>(packed_out) + tc::fwd_stream_bytes(net.desc));
+  SCADE_LAUNCH_CHECK();
   return SCADE_OK;
 }
 
@@ -1223,32 +1036,14 @@ int mlp_tc_stash_layout(const scade_net_desc& d, int64_t P, int64_t* out, int n)
 int mlp_tc_forward(const scade_net& net, const float* rays, int ray_stride, const float* z, const float* x_embedded,
                    int64_t N, int S, const float* bb_center, float bb_scale, float* raw_out, void* workspace,
                    size_t ws_bytes, int save, cudaStream_t st) {
-  const bool pair = tc::use_pair();
-  static const bool ping = []() {
-    const char* e = getenv("SCADE_TC_PING");
-    return !(e && e[0] == '0');
-  }();
-  using KernelFn = void (*)(const tc::FwdArgs, const tc::NetPlan);
-  KernelFn kern = pair ? (ping ? (KernelFn)tc::nerf_mlp_tc_kernel<true, true> : (KernelFn)tc::nerf_mlp_tc_kernel<true, false>)
-                       : (ping ? (KernelFn)tc::nerf_mlp_tc_kernel<false, true> : (KernelFn)tc::nerf_mlp_tc_kernel<false, false>);
-  static const bool use_pp = []() {
-    const char* e = getenv("SCADE_TC_PP");
-    return !(e && e[0] == '0');
-  }();
-  const bool pp = pair && use_pp;
-  if (save && !pp) {
-    set_error("SCADE_PREC_TC_F16 training needs the SM-pair ping-pong kernel (unset SCADE_TC_PAIR / SCADE_TC_PP)");
-    return SCADE_ERR_UNSUPPORTED;
-  }
   static bool attr_set = false;
   if (!attr_set) {
-    SCADE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
-    SCADE_CUDA(cudaFuncSetAttribute(tc::nerf_mlp_tc_pp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
-    SCADE_CUDA(cudaFuncSetAttribute(tc::nerf_mlp_tc_pp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
+    SCADE_CUDA(cudaFuncSetAttribute(tc::nerf_mlp_tc_pp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::FWD_SMEM_BYTES));
+    SCADE_CUDA(cudaFuncSetAttribute(tc::nerf_mlp_tc_pp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::FWD_SMEM_BYTES));
     attr_set = true;
   }
   tc::NetPlan plan;
-  tc::build_plans(net, pair, &plan, nullptr);
+  tc::build_plans(net, &plan, nullptr);
   NetDims nd(net.desc);
   tc::FwdArgs a{};
   a.packed = reinterpret_cast<const uint8_t*>(net.packed_f16);
@@ -1260,38 +1055,30 @@ int mlp_tc_forward(const scade_net& net, const float* rays, int ray_stride, cons
   a.multires = net.desc.multires; a.multires_views = net.desc.multires_views;
   a.out = reinterpret_cast<float4*>(raw_out);
   a.n_pairs = ceil_div<int64_t>(a.P, tc::TILES * tc::TILE_M);
+#if SCADE_TC_TRACE
   { const char* e = getenv("SCADE_TC_DBG"); a.dbg = e ? atoi(e) : 0; }
-  if (pp) {
-    // the packed stream as a 2D byte tensor: rows of 128 B (one swizzled K-major row), 128 rows per 16 KB stage
-    CUtensorMap tmap;
-    SCADE_TRY(tc::encode_rows_tmap(&tmap, net.packed_f16, (size_t)plan.stages_per_pass * tc::STAGE_BYTES, tc::STAGE_N));
-    tc::StashArgs sa{};
-    if (save) {
-      sa.L = tc::train_layout(net.desc, a.P);
-      if (workspace == nullptr || ws_bytes < sa.L.total) {
-        set_error("mlp_forward (tc_f16, save_for_backward): workspace %zu < %llu bytes", ws_bytes, sa.L.total);
-        return SCADE_ERR_WORKSPACE;
-      }
-      if (reinterpret_cast<uintptr_t>(workspace) & 127) {
-        set_error("mlp_forward (tc_f16, save_for_backward): workspace must be 128-byte aligned");
-        return SCADE_ERR_INVALID_ARGUMENT;
-      }
-      sa.ws = reinterpret_cast<uint8_t*>(workspace);
+#endif
+  // the packed stream as a 2D byte tensor: rows of 128 B (one swizzled K-major row), 128 rows per 16 KB stage
+  CUtensorMap tmap;
+  SCADE_TRY(tc::encode_rows_tmap(&tmap, net.packed_f16, (size_t)plan.stages_per_pass * tc::STAGE_BYTES, tc::STAGE_N));
+  tc::StashArgs sa{};
+  if (save) {
+    sa.L = tc::train_layout(net.desc, a.P);
+    if (workspace == nullptr || ws_bytes < sa.L.total) {
+      set_error("mlp_forward (tc_f16, save_for_backward): workspace %zu < %llu bytes", ws_bytes, sa.L.total);
+      return SCADE_ERR_WORKSPACE;
     }
-    const int64_t n_steps = (a.n_pairs + 1) / 2;
-    const int clusters = (int)std::min<int64_t>(n_steps, num_sms() / 2);
-    void* args[] = {&a, &plan, &tmap, &sa};
-    SCADE_TRY(tc::launch_pair(save ? (const void*)tc::nerf_mlp_tc_pp_kernel<true> : (const void*)tc::nerf_mlp_tc_pp_kernel<false>,
-                              clusters, tc::PP_THREADS, tc::SMEM_BYTES, st, args));
-  } else if (pair) {
-    const int64_t n_steps = (a.n_pairs + 1) / 2;
-    const int clusters = (int)std::min<int64_t>(n_steps, num_sms() / 2);
-    void* args[] = {&a, &plan};
-    SCADE_TRY(tc::launch_pair((const void*)kern, clusters, tc::THREADS, tc::SMEM_BYTES, st, args));
-  } else {
-    int grid = (int)std::min<int64_t>(a.n_pairs, num_sms());
-    kern<<<grid, tc::THREADS, tc::SMEM_BYTES, st>>>(a, plan);
+    if (reinterpret_cast<uintptr_t>(workspace) & 127) {
+      set_error("mlp_forward (tc_f16, save_for_backward): workspace must be 128-byte aligned");
+      return SCADE_ERR_INVALID_ARGUMENT;
+    }
+    sa.ws = reinterpret_cast<uint8_t*>(workspace);
   }
+  const int64_t n_steps = (a.n_pairs + 1) / 2;
+  const int clusters = (int)std::min<int64_t>(n_steps, num_sms() / 2);
+  void* args[] = {&a, &plan, &tmap, &sa};
+  SCADE_TRY(tc::launch_pair(save ? (const void*)tc::nerf_mlp_tc_pp_kernel<true> : (const void*)tc::nerf_mlp_tc_pp_kernel<false>,
+                            clusters, tc::PP_THREADS, tc::FWD_SMEM_BYTES, st, args));
   SCADE_LAUNCH_CHECK();
   return SCADE_OK;
 }
@@ -1299,10 +1086,6 @@ int mlp_tc_forward(const scade_net& net, const float* rays, int ray_stride, cons
 // Backward of a forward call that stashed (save_for_backward = 1): gradients of all parameter tensors, accumulated.
 int mlp_tc_backward(const scade_net& net, const float* d_out, int64_t P, float* const* grads, void* workspace, size_t ws_bytes,
                     cudaStream_t st) {
-  if (!tc::use_pair()) {
-    set_error("SCADE_PREC_TC_F16 training needs the SM-pair kernels (unset SCADE_TC_PAIR)");
-    return SCADE_ERR_UNSUPPORTED;
-  }
   const scade_net_desc& d = net.desc;
   NetDims nd(d);
   const tc::TrainLayout L = tc::train_layout(d, P);
@@ -1338,7 +1121,7 @@ int mlp_tc_backward(const scade_net& net, const float* d_out, int64_t P, float* 
     SCADE_TRY(tc::encode_rows_tmap(&tmap, packed + bwd_off, (size_t)plan.stages_per_pass * tc::STAGE_BYTES, tc::STAGE_N));
     tc::BwdArgs a{};
     a.packed = packed;
-    a.tail_off = (unsigned long long)tc::count_stages(d, true) * tc::STAGE_BYTES;
+    a.tail_off = (unsigned long long)tc::count_stages(d) * tc::STAGE_BYTES;
     a.ws = ws; a.L = L;
     a.d_out = reinterpret_cast<const float4*>(d_out);
     a.P = P; a.n_pairs = n_pairs;

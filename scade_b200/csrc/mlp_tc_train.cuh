@@ -95,9 +95,9 @@ __global__ void __launch_bounds__(PP_THREADS, 1) nerf_mlp_tc_dgrad_kernel(const 
     if (lane == 0) pp_weight_producer(plan, &tmap, sbase, bar_full, bar_empty, cta_rank, unit0, n_steps, n_units);
   } else if (warp == 1) {
     if (cta_rank == 0) pp_mma_issuer(plan, sbase, tmem_base, bar_full, bar_empty, bar_acc, bar_aready, unit0, n_steps, n_units);
-  } else if (warp >= 4) {
+  } else if (warp >= PP_EPI_WARP0) {
     // ================= prologue / epilogue warps: thread == one row x 128 columns =================
-    const int ew = warp - 4;
+    const int ew = warp - PP_EPI_WARP0;
     const int tile = ew >> 3;
     const int quarter = warp & 3;
     const int half = (ew >> 2) & 1;

@@ -87,11 +87,12 @@ for w, name in [(4, "tile0 half0"), (8, "tile0 half1"), (12, "tile1 half0"), (16
     for g, c in zip(tag, clk):
         kind, l = g >> 8, g & 0xFF
         if g == 0x400:
-            p0 = c; st += 1
+            p0 = c
         elif g == 0x401:
-            if st > 1: pro.append(c - p0)
+            pro.append(c - p0)
             last = c
         elif kind == 5:
+            if l == 0: st += 1
             if st > 1: acc_wait[l] += c - last; n[l] += 1
             acc_t[l] = c
         elif kind == 6:
