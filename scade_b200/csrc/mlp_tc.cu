@@ -329,7 +329,7 @@ __device__ __forceinline__ void pp_mma_issuer(const NetPlan& plan, uint32_t sbas
 // the 128 alpha_linear weights at `srow` (H:233).  kMask: sign masks of the pre-activations for the training stash.
 // Branch-free inside; the caller dispatches on the layer's flags.
 template <bool kBias, bool kRelu, bool kAlpha, bool kMask>
-__device__ __forceinline__ float hidden_epilogue(uint32_t t_col, uint8_t* dst, uint32_t rx4, const float* srow, const float* walpha,
+__device__ __forceinline__ float hidden_epilogue(uint32_t t_col, uint8_t* dst, uint32_t rx4, const float* srow, float4 wa,
                                                  uint32_t* sgn) {
   uint32_t rb[2][32];
   float al0 = 0.f, al1 = 0.f, al2 = 0.f, al3 = 0.f;
@@ -337,11 +337,6 @@ __device__ __forceinline__ float hidden_epilogue(uint32_t t_col, uint8_t* dst, u
 #pragma unroll
   for (int c4 = 0; c4 < 4; ++c4) {
     uint32_t* r = rb[c4 & 1];
-    float4 w[4];
-    if (kAlpha) {                                          // global (L1-resident, warp-uniform) loads issued ahead of the TMEM wait
-#pragma unroll
-      for (int i = 0; i < 4; ++i) w[i] = __ldg(reinterpret_cast<const float4*>(walpha + c4 * 32) + i);
-    }
     tmem_ld_wait();
     if (c4 + 1 < 4) tmem_ld32(t_col + (c4 + 1) * 32, rb[(c4 + 1) & 1]);
 #pragma unroll
@@ -354,8 +349,16 @@ __device__ __forceinline__ float hidden_epilogue(uint32_t t_col, uint8_t* dst, u
         for (int i = 0; i < 16; ++i) r[g * 16 + i] = __float_as_uint(__uint_as_float(r[g * 16 + i]) + v[i]);
       }
       if (kAlpha) {
-        const float v[16] = {w[0].x, w[0].y, w[0].z, w[0].w, w[1].x, w[1].y, w[1].z, w[1].w,
-                             w[2].x, w[2].y, w[2].z, w[2].w, w[3].x, w[3].y, w[3].z, w[3].w};
+        // lane j of the warp holds the alpha_linear weights of columns 4j..4j+3 (wa): 16 shuffles fetch this group's 16
+        float v[16];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int src = c4 * 8 + g * 4 + j;
+          v[4 * j + 0] = __shfl_sync(0xffffffffu, wa.x, src);
+          v[4 * j + 1] = __shfl_sync(0xffffffffu, wa.y, src);
+          v[4 * j + 2] = __shfl_sync(0xffffffffu, wa.z, src);
+          v[4 * j + 3] = __shfl_sync(0xffffffffu, wa.w, src);
+        }
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
           const float hx = fmaxf(__uint_as_float(r[g * 16 + i]), 0.f);
@@ -363,10 +366,6 @@ __device__ __forceinline__ float hidden_epilogue(uint32_t t_col, uint8_t* dst, u
           else if ((i & 3) == 1) al1 = fmaf(hx, v[i], al1);
           else if ((i & 3) == 2) al2 = fmaf(hx, v[i], al2);
           else al3 = fmaf(hx, v[i], al3);
-        }
-        if (g == 0) {
-#pragma unroll
-          for (int i = 0; i < 4; ++i) w[i] = __ldg(reinterpret_cast<const float4*>(walpha + c4 * 32 + 16) + i);
         }
       }
     }
@@ -570,7 +569,9 @@ __global__ void __launch_bounds__(PP_THREADS, 1) nerf_mlp_tc_pp_kernel(const __g
         if (kind != 3) {
           // fetched while the layer's MMAs run: this thread's element of the bias row that goes through shared memory
           float s_mine = 0.f;
+          float4 wa = make_float4(0.f, 0.f, 0.f, 0.f);
           if (bias_epi) s_mine = __ldg(tail->bias[l] + tid_tile);
+          if (kind == 1) wa = __ldg(reinterpret_cast<const float4*>(tail->w_alpha + half * 128) + lane);
           mbar_wait(my_acc, acc_phase);
           acc_phase ^= 1;
           tc_fence_after();
@@ -601,13 +602,12 @@ __global__ void __launch_bounds__(PP_THREADS, 1) nerf_mlp_tc_pp_kernel(const __g
           }
           uint8_t* dst = a_tile + 2 * half * CHUNK_BYTES + row_off;
           const float* srow = sbias + half * 128;
-          const float* walpha = tail->w_alpha + half * 128;
           if (kind == 1) {
-            if (bias_epi) alpha = hidden_epilogue<true, true, true, kStash>(t_col, dst, rx4, srow, walpha, sgn);
-            else alpha = hidden_epilogue<false, true, true, kStash>(t_col, dst, rx4, srow, walpha, sgn);
-          } else if (kind == 2) hidden_epilogue<true, false, false, false>(t_col, dst, rx4, srow, walpha, sgn);
-          else if (bias_epi) hidden_epilogue<true, true, false, kStash>(t_col, dst, rx4, srow, walpha, sgn);
-          else hidden_epilogue<false, true, false, kStash>(t_col, dst, rx4, srow, walpha, sgn);
+            if (bias_epi) alpha = hidden_epilogue<true, true, true, kStash>(t_col, dst, rx4, srow, wa, sgn);
+            else alpha = hidden_epilogue<false, true, true, kStash>(t_col, dst, rx4, srow, wa, sgn);
+          } else if (kind == 2) hidden_epilogue<true, false, false, false>(t_col, dst, rx4, srow, wa, sgn);
+          else if (bias_epi) hidden_epilogue<true, true, false, kStash>(t_col, dst, rx4, srow, wa, sgn);
+          else hidden_epilogue<false, true, false, kStash>(t_col, dst, rx4, srow, wa, sgn);
           TRACE(tr, 0x600 + l);                          // operand chunks written
           signal_a_ready();
           TRACE(tr, 0x700 + l);                          // signalled
@@ -652,6 +652,19 @@ __global__ void __launch_bounds__(PP_THREADS, 1) nerf_mlp_tc_pp_kernel(const __g
             continue;
           }
 #endif
+          // 1. this thread's 64 accumulator columns -> registers; the tile's TMEM and encoding chunk are then free, so the
+          //    next step's layer 0 is released BEFORE the rgb arithmetic (which then runs under that layer's MMAs)
+          uint32_t rr[2][32];
+          tmem_ld32(t_lane + half * 64, rr[0]);
+          tmem_ld32(t_lane + half * 64 + 32, rr[1]);
+          tmem_ld_wait();
+          tc_fence_before();
+          if (has_next) {
+            store_emb(pk, vd);
+            signal_a_ready();
+          }
+          TRACE(tr, 0x600 + l);
+          // 2. rgb_linear weights -> shared memory (chunk 3 is dead: this layer's MMAs have retired)
           float cr[2] = {0.f, 0.f}, cg[2] = {0.f, 0.f}, cb[2] = {0.f, 0.f};
           uint32_t sgn[2];
           uint8_t* hv_chunk = a_tile + 2 * half * CHUNK_BYTES;      // stash staging of this half's 64 h_v columns (own chunk)
@@ -671,9 +684,7 @@ __global__ void __launch_bounds__(PP_THREADS, 1) nerf_mlp_tc_pp_kernel(const __g
           const float4* wb4 = reinterpret_cast<const float4*>(srgb + 256 + half * 64);
 #pragma unroll
           for (int c2 = 0; c2 < 2; ++c2) {
-            uint32_t r[32];
-            tmem_ld32(t_lane + half * 64 + c2 * 32, r);
-            tmem_ld_wait();
+            const uint32_t* r = rr[c2];
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
               const float4 wr = wr4[c2 * 8 + q], wg = wg4[c2 * 8 + q], wb = wb4[c2 * 8 + q];
@@ -697,24 +708,15 @@ __global__ void __launch_bounds__(PP_THREADS, 1) nerf_mlp_tc_pp_kernel(const __g
               }
             }
           }
-          // accumulators are in registers: the next step's layer 0 may overwrite them.  Half 1 publishes its partial sums,
-          // half 0 picks them up BEFORE either signals (the scratch rows are overwritten by the next step's layer-0 epilogue).
-          tc_fence_before();
+          // 3. half 1 hands its partial sums (and its share of alpha) to half 0
           const float pr = cr[0] + cr[1], pg = cg[0] + cg[1], pb = cb[0] + cb[1];
-          float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
           if (half == 1) {
             *scratch = make_float4(pr, pg, pb, alpha);
             __threadfence_block();
             named_bar_arrive(pair_bar, 64);
-          }
-          if (has_next) store_emb(pk, vd);
-          if (half == 0) {
+          } else {
             named_bar_sync(pair_bar, 64);
-            o = *scratch;
-          }
-          if (has_next) signal_a_ready();
-          TRACE(tr, 0x600 + l);
-          if (half == 0) {
+            const float4 o = *scratch;
             const float al = (alpha + o.w) + __ldg(&tail->b_alpha);
             if (live) {
               a.out[p_raw] = make_float4((pr + o.x) + __ldg(&tail->b_rgb[0]), (pg + o.y) + __ldg(&tail->b_rgb[1]),
@@ -724,13 +726,16 @@ __global__ void __launch_bounds__(PP_THREADS, 1) nerf_mlp_tc_pp_kernel(const __g
           }
           if (kStash) {
             *reinterpret_cast<uint2*>(sa.ws + sa.L.maskv + (size_t)(tile_g * TILE_M + row) * 16 + half * 8) = make_uint2(sgn[0], sgn[1]);
-            if (!has_next) fence_proxy_async();            // (signal_a_ready already fenced the generic-proxy writes otherwise)
+            fence_proxy_async();                           // the h_v staging rows were written through the generic proxy
             __syncwarp();
             if (lane == 0) {
               bulk_s2g(sa.ws + sa.L.hv + (size_t)(tile_g * 2 + half) * CHUNK_BYTES + quarter * 4096, smem_u32(hv_chunk) + quarter * 4096, 4096);
               bulk_commit();
             }
           }
+          // 4. every warp of the tile is done with the staged weights / scratch rows before the next step's layer-0 epilogue
+          //    (which overwrites chunk 3) can begin
+          named_bar_sync(tile_bar, 256);
           TRACE(tr, 0x700 + l);                          // views epilogue done
         }
       }
