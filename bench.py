@@ -272,7 +272,7 @@ def run_gpu(args):
                     "api": "scade_b200.render.render_rays (pinned host ray batch in, rgb/disp/acc/depth maps out)"},
             "gpu_launches": int(launches),
             "wall_ms_timed_region": wall * 1e3,
-            "roofline": {"bound": "tensor", "kernel": "nerf_mlp_tc_kernel (fine pass, 4096x256 points)" if is_tc
+            "roofline": {"bound": "tensor", "kernel": "nerf_mlp_tc_pp_kernel (fine pass, 4096x256 points)" if is_tc
                          else "sgemm_kernel chain (fine pass)",
                          "achieved": achieved, "peak": burst, "unit": "TFLOP/s", "frac": achieved / burst,
                          "peak_source": f"{src} bf16 dense burst (kernel timed alone)", "traffic": traffic,
