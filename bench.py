@@ -381,6 +381,103 @@ def run_train(args):
         dist.destroy_process_group()
 
 
+def run_image(args):
+    """BASELINE configs 4 / 5: full 640x480 frames (64 coarse + 128 importance -> 192 fine samples per ray), pixels sharded
+    across the ranks (strong scaling: the frame is fixed), rays generated on the device from the pixel index, one all_gather of
+    the finished maps per frame.  `--workload video` additionally builds the three-panel uint8 video frame on the device
+    (scade_video_frame) and reads it back to pinned host memory every frame (what render_video RS:236-260 writes to disk),
+    and reports PSNR of the tensor-core frames against the fp32-arithmetic path (the reference's arithmetic) on a few frames."""
+    import torch
+    import torch.distributed as dist
+    from scade_b200 import _lib, nerf_helpers as NH, postprocess as PP, render as R_, synthetic as syn
+    from scade_b200.dist import render_image_sharded
+    from tests.golden.generate_goldens import net_pair
+    rank, world, local = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+    H, W, Nc, Nf = 480, 640, 64, 128
+    video = args.workload == "video"
+    bb_center, bb_scale = syn.bounding_box()
+    pc, pf = net_pair(NET_D, NET_W)
+
+    def make_kwargs(prec):
+        nets = []
+        for p in (pc, pf):
+            net = NH.NeRF(D=NET_D, W=NET_W, input_ch=57, input_ch_views=3, output_ch=5, skips=[4], use_viewdirs=True, precision=prec)
+            net.load_state_dict({k: torch.from_numpy(v) for k, v in p.items()})
+            nets.append(net.to(dev).requires_grad_(False))
+        qf = R_.NetworkQuery(NH.get_embedder(9, 0)[0], NH.get_embedder(0, 0)[0], bb_center, bb_scale, precision=prec)
+        return dict(network_fn=nets[0], network_query_fn=qf, N_samples=Nc, embedded_cam=torch.tensor((), device=dev), retraw=False,
+                    perturb=0.0, N_importance=Nf, network_fine=nets[1], raw_noise_std=0.0)
+    kw = make_kwargs(args.precision)
+    poses = [torch.from_numpy(p) for p in syn.spiral_poses(120)]
+    keys = ("rgb_map", "depth_map", "acc_map", "z_vals", "weights") if video else ("rgb_map", "depth_map", "acc_map")
+    frame_host = torch.empty((H, 3 * W, 3), dtype=torch.uint8).pin_memory() if video else None
+    rgb_host = torch.empty((H, W, 3), dtype=torch.float32).pin_memory()
+    chunk = 32768                                        # rays per render_rays call (the reference's eval chunk is 16384, RS:347)
+
+    def frame(i, kwargs=kw):
+        out = render_image_sharded(H, W, syn.CAM_INTRINSIC, poses[i % len(poses)], 0.1, 5.0, kwargs, chunk=chunk, keys=keys)
+        out = {k: v.reshape((H, W) + ((v.shape[-1],) if k in ("rgb_map", "z_vals", "weights") else ())) for k, v in out.items()}
+        if rank == 0:
+            if video:
+                fr = PP.video_frame(out["rgb_map"], out["depth_map"], out["z_vals"], out["weights"], depth_scale=5.0)
+                frame_host.copy_(fr["frame"], non_blocking=True)
+            else:
+                rgb_host.copy_(out["rgb_map"], non_blocking=True)
+        return out
+    for i in range(max(args.warmup, 3)):
+        frame(i)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    l0 = lib.scade_kernel_launch_count()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for i in range(args.steps):
+        frame(i)
+    e.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = torch.tensor([s.elapsed_time(e)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    psnr = None
+    if video and args.precision == "tc_f16":
+        kw32 = make_kwargs("fp32")
+        vals = []
+        for i in (0, 40, 80):
+            a = frame(i)["rgb_map"]
+            b = frame(i, kw32)["rgb_map"]
+            vals.append(float(-10.0 * torch.log10(torch.mean((a - b) ** 2))))
+        psnr = vals
+    if rank == 0:
+        sec = float(ms) * 1e-3 / args.steps
+        burst, sustained, _, src = load_peaks()
+        flop_frame = H * W * (Nc + Nc + Nf) * FLOP_PER_EVAL
+        line = {"metric": "rays/sec, full 640x480 frames (64c+128f -> 192 samples/ray), pixels sharded across GPUs",
+                "value": H * W / sec, "unit": "rays/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+                "ms_per_step": sec * 1e3, "frames_per_s": 1.0 / sec, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "f16 operands / f32 accumulate (tcgen05)" if args.precision == "tc_f16" else "f32", "data": "synthetic",
+                "config": {"workload": "BASELINE config 5 (spiral video frames incl. device post-processing + frame read-back)" if video
+                           else "BASELINE config 4 (full image render, maps gathered on every rank, rgb read back)",
+                           "H": H, "W": W, "samples": f"{Nc}c+{Nf}f", "chunk": chunk, "parallelism": f"pixels x{world}",
+                           "poses": "120-pose synthetic spiral (synthetic.spiral_poses)"},
+                "gpu_launches": int(lib.scade_kernel_launch_count() - l0),
+                "roofline": {"bound": "tensor", "achieved": flop_frame / sec / 1e12 / world, "peak": sustained, "unit": "TFLOP/s per GPU",
+                             "frac": flop_frame / sec / 1e12 / world / sustained, "peak_source": f"{src} bf16 sustained", "traffic": None}}
+        if psnr is not None:
+            line["psnr_vs_fp32_path_db"] = psnr
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -391,13 +488,16 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--optimizer", default="fused", choices=["fused", "torch"],
                     help="train workload: fused = flat parameters + scade_adam_step (default); torch = torch.optim.Adam on 48 tensors")
-    ap.add_argument("--workload", default="render", choices=["render", "train"],
-                    help="render = BASELINE metric (default); train = config 3 (4096 rays, 64c+128f, K=20, fwd+loss+bwd+allreduce+Adam)")
+    ap.add_argument("--workload", default="render", choices=["render", "train", "image", "video"],
+                    help="render = BASELINE metric (default); train = config 3 (4096 rays, 64c+128f, K=20, fwd+loss+bwd+allreduce+Adam); "
+                         "image / video = configs 4 / 5 (full 640x480 frames, pixels sharded across the GPUs)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
     elif args.workload == "train":
         run_train(args)
+    elif args.workload in ("image", "video"):
+        run_image(args)
     else:
         run_gpu(args)
 

@@ -76,6 +76,8 @@ struct LayerDesc {
   int n_out;              // output width (256, or 128 for the views layer)
   int a_step;             // issuer: K chunk i (after the encoding chunk) reads activation chunk a_step * i
   int kpack;              // K chunks per ring stage (2 when a CTA's N half is only 64 rows: views layer)
+  int emb_ks0;            // first K=16 step of the encoding chunk this layer needs (views layer: 3 -- only the view direction and
+                          // the 1.0 columns, K positions 48..63, have non-zero weights)
   int bias_stage;         // 1: one extra ring stage carries the bias as a K=16 MMA step against the encoding chunk's 1.0 columns
                           //    (last hidden layer: its shared-memory row is taken by the alpha_linear weights)
 };
@@ -247,6 +249,7 @@ __device__ __forceinline__ void pp_mma_issuer(const NetPlan& plan, uint32_t sbas
       const int n_own = n_kst + plan.layers[l].bias_stage;     // this layer's stages per CTA (<= 5)
       const int has_emb = plan.layers[l].a_src[0] == SRC_EMB;
       const int a_step = plan.layers[l].a_step;                // A chunk of K chunk i (after the encoding chunk) = a_step * i
+      const int emb_ks0 = plan.layers[l].emb_ks0;
       const uint32_t idesc = make_idesc(2 * TILE_M, plan.layers[l].n_out);
       // one (stage, tile): wait for the slot in both CTAs, issue its MMAs for super-tile t, optionally release it
       auto consume_at = [&](int t, uint32_t& slot_ref, uint32_t& ph_ref, int i, bool release) {
@@ -272,9 +275,10 @@ __device__ __forceinline__ void pp_mma_issuer(const NetPlan& plan, uint32_t sbas
                                         : sbase + OFF_A + (t * 4 + (kc - has_emb) * a_step) * CHUNK_BYTES;
             const uint64_t a_desc = desc_hi | (uint64_t)((a_addr & 0x3FFFF) >> 4);
             const uint64_t b_desc = desc_hi | (uint64_t)(((sbase + OFF_STAGE + sl * STAGE_BYTES + j * (STAGE_BYTES / 2)) & 0x3FFFF) >> 4);
+            const int ks0 = emb ? emb_ks0 : 0;                 // the layer's first MMA (K chunk 0, step ks0) overwrites the accumulator
 #pragma unroll
             for (int ks = 0; ks < KCHUNK / 16; ++ks)
-              mma_f16_ss_pair(d_addr, a_desc + 2 * ks, b_desc + 2 * ks, idesc, (kc | ks) != 0 ? 1u : 0u);
+              if (ks >= ks0) mma_f16_ss_pair(d_addr, a_desc + 2 * ks, b_desc + 2 * ks, idesc, (kc != 0 || ks != ks0) ? 1u : 0u);
           }
           if (release) mma_commit_pair(bar_empty + 8 * sl, (uint16_t)3);
         }
@@ -835,6 +839,7 @@ static void build_plans(const scade_net& net, NetPlan* np, PackPlan* pp) {
     L.n_k = nk;
     const int rows = n_out / 2;                                // N rows per CTA
     L.kpack = STAGE_N / rows;                                  // 1 (N = 256) or 2 (N = 128)
+    L.emb_ks0 = with_emb ? emb_dst / 16 : 0;                   // K steps below the first mapped column hold only zero weights
     const int n_own = (nk + L.kpack - 1) / L.kpack;
     for (int i = 0; i < n_own; ++i)
       for (int h = 0; h < 2; ++h) {
@@ -902,7 +907,7 @@ static void build_bwd_plans(const scade_net& net, NetPlan* np, PackPlan* pp) {
   auto add_layer = [&](const float* Wt, int ld, int n_out_fwd, int col0, int a_step) {
     LayerDesc L{};
     P.first_stage[P.n_layers] = Q.n_stages;
-    L.relu = 0; L.kind = 0; L.n_out = W; L.a_step = a_step; L.bias_epi = 0; L.kpack = 1; L.bias_stage = 0;
+    L.relu = 0; L.kind = 0; L.n_out = W; L.a_step = a_step; L.bias_epi = 0; L.kpack = 1; L.bias_stage = 0; L.emb_ks0 = 0;
     L.n_k = n_out_fwd / KCHUNK;
     for (int kc = 0; kc < L.n_k; ++kc) {
       L.a_src[kc] = kc * a_step;
