@@ -158,3 +158,17 @@ class FusedAdam(torch.optim.Optimizer):
                                         st["step"], stream_ptr()), "scade_adam_step")
         F_.mark_weights_changed()
         return loss
+
+
+def update_learning_rate(optimizer, learning_rate):
+    """train_utils/hyperparameter_update.py:3-5 (RS:990): every param group takes the new rate; FusedAdam reads it at step()."""
+    for group in optimizer.param_groups:
+        group["lr"] = learning_rate
+
+
+def get_learning_rate(init_learning_rate, iteration_num, decay_step, decay_rate, staircase=True):
+    """train_utils/hyperparameter_update.py:9-15 (RS:988): init * decay_rate ** (iteration / decay_step), floored when `staircase`."""
+    p = iteration_num / decay_step
+    if staircase:
+        p = int(p // 1)
+    return init_learning_rate * (decay_rate ** p)

@@ -74,3 +74,15 @@ def test_fused_adam_matches_torch_adam(use_flat):
     st0, ref0 = sd["state"][0], opt_ref.state_dict()["state"][0]
     assert int(st0["step"]) == 6 and st0["exp_avg"].shape == tuple(shapes[0])
     np.testing.assert_allclose(st0["exp_avg_sq"].cpu().numpy(), ref0["exp_avg_sq"].cpu().numpy(), rtol=1e-5, atol=1e-12)
+
+
+def test_learning_rate_schedule_matches_reference_formula():
+    """train_utils/hyperparameter_update.py:9-15: staircase decay, and update_learning_rate writes every param group."""
+    from scade_b200.optim import get_learning_rate, update_learning_rate
+    assert get_learning_rate(5e-4, 0, 400000, 0.1) == 5e-4
+    assert get_learning_rate(5e-4, 399999, 400000, 0.1) == 5e-4
+    assert abs(get_learning_rate(5e-4, 400000, 400000, 0.1) - 5e-5) < 1e-12
+    assert abs(get_learning_rate(5e-4, 200000, 400000, 0.1, staircase=False) - 5e-4 * 0.1 ** 0.5) < 1e-12
+    opt = torch.optim.SGD([torch.nn.Parameter(torch.zeros(1))], lr=1.0)
+    update_learning_rate(opt, 0.25)
+    assert all(g["lr"] == 0.25 for g in opt.param_groups)
