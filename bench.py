@@ -374,8 +374,10 @@ def run_train(args):
                        else "fp32 FFMA GEMMs (fwd+bwd)",
                        "collective": "1 NCCL all-reduce / step, flat fp32 buffer 4.72 MB", "optimizer": args.optimizer},
             "gpu_launches": int(lib.scade_kernel_launch_count() - l0), "loss": float(losses["loss"]),
-            "roofline": {"bound": "tensor", "achieved": flop_step / sec / 1e12, "peak": sustained, "unit": "TFLOP/s",
-                         "frac": flop_step / sec / 1e12 / sustained, "peak_source": f"{src} bf16 sustained", "traffic": None}}), flush=True)
+            "roofline": {"bound": "tensor", "achieved": flop_step / sec / 1e12 / world, "peak": sustained, "unit": "TFLOP/s per GPU",
+                         "frac": flop_step / sec / 1e12 / world / sustained, "peak_source": f"{src} bf16 sustained", "traffic": None,
+                         "note": "the dominant training kernels are HBM-bound (10 KB/point activation stash): wgrad runs at 99% of the "
+                                 "measured HBM bandwidth (profiles/r01_v15_train_launches.csv, DESIGN.md 3.1b)"}}), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
