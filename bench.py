@@ -187,7 +187,7 @@ def run_gpu(args):
     out_host = {k: torch.empty(s, dtype=torch.float32).pin_memory()
                 for k, s in {"rgb_map": (N_RAYS, 3), "disp_map": (N_RAYS,), "acc_map": (N_RAYS,), "depth_map": (N_RAYS,)}.items()}
 
-    def step_e2e():
+    def step_e2e_eager():
         rb = rb_host.to(dev, non_blocking=True)
         with torch.no_grad():
             ret = R_.render_rays(rb, True, **kwargs)
@@ -195,10 +195,19 @@ def run_gpu(args):
             buf.copy_(ret[k], non_blocking=True)
         return ret
 
+    # public API: render_rays for a fixed chunk size as one CUDA graph that starts with the host->device copy of the pinned ray
+    # batch and ends with the device->host copies of the image maps
+    graphed = R_.GraphedRenderRays(N_RAYS, host_outputs=tuple(out_host), **kwargs)
+    graphed.rays_host.copy_(rb_host)
+
+    def step_e2e():
+        return graphed()
+
     # ---- warm-up ----
     for _ in range(max(args.warmup, 3)):
         step_resident()
         step_e2e()
+        step_e2e_eager()
     sync_all()
 
     sampler = ClockSampler(local)
@@ -228,6 +237,12 @@ def run_gpu(args):
         torch.cuda.current_stream().synchronize()      # the result is on the host when the step ends
     sync_all()
     e2e_sec = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_e2e_eager()
+        torch.cuda.current_stream().synchronize()
+    sync_all()
+    e2e_eager_sec = time.perf_counter() - t0
 
     # ---- dominant kernel alone: fine-pass MLP launch (4096 x 256 points) ----
     z_f = step_resident()["z_vals"]
@@ -269,7 +284,11 @@ def run_gpu(args):
                        "weights": "Xavier-uniform random init (synthetic.make_nerf_params)"},
             "e2e": {"value": total_rays / (e2e_ms * 1e-3), "unit": "rays/s", "h2d_bytes_per_step": int(rb_host.numel() * 4),
                     "d2h_bytes_per_step": int(sum(b.numel() * 4 for b in out_host.values())),
-                    "api": "scade_b200.render.render_rays (pinned host ray batch in, rgb/disp/acc/depth maps out)"},
+                    "api": "scade_b200.render.GraphedRenderRays (render_rays for a fixed chunk size replayed as one CUDA graph that "
+                           "includes the H2D copy of the pinned host ray batch and the D2H copies of the rgb/disp/acc/depth maps; "
+                           "stream sync every step)",
+                    "eager_value": N_RAYS * world * args.steps / e2e_eager_sec,
+                    "eager_api": "scade_b200.render.render_rays called eagerly every step (same copies; rank-0 clock)"},
             "gpu_launches": int(launches),
             "wall_ms_timed_region": wall * 1e3,
             "roofline": {"bound": "tensor", "kernel": "nerf_mlp_tc_pp_kernel (fine pass, 4096x256 points)" if is_tc

@@ -186,6 +186,66 @@ def render_rays(ray_batch, use_viewdirs, network_fn, network_query_fn, N_samples
     return ret
 
 
+class GraphedRenderRays:
+    """render_rays (RS:581-751, eval configuration: no autograd, deterministic sampling or injected uniforms) for a FIXED ray
+    count, replayed as one CUDA graph: the 7 kernel launches of the pass, their output allocations and the host-side argument
+    marshalling happen once at construction.  For loops that render many equal-sized chunks (RS:347, batchify_rays).
+
+        g = GraphedRenderRays(n_rays, **render_kwargs_test)      # same kwargs as render_rays / create_nerf's dict
+        out = g(ray_batch)                                        # ray_batch [n_rays, 11]: CUDA tensor or (pinned) host tensor
+
+    `out` holds the graph's own output tensors (the reference's dict keys); the next call overwrites them.  The weights are read
+    through the packed fp16 stream: call `g.refresh()` (re-capture) after an optimizer step.
+    """
+
+    def __init__(self, n_rays, use_viewdirs=True, device=None, host_outputs=None, **kwargs):
+        """host_outputs: names of result tensors to be delivered in pinned host memory.  The graph then also contains the
+        host->device copy of `self.rays_host` (pinned, [n_rays, 11]) and the device->host copies into `self.out_host[name]`:
+        fill `rays_host`, call `g()`, synchronise the stream, read `out_host`."""
+        self.n_rays, self.use_viewdirs, self.kwargs = int(n_rays), use_viewdirs, dict(kwargs)
+        self.device = device or torch.device("cuda", torch.cuda.current_device())
+        self.rays = torch.zeros((self.n_rays, 11), dtype=torch.float32, device=self.device)
+        self.rays[:, 3:6] = 1.0
+        self.rays[:, 6], self.rays[:, 7] = 0.1, 1.0
+        self.host_outputs = tuple(host_outputs) if host_outputs else None
+        self.rays_host = self.rays.cpu().pin_memory() if self.host_outputs else None
+        self.out_host = None
+        self.graph, self.out = None, None
+        self.refresh()
+
+    def refresh(self):
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(side), torch.no_grad():
+            for _ in range(2):                               # warm-up outside the capture: packs weights, sets kernel attributes
+                ret = render_rays(self.rays, self.use_viewdirs, **self.kwargs)
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        torch.cuda.synchronize(self.device)
+        if self.host_outputs and self.out_host is None:
+            self.out_host = {k: torch.empty(ret[k].shape, dtype=ret[k].dtype).pin_memory() for k in self.host_outputs}
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph), torch.no_grad():
+            if self.host_outputs:
+                self.rays.copy_(self.rays_host, non_blocking=True)
+            self.out = render_rays(self.rays, self.use_viewdirs, **self.kwargs)
+            if self.host_outputs:
+                for k in self.host_outputs:
+                    self.out_host[k].copy_(self.out[k], non_blocking=True)
+
+    def __call__(self, ray_batch=None):
+        if ray_batch is not None:
+            if tuple(ray_batch.shape) != (self.n_rays, 11):
+                raise ValueError(f"GraphedRenderRays was captured for [{self.n_rays}, 11] ray batches, got {tuple(ray_batch.shape)}")
+            if self.host_outputs:
+                if ray_batch.is_cuda:
+                    raise ValueError("this GraphedRenderRays takes its rays from pinned host memory (rays_host)")
+                self.rays_host.copy_(ray_batch)
+            else:
+                self.rays.copy_(ray_batch, non_blocking=True)
+        self.graph.replay()
+        return self.out
+
+
 def batchify_rays(rays_flat, chunk=1024 * 32, use_viewdirs=False, **kwargs):
     """RS:66-78"""
     all_ret = {}

@@ -118,3 +118,30 @@ def test_cpu_input_and_bad_shapes_fail_loudly(dev):
     kwargs["N_importance"] = 0
     with pytest.raises(NotImplementedError):
         R_.render_rays(rb.to(dev), True, **kwargs)
+
+
+def test_graphed_render_rays_equals_eager(dev):
+    """GraphedRenderRays replays render_rays as one CUDA graph: same values as the eager call, for device and pinned-host inputs."""
+    from scade_b200 import render as R_
+    kwargs, _ = make_render_kwargs(8, 256, dev, "tc_f16", 0.0, 32, 48)
+    kwargs["retraw"] = False
+    g = R_.GraphedRenderRays(200, **kwargs)
+    for seed in (11, 12):
+        rb = syn.make_ray_batch(200, seed=seed)
+        with torch.no_grad():
+            ref = R_.render_rays(T(rb, dev), True, **kwargs)
+        out = g(torch.from_numpy(rb).pin_memory() if seed == 12 else T(rb, dev))
+        torch.cuda.synchronize()
+        for k in ref:
+            np.testing.assert_array_equal(npy(out[k]), npy(ref[k]), err_msg=k)
+    with pytest.raises(ValueError):
+        g(T(syn.make_ray_batch(10, seed=1), dev))
+    # host-I/O form: the graph contains the H2D copy of rays_host and the D2H copies of the requested maps
+    gh = R_.GraphedRenderRays(200, host_outputs=("rgb_map", "depth_map"), **kwargs)
+    rb = syn.make_ray_batch(200, seed=13)
+    gh(torch.from_numpy(rb))
+    torch.cuda.synchronize()
+    with torch.no_grad():
+        ref = R_.render_rays(T(rb, dev), True, **kwargs)
+    np.testing.assert_array_equal(gh.out_host["rgb_map"].numpy(), npy(ref["rgb_map"]))
+    np.testing.assert_array_equal(gh.out_host["depth_map"].numpy(), npy(ref["depth_map"]))
