@@ -21,13 +21,15 @@ from scade_b200 import _lib, functional as F_, nerf_helpers as NH, synthetic as 
 CAP = 8192
 dev = torch.device("cuda:0")
 n_rays = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
+stash = len(sys.argv) > 2 and sys.argv[2] == "stash"       # trace the training forward (kStash) instead
+S = 192 if stash else 256
 pf = syn.make_nerf_params(seed=11, bias_scale=0.05, alpha_bias=0.5, weight_gain=1.3)
 net = NH.NeRF(D=8, W=256, input_ch=57, input_ch_views=3, output_ch=5, skips=[4], use_viewdirs=True, precision="tc_f16")
 net.load_state_dict({k: torch.from_numpy(v) for k, v in pf.items()})
 net = net.to(dev).requires_grad_(False)
 bb_center, bb_scale = syn.bounding_box()
 rb = torch.from_numpy(syn.make_ray_batch(n_rays, seed=50)).to(dev)
-z = torch.sort(torch.rand(n_rays, 256, device=dev) * 4.9 + 0.1, -1).values
+z = torch.sort(torch.rand(n_rays, S, device=dev) * 4.9 + 0.1, -1).values
 lib = _lib.load()
 buf = torch.zeros(32 * CAP, dtype=torch.int64, device=dev)
 lib.scade_debug_tc_trace.argtypes = [ctypes.c_void_p]
@@ -38,7 +40,17 @@ with torch.no_grad():
             assert lib.scade_debug_tc_trace(ctypes.c_void_p(buf.data_ptr())) == 0
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record()
-        raw = F_.mlp_forward_rays(net.handle(), rb, z, bb_center, bb_scale, "tc_f16")
+        if stash:
+            h = net.handle()
+            if i == 0:
+                ws = torch.empty(h.workspace_bytes(n_rays * S, _lib.PREC_TC_F16, 1), dtype=torch.uint8, device=dev)
+                raw = torch.empty((n_rays, S, 4), device=dev)
+                cnet = h.struct(_lib.PREC_TC_F16)
+            _lib.check(lib.scade_mlp_forward_rays(ctypes.byref(cnet), _lib.PREC_TC_F16, _lib.ptr(rb), 11, _lib.ptr(z), n_rays, S,
+                                                  _lib.host_floats(bb_center), float(bb_scale), _lib.ptr(raw), _lib.ptr(ws), ws.numel(), 1,
+                                                  _lib.stream_ptr()), "fwd")
+        else:
+            raw = F_.mlp_forward_rays(net.handle(), rb, z, bb_center, bb_scale, "tc_f16")
         e.record()
         torch.cuda.synchronize()
         print(f"launch {i}: {s.elapsed_time(e):.3f} ms")
