@@ -440,8 +440,11 @@ def run_image(args):
     rgb_host = torch.empty((H, W, 3), dtype=torch.float32).pin_memory()
     chunk = 32768                                        # rays per render_rays call (the reference's eval chunk is 16384, RS:347)
 
+    graphs = {}                                          # chunk size -> GraphedRenderRays, kept across frames (weights are static)
+
     def frame(i, kwargs=kw):
-        out = render_image_sharded(H, W, syn.CAM_INTRINSIC, poses[i % len(poses)], 0.1, 5.0, kwargs, chunk=chunk, keys=keys)
+        out = render_image_sharded(H, W, syn.CAM_INTRINSIC, poses[i % len(poses)], 0.1, 5.0, kwargs, chunk=chunk, keys=keys,
+                                   graph_cache=graphs if kwargs is kw else None)
         out = {k: v.reshape((H, W) + ((v.shape[-1],) if k in ("rgb_map", "z_vals", "weights") else ())) for k, v in out.items()}
         if rank == 0:
             if video:

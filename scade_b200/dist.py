@@ -120,11 +120,33 @@ def F_img2mse(x, y, denominator):
     return F_.img2mse(x, y, denominator)
 
 
+def _batchify_graphed(rays, chunk, kw, keys, cache):
+    """batchify_rays (RS:66-78) with every full chunk replayed through a cached GraphedRenderRays (one CUDA graph per chunk size);
+    only `keys` are kept (the graph's output tensors are overwritten by the next replay, so they are copied out)."""
+    from . import render as R_
+    pieces = {k: [] for k in keys}
+    for i in range(0, rays.shape[0], chunk):
+        part = rays[i:i + chunk]
+        if part.shape[0] == chunk:
+            g = cache.get(chunk)
+            if g is None:
+                g = cache[chunk] = R_.GraphedRenderRays(chunk, True, device=rays.device, **kw)
+            ret = g(part)
+            for k in keys:
+                pieces[k].append(ret[k].clone())
+        else:
+            ret = R_.render_rays(part, True, **kw)
+            for k in keys:
+                pieces[k].append(ret[k])
+    return {k: (v[0] if len(v) == 1 else torch.cat(v, 0)) for k, v in pieces.items()}
+
+
 def render_image_sharded(H, W, intrinsic, c2w, near, far, render_kwargs, chunk=1024 * 16, keys=("rgb_map", "depth_map", "acc_map"),
-                         group=None, gather=True, device=None):
+                         group=None, gather=True, device=None, graph_cache=None):
     """Full-image render (RS:106-108,147) with the pixel list split across ranks.  Every rank builds the rays of its
     own pixel range on the device (no full-image get_rays + scatter), renders them in `chunk`-ray pieces and, if
-    `gather`, all ranks end with the [H,W,...] maps."""
+    `gather`, all ranks end with the [H,W,...] maps.  `graph_cache` (a dict the caller keeps across frames, eval only: the
+    weights must not change) replays full chunks as CUDA graphs."""
     from . import functional as F_
     from . import render as R_
     rank, world = _world(group)
@@ -134,7 +156,10 @@ def render_image_sharded(H, W, intrinsic, c2w, near, far, render_kwargs, chunk=1
     rays = F_.camera_ray_batch(H, W, intrinsic, c2w, near, far, pix0=lo, n=hi - lo, device=device)
     kw = {k: v for k, v in render_kwargs.items() if k not in ("near", "far", "ndc", "use_viewdirs")}
     with torch.no_grad():
-        ret = R_.batchify_rays(rays, chunk, True, **kw)
+        if graph_cache is not None:
+            ret = _batchify_graphed(rays, chunk, kw, keys, graph_cache)
+        else:
+            ret = R_.batchify_rays(rays, chunk, True, **kw)
     out = {}
     for k in keys:
         local = ret[k].reshape(hi - lo, -1)

@@ -76,7 +76,7 @@ ok &= dl < 1e-5 and worst < 2e-3     # fp32 summation order (atomics / split-K o
 # ---- (2) image render ----
 kw = make(8, 256, "tc_f16", False)
 c2w = torch.from_numpy(syn.spiral_poses(8)[3])
-out = render_image_sharded(60, 80, syn.CAM_INTRINSIC, c2w, 0.1, 5.0, kw, chunk=1000)
+out = render_image_sharded(60, 80, syn.CAM_INTRINSIC, c2w, 0.1, 5.0, kw, chunk=1000, graph_cache={})
 with torch.no_grad():
     rgb, disp, acc, extras = R_.render(60, 80, syn.CAM_INTRINSIC, chunk=4800, c2w=c2w, near=0.1, far=5.0, use_viewdirs=True,
                                        **{k: v for k, v in kw.items() if k != "use_viewdirs"})
