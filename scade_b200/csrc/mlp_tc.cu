@@ -4,31 +4,32 @@
 //   (model/run_nerf_helpers.py:142-172) -> NeRF.forward (H:223-247), i.e. 19 elementwise launches
 //   + 12 cuBLAS SGEMMs + cats per call, each round-tripping [P,256] fp32 activations through HBM.
 //
-// Design (B200, sm_100a)
-//   * CTA = 2 row tiles of 128 points (256 points per step), persistent over tile pairs.
-//   * Activations never leave the SM: fp16 A operand tiles live in shared memory in the canonical
-//     K-major SWIZZLE_128B layout (4 chunks of [128 x 64] per tile + one [128 x 64] "encoding chunk"
-//     holding gamma(x), the view direction and zero padding); accumulators live in TMEM
-//     (2 tiles x 256 fp32 columns = all 512 columns).
-//   * Weights are pre-packed (scade_mlp_pack_f16) into the exact shared-memory image of each
-//     [128 (N) x 64 (K)] fp16 stage, in consumption order, so the producer warp streams them with plain
-//     16 KB cp.async.bulk (TMA) copies through a 4-stage mbarrier ring.  Both row tiles consume every
-//     stage, halving L2->SMEM weight traffic per point.
-//   * warp 0: TMA producer; warp 1: TMEM allocator + single-thread tcgen05.mma issuer (warps 2-3 idle; the
-//     control warpgroup hands its registers over with setmaxnreg);
-//     warps 4..11: prologue/epilogue (thread == point row): positional encoding straight into the
-//     swizzled A tile, then per layer TMEM -> registers -> bias + ReLU -> fp16 -> swizzled A tile of the
-//     next layer.  alpha_linear (256->1) and rgb_linear (128->3) are fp32 dot products done in the
-//     epilogues on the un-rounded fp32 activations; softplus(beta=10) is applied before the single
-//     float4 store of (rgb_raw, sigma) per point -- the only HBM write of the kernel.
-//   * skip connection (H:230) and view concat (H:235) are extra K chunks that re-use the encoding chunk;
-//     nothing is concatenated in memory.
-//   * Biases ride on the tensor core: the encoding chunk carries two constant-1 columns (60, 61) and the packed
-//     weights carry fp16 hi/lo halves of the bias in the matching K positions (layers without an encoding K
-//     chunk get one extra K=16 MMA step per tile from a "bias stage"), so the epilogue is LDTM -> cvt.rn.relu.f16x2
-//     -> st.shared only.
-//   * CTAs run as clusters of 2: each CTA bulk-copies half of every weight stage and multicasts it to both, so
-//     L2->SMEM weight traffic per SM is halved again (the v1 kernel was L2-bound at ~6 TB/s during MMA phases).
+// Design (B200, sm_100a) -- nerf_mlp_tc_pp_kernel
+//   * Clusters of 2 CTAs on an SM pair, persistent over 512-point steps.  A step = 2 "super-tiles" of 256 points
+//     (row tile t of both CTAs); MMAs are tcgen05.mma.cta_group::2 with M = 256, N = 256 (128 for the views layer), K = 16.
+//   * Activations never leave the SM: fp16 A operand tiles live in shared memory in the canonical K-major SWIZZLE_128B
+//     layout (4 chunks of [128 x 64] per tile + one [128 x 64] "encoding chunk" holding gamma(x), the view direction, two
+//     constant-1 columns and zero padding); accumulators live in TMEM (2 tiles x 256 fp32 columns = all 512 columns).
+//   * Weights are pre-packed (scade_mlp_pack_f16) into the exact shared-memory image of each [128 (N) x 64 (K)] fp16 stage,
+//     in consumption order; each CTA streams only its own N half of every weight block, once per layer for both tiles,
+//     through a 4-slot mbarrier ring filled by 2D-tiled TMA whose completion lands on the leader CTA's barrier.
+//   * The two tiles ping-pong: while tile 1's MMAs of layer l run, tile 0's epilogue warps turn its layer-l accumulators into
+//     its layer-(l+1) operand, and vice versa.  Every wide layer is exactly 4 ring stages (no bias stages; the views layer
+//     packs two K chunks per stage), so the ring never blocks a tile on a slot the other tile still holds.
+//   * warp 0: TMA producer; warp 1: TMEM allocator + single-thread tcgen05.mma issuer (warps 2-3 idle; the control
+//     warpgroup hands its registers to the epilogue warpgroups with setmaxnreg); warps 4..19: prologue / epilogue
+//     (thread == one point row x 128 columns): positional encoding straight into the swizzled A tile, then per layer
+//     TMEM -> registers -> + fp32 bias (row broadcast from shared memory) -> ReLU -> fp16 -> swizzled A tile of the next layer.
+//   * Layers whose K includes the encoding chunk (layer 0, the skip layer, the views layer) get their bias from the tensor core:
+//     the packed weights carry fp16 hi/lo halves of the bias in the K positions of the chunk's two constant-1 columns.
+//   * alpha_linear (256->1) is fused into the last hidden layer's epilogue and rgb_linear (128->3) into the views epilogue, both
+//     as fp32 dot products on the un-rounded fp32 activations; softplus(beta=10) is applied before the single float4 store of
+//     (rgb_raw, sigma) per point -- the only HBM write of the kernel.
+//   * skip connection (H:230) and view concat (H:235) are extra K chunks that re-use the encoding chunk; nothing is
+//     concatenated in memory.
+//   * kStash = true additionally leaves every layer's fp16 operand tile, ReLU sign masks and the alpha pre-activation in the
+//     training stash (TMA bulk stores); mlp_tc_train.cuh holds the backward kernels.
+//   * -DSCADE_TC_TRACE=1 (tools/tc_trace.py) compiles in clock stamps and timing ablations.
 #include <cuda.h>
 #include <cuda_fp16.h>
 
@@ -163,7 +164,8 @@ struct FwdArgs {
   int multires, multires_views;
   float4* out;
   int64_t n_pairs;
-  int dbg;              // timing ablations only (results are WRONG when set): 1 = skip peer_full waits, 2 = skip a_ready waits
+  int dbg;              // trace build only -- timing ablations (results are WRONG when set): 1 = ignore weight arrival,
+                        // 2 = ignore operand readiness, 32 = no epilogue work
 };
 
 // Activation / gradient stash of the tensor-core training path (workspace of a forward call with save_for_backward=1).
@@ -415,8 +417,7 @@ __global__ void __launch_bounds__(PP_THREADS, 1) nerf_mlp_tc_pp_kernel(const __g
   const int64_t n_steps = (a.n_pairs + 1) / 2;
 
   const uint32_t bar_full = sbase + OFF_BAR, bar_empty = bar_full + 8 * NUM_STAGES;
-  const uint32_t bar_peer_full = bar_empty + 8 * NUM_STAGES;
-  const uint32_t bar_acc = bar_peer_full + 8 * NUM_STAGES, bar_aready = bar_acc + 16;
+  const uint32_t bar_acc = bar_empty + 16 * NUM_STAGES, bar_aready = bar_acc + 16;     // (8 * NUM_STAGES bytes after bar_empty are unused)
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + OFF_BAR + 8 * (3 * NUM_STAGES + 4));
 
   if (threadIdx.x == 0) {

@@ -69,8 +69,7 @@ __global__ void __launch_bounds__(PP_THREADS, 1) nerf_mlp_tc_dgrad_kernel(const 
   const int64_t n_steps = (a.n_pairs + 1) / 2;
 
   const uint32_t bar_full = sbase + OFF_BAR, bar_empty = bar_full + 8 * NUM_STAGES;
-  const uint32_t bar_peer_full = bar_empty + 8 * NUM_STAGES;
-  const uint32_t bar_acc = bar_peer_full + 8 * NUM_STAGES, bar_aready = bar_acc + 16;
+  const uint32_t bar_acc = bar_empty + 16 * NUM_STAGES, bar_aready = bar_acc + 16;     // (8 * NUM_STAGES bytes after bar_empty are unused)
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + OFF_BAR + 8 * (3 * NUM_STAGES + 4));
 
   if (threadIdx.x == 0) {
