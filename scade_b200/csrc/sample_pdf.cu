@@ -93,7 +93,7 @@ sample_pdf_kernel(RayPdfSource src, int64_t N, int n, const float* __restrict__ 
   const int64_t r = (int64_t)blockIdx.x * SP_WARPS + wid;
   if (r >= N) return;
   const int B = src.B;
-  float* s_cdf = smem + (size_t)wid * (2 * B + sort_pow2);
+  float* s_cdf = smem + (size_t)wid * (2 * B + 2 * sort_pow2);     // cdf | bins | sort area | merge output
   float* s_bins = s_cdf + B;
   float* s_sort = s_bins + B;
   build_cdf(src, r, s_cdf, s_bins, lane);
@@ -128,10 +128,43 @@ sample_pdf_kernel(RayPdfSource src, int64_t N, int n, const float* __restrict__ 
     const int S = B + 1, tot = S + n;
     const float* z = src.bins + r * S;                  // from_z form only
     for (int i = lane; i < S; i += 32) s_sort[i] = z[i];
-    for (int i = tot + lane; i < sort_pow2; i += 32) s_sort[i] = __int_as_float(0x7f800000);
     __syncwarp();
-    bitonic_sort_warp(s_sort, sort_pow2, lane);
-    for (int i = lane; i < tot; i += 32) z_merged[r * tot + i] = s_sort[i];
+    // Both lists are normally already sorted (the stratified z_vals always, the importance samples whenever u is -- det
+    // sampling): then the sorted concatenation is a merge, and every element's output slot is its own index plus its rank
+    // in the other list (one binary search each).  Checked per ray; anything else takes the bitonic network.
+    const float* za = s_sort;
+    const float* zb = s_sort + S;
+    bool sorted = true;
+    for (int i = lane; i < S - 1; i += 32) sorted &= za[i] <= za[i + 1];
+    for (int j = lane; j < n - 1; j += 32) sorted &= zb[j] <= zb[j + 1];
+    if (__all_sync(FULL, sorted)) {
+      float* s_out = s_sort + sort_pow2;
+      for (int i = lane; i < S; i += 32) {
+        const float a = za[i];
+        int lo = 0, hi = n;                             // #{b < a}: equal values keep the coarse sample first
+        while (lo < hi) {
+          int mid = (lo + hi) >> 1;
+          if (zb[mid] < a) lo = mid + 1; else hi = mid;
+        }
+        s_out[i + lo] = a;
+      }
+      for (int j = lane; j < n; j += 32) {
+        const float b = zb[j];
+        int lo = 0, hi = S;                             // #{a <= b}
+        while (lo < hi) {
+          int mid = (lo + hi) >> 1;
+          if (za[mid] <= b) lo = mid + 1; else hi = mid;
+        }
+        s_out[j + lo] = b;
+      }
+      __syncwarp();
+      for (int i = lane; i < tot; i += 32) z_merged[r * tot + i] = s_out[i];
+    } else {
+      for (int i = tot + lane; i < sort_pow2; i += 32) s_sort[i] = __int_as_float(0x7f800000);
+      __syncwarp();
+      bitonic_sort_warp(s_sort, sort_pow2, lane);
+      for (int i = lane; i < tot; i += 32) z_merged[r * tot + i] = s_sort[i];
+    }
   }
 }
 
@@ -227,7 +260,7 @@ static int next_pow2(int v) {
 static int launch_sample(RayPdfSource src, int64_t N, int n, const float* u, int u_is_joint, float* samples_out,
                          float* u_out, float* z_merged, float* z_std, void* stream) {
   int sort_pow2 = z_merged ? next_pow2(src.B + 1 + n) : 0;
-  size_t smem = (size_t)SP_WARPS * (2 * src.B + sort_pow2) * sizeof(float);
+  size_t smem = (size_t)SP_WARPS * (2 * src.B + 2 * sort_pow2) * sizeof(float);
   if (smem > 200 * 1024) {
     set_error("sample_pdf: %d bins / %d samples exceed the shared-memory budget", src.B, n);
     return SCADE_ERR_UNSUPPORTED;
