@@ -51,24 +51,36 @@ class NetHandle:
         self.desc = _lib.NetDesc(D, W, multires, multires_views, skip)
         self._packed = None
         self._packed_key = None
+        self._struct_key = None          # (data pointers) the cached scade_net structs were built from
+        self._structs = {}
 
     def tc_supported(self):
         return _L().scade_mlp_packed_bytes(byref(self.desc)) > 0
 
     def struct(self, precision):
-        net = _lib.Net()
-        net.desc = self.desc
-        for i, p in enumerate(self.params):
-            if not p.is_cuda or p.dtype != torch.float32 or not p.is_contiguous():
-                raise _lib.ScadeError("network parameters must be contiguous fp32 CUDA tensors")
-            net.params[i] = p.data_ptr()
-        net.packed_f16 = None
+        """scade_net for this call.  The struct (24 pointers) is cached per precision and rebuilt only when a parameter's
+        storage moved; the fp16 stream is re-packed by packed() when a version counter moved."""
+        ptrs = tuple(p.data_ptr() for p in self.params)
+        if ptrs != self._struct_key:
+            for p in self.params:
+                if not p.is_cuda or p.dtype != torch.float32 or not p.is_contiguous():
+                    raise _lib.ScadeError("network parameters must be contiguous fp32 CUDA tensors")
+            self._struct_key, self._structs = ptrs, {}
+        net = self._structs.get(precision)
+        if net is None:
+            net = _lib.Net()
+            net.desc = self.desc
+            for i, ptr_ in enumerate(ptrs):
+                net.params[i] = ptr_
+            net.packed_f16 = None
+            self._structs[precision] = net
         if precision == PREC_TC_F16:
             net.packed_f16 = self.packed().data_ptr()
         return net
 
     def packed(self):
-        key = (_weights_epoch,) + tuple((p.data_ptr(), p._version) for p in self.params)
+        key = (_weights_epoch, self._struct_key if self._struct_key is not None else tuple(p.data_ptr() for p in self.params)) \
+            + tuple(p._version for p in self.params)
         if self._packed is None or key != self._packed_key:
             nbytes = _L().scade_mlp_packed_bytes(byref(self.desc))
             if nbytes == 0:

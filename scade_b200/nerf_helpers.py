@@ -124,13 +124,24 @@ class NeRF(nn.Module):
             ps += [layer.weight, layer.bias]
         return ps
 
+    def _apply(self, fn, *args, **kwargs):
+        # .to() / .cuda() / .float() move the parameter storage: drop the cached C-side view
+        self._handle = None
+        return super()._apply(fn, *args, **kwargs)
+
     def handle(self):
+        """C-side view of the parameters (cached: this sits on the per-call path of render_rays).  The cache is checked
+        against the identity and storage of the first and last parameter; `_apply` and load_state_dict paths that move storage
+        reset it."""
+        h = self._handle
+        if h is not None:
+            first, last = self.pts_linears[0].weight, self.rgb_linear.bias
+            if h.params[0] is first and h.params[-1] is last and self._handle_key == (first.data_ptr(), last.data_ptr()):
+                return h
         ps = self.ordered_parameters()
-        key = tuple(id(p) for p in ps) + tuple(p.data_ptr() for p in ps)
-        if self._handle is None or key != self._handle_key:
-            skip = self.skips[0] if self.skips else -1
-            self._handle = F_.NetHandle(ps, self.D, self.W, (self.input_ch - 3) // 6, (self.input_ch_views - 3) // 6, skip)
-            self._handle_key = key
+        skip = self.skips[0] if self.skips else -1
+        self._handle = F_.NetHandle(ps, self.D, self.W, (self.input_ch - 3) // 6, (self.input_ch_views - 3) // 6, skip)
+        self._handle_key = (ps[0].data_ptr(), ps[-1].data_ptr())
         return self._handle
 
     def forward(self, x):
