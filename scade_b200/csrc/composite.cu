@@ -40,26 +40,47 @@ raw2outputs_fwd_kernel(const float4* __restrict__ raw, const float* __restrict__
   const float4* raw_r = raw + r * S;
   const float* z_r = z + r * S;
   float carry = 1.0f, sr = 0.f, sg = 0.f, sb = 0.f, sdepth = 0.f, sacc = 0.f;
-  for (int base = 0; base < S; base += 32) {
-    const int i = base + lane;
-    const bool valid = i < S;
-    float4 rw = valid ? raw_r[i] : make_float4(0.f, 0.f, 0.f, 0.f);
-    float zi = valid ? z_r[i] : 0.f;
-    float zn = (i + 1 < S) ? z_r[i + 1] : zi;
-    float nz = (noise != nullptr && valid) ? noise[r * S + i] : 0.f;
-    SampleTerms t = sample_terms(rw.w, nz, zi, zn, i == S - 1, norm);
-    float tf = valid ? t.tfac : 1.0f;
-    float incl = warp_scan_prod(tf, lane);
-    float excl = __shfl_up_sync(FULL, incl, 1);
-    if (lane == 0) excl = 1.0f;
-    float w = valid ? t.alpha * (carry * excl) : 0.f;
-    carry *= __shfl_sync(FULL, incl, 31);
-    if (valid && weights != nullptr) weights[r * S + i] = w;
-    sr += w * sigmoidf_(rw.x);                         // RS:543, RS:556
-    sg += w * sigmoidf_(rw.y);
-    sb += w * sigmoidf_(rw.z);
-    sdepth += w * zi;                                  // RS:558
-    sacc += w;                                         // RS:560
+  // Samples are walked 8 chunks (256 samples) at a time: all of a group's loads are issued before its first use, so a ray
+  // of up to 256 samples pays one DRAM latency instead of one per chunk; z_{i+1} comes from the neighbouring lane.
+  constexpr int G = 8;
+  for (int base0 = 0; base0 < S; base0 += 32 * G) {
+    float4 rw[G];
+    float zz[G];
+#pragma unroll
+    for (int c = 0; c < G; ++c) {
+      const int i = base0 + 32 * c + lane;
+      const bool valid = i < S;
+      rw[c] = valid ? raw_r[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+      zz[c] = valid ? z_r[i] : 0.f;
+    }
+    const int i_after = base0 + 32 * G;                 // first sample of the next group (only when S > 256)
+    const float z_after = (i_after < S) ? z_r[i_after] : 0.f;
+#pragma unroll
+    for (int c = 0; c < G; ++c) {
+      const int base = base0 + 32 * c;
+      if (base >= S) break;
+      const int i = base + lane;
+      const bool valid = i < S;
+      const float zi = zz[c];
+      const float z_next_chunk = (c + 1 < G) ? __shfl_sync(FULL, zz[c + 1 < G ? c + 1 : c], 0) : z_after;
+      float zn = __shfl_down_sync(FULL, zi, 1);
+      if (lane == 31) zn = z_next_chunk;
+      if (!(i + 1 < S)) zn = zi;
+      float nz = (noise != nullptr && valid) ? noise[r * S + i] : 0.f;
+      SampleTerms t = sample_terms(rw[c].w, nz, zi, zn, i == S - 1, norm);
+      float tf = valid ? t.tfac : 1.0f;
+      float incl = warp_scan_prod(tf, lane);
+      float excl = __shfl_up_sync(FULL, incl, 1);
+      if (lane == 0) excl = 1.0f;
+      float w = valid ? t.alpha * (carry * excl) : 0.f;
+      carry *= __shfl_sync(FULL, incl, 31);
+      if (valid && weights != nullptr) weights[r * S + i] = w;
+      sr += w * sigmoidf_(rw[c].x);                      // RS:543, RS:556
+      sg += w * sigmoidf_(rw[c].y);
+      sb += w * sigmoidf_(rw[c].z);
+      sdepth += w * zi;                                  // RS:558
+      sacc += w;                                         // RS:560
+    }
   }
   sr = warp_sum(sr); sg = warp_sum(sg); sb = warp_sum(sb); sdepth = warp_sum(sdepth); sacc = warp_sum(sacc);
   if (lane == 0) {

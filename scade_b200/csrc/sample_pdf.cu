@@ -34,22 +34,27 @@ __device__ __forceinline__ float src_weight(const RayPdfSource& s, int64_t r, in
   return s.weights[r * (s.B - 1) + i];
 }
 
-// Fills s_cdf[0..B) and s_bins[0..B); returns sum(w + 1e-5).
+// Fills s_cdf[0..B) and s_bins[0..B); returns sum(w + 1e-5).  Every global load of the ray (weights, bin edges) is issued
+// before the first reduction, and the scan pass re-reads the staged w + 1e-5 from shared memory: one DRAM latency per ray.
 __device__ __forceinline__ float build_cdf(const RayPdfSource& src, int64_t r, float* s_cdf, float* s_bins, int lane) {
   const int B = src.B, nw = B - 1;
   float part = 0.f;
-  for (int i = lane; i < nw; i += 32) part += src_weight(src, r, i) + 1e-5f;     // H:339
+  for (int i = lane; i < nw; i += 32) {
+    const float w = src_weight(src, r, i) + 1e-5f;                               // H:339
+    s_cdf[i + 1] = w;
+    part += w;
+  }
+  for (int i = lane; i < B; i += 32) s_bins[i] = src_bin(src, r, i);
   const float total = warp_sum(part);                                            // H:340
   float carry = 0.f;
   if (lane == 0) s_cdf[0] = 0.f;                                                 // H:343
   for (int base = 0; base < nw; base += 32) {
     int i = base + lane;
-    float p = i < nw ? (src_weight(src, r, i) + 1e-5f) / total : 0.f;
+    float p = i < nw ? s_cdf[i + 1] / total : 0.f;                               // own write, same lane
     float incl = warp_scan_sum(p, lane) + carry;                                 // H:342
     if (i < nw) s_cdf[i + 1] = incl;
     carry = __shfl_sync(FULL, incl, 31);
   }
-  for (int i = lane; i < B; i += 32) s_bins[i] = src_bin(src, r, i);
   __syncwarp();
   return total;
 }
