@@ -175,6 +175,15 @@ int scade_resample_from_z(const float* z_vals, const float* weights_full, int64_
                           const float* u, int u_is_joint, float* samples_out, float* u_out,
                           float* z_merged, float* z_std, void* stream);
 
+/* Compositing + resampling of every ray in one launch: scade_raw2outputs (RS:530-562, no sigma noise) followed by
+ * scade_resample_from_z on the weights it produced (RS:660 + RS:702-713 for the coarse pass, RS:720 + RS:723-730 for the fine
+ * pass); the weights travel through shared memory.  Same results as the two calls.  weights [N,S] is required; the map
+ * outputs and u_out / z_merged / z_std are nullable as in the two calls. */
+int scade_composite_resample(const float* raw, const float* z_vals, const float* rays_d, int d_stride, int64_t N, int S,
+                             float* rgb_map, float* disp_map, float* acc_map, float* weights, float* depth_map,
+                             int n_samples, const float* u, int u_is_joint, float* samples_out, float* u_out,
+                             float* z_merged, float* z_std, void* stream);
+
 /* Backward of the above w.r.t. weights_full [N,S] (zero on the first and last column). */
 int scade_resample_from_z_backward(const float* z_vals, const float* weights_full, const float* u, int64_t N,
                                    int S, int n_samples, const float* d_samples, float* d_weights_full,

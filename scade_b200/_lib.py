@@ -68,6 +68,7 @@ _SIGNATURES = {
     "scade_sample_pdf": (c_int, [_P, _P, c_int64, c_int, c_int, _P, c_int, _P, _P, _P]),
     "scade_sample_pdf_backward": (c_int, [_P, _P, _P, c_int64, c_int, c_int, _P, _P, _P]),
     "scade_resample_from_z": (c_int, [_P, _P, c_int64, c_int, c_int, _P, c_int, _P, _P, _P, _P, _P]),
+    "scade_composite_resample": (c_int, [_P, _P, _P, c_int, c_int64, c_int, _P, _P, _P, _P, _P, c_int, _P, c_int, _P, _P, _P, _P, _P]),
     "scade_resample_from_z_backward": (c_int, [_P, _P, _P, c_int64, c_int, c_int, _P, _P, c_int, _P]),
     "scade_sort_merge": (c_int, [_P, c_int, _P, c_int, c_int64, _P, _P]),
     "scade_space_carving_workspace_bytes": (c_size_t, [c_int, c_int64, c_int]),

@@ -195,18 +195,15 @@ extern "C" int scade_render_rays_forward(const scade_render_cfg* cfg, const floa
   SCADE_TRY(scade_coarse_z_vals(ray_batch, rs, N, Nc, cfg->lindisp, t_rand, z0, stream));
   SCADE_TRY(scade_mlp_forward_rays(coarse, cfg->precision, ray_batch, rs, z0, N, Nc, cfg->bb_center, cfg->bb_scale,
                                    f(L.raw0), ws + L.mlp, L.mlp_bytes, 0, stream));
-  SCADE_TRY(scade_raw2outputs(f(L.raw0), z0, ray_batch + 3, rs, nullptr, N, Nc, out->rgb0, out->disp0, out->acc0, w0,
-                              out->depth0, stream));
-  // importance sampling + sort-merge                                              RS:702-713
-  SCADE_TRY(scade_resample_from_z(z0, w0, N, Nc, Nf, perturbed ? u_coarse : nullptr, cfg->is_joint, f(L.zs), nullptr, zf,
-                                  nullptr, stream));
+  // compositing (RS:660) + importance sampling + sort-merge (RS:702-713) in one launch
+  SCADE_TRY(scade_composite_resample(f(L.raw0), z0, ray_batch + 3, rs, N, Nc, out->rgb0, out->disp0, out->acc0, w0, out->depth0,
+                                     Nf, perturbed ? u_coarse : nullptr, cfg->is_joint, f(L.zs), nullptr, zf, nullptr, stream));
   // fine pass                                                                     RS:714-720
   SCADE_TRY(scade_mlp_forward_rays(fine, cfg->precision, ray_batch, rs, zf, N, S, cfg->bb_center, cfg->bb_scale, rawf,
                                    ws + L.mlp, L.mlp_bytes, 0, stream));
-  SCADE_TRY(scade_raw2outputs(rawf, zf, ray_batch + 3, rs, nullptr, N, S, out->rgb_map, out->disp_map, out->acc_map, wf,
-                              out->depth_map, stream));
-  // depth hypotheses from the fine distribution                                   RS:723-730, 744
-  SCADE_TRY(scade_resample_from_z(zf, wf, N, S, Nf, perturbed ? u_fine : nullptr, cfg->is_joint, hyp, out->u, nullptr,
-                                  out->z_std, stream));
+  // compositing (RS:720) + depth hypotheses from the fine distribution (RS:723-730, 744) in one launch
+  SCADE_TRY(scade_composite_resample(rawf, zf, ray_batch + 3, rs, N, S, out->rgb_map, out->disp_map, out->acc_map, wf,
+                                     out->depth_map, Nf, perturbed ? u_fine : nullptr, cfg->is_joint, hyp, out->u, nullptr,
+                                     out->z_std, stream));
   return SCADE_OK;
 }

@@ -4,28 +4,11 @@
 // T_i = prod_{j<i}(1 - alpha_j + 1e-10) (RS:520) is an exclusive product scan done with warp shuffles
 // plus a carry between chunks; rgb/depth/acc are shuffle reductions.  HBM-bound: 20 B/sample in
 // (raw float4 + z), 4 B/sample out (weights), 28 B/ray out.  Loads are 512-B coalesced per warp.
-#include "common.cuh"
+#include "composite.cuh"
 
 namespace scade {
 
 constexpr int COMP_WARPS = 4;
-
-struct SampleTerms {
-  float alpha, e, dist, tfac, pre;
-};
-
-__device__ __forceinline__ SampleTerms sample_terms(float sigma_raw, float noise, float z_i, float z_next, bool last,
-                                                    float norm) {
-  SampleTerms s;
-  float d = last ? 1e10f : (z_next - z_i);            // RS:514-515
-  s.dist = d * norm;                                   // RS:516
-  s.pre = sigma_raw + noise;                           // RS:518
-  float sig = fmaxf(s.pre, 0.0f);                      // act_fn = relu, RS:512
-  s.e = expf(-sig * s.dist);
-  s.alpha = 1.0f - s.e;
-  s.tfac = 1.0f - s.alpha + 1e-10f;                    // RS:520
-  return s;
-}
 
 __global__ void __launch_bounds__(COMP_WARPS * 32)
 raw2outputs_fwd_kernel(const float4* __restrict__ raw, const float* __restrict__ z, const float* __restrict__ rays_d,
@@ -35,63 +18,8 @@ raw2outputs_fwd_kernel(const float4* __restrict__ raw, const float* __restrict__
   const int lane = threadIdx.x & 31;
   const int64_t r = (int64_t)blockIdx.x * COMP_WARPS + (threadIdx.x >> 5);
   if (r >= N) return;
-  const float dx = rays_d[r * d_stride], dy = rays_d[r * d_stride + 1], dz = rays_d[r * d_stride + 2];
-  const float norm = sqrtf(dx * dx + dy * dy + dz * dz);
-  const float4* raw_r = raw + r * S;
-  const float* z_r = z + r * S;
-  float carry = 1.0f, sr = 0.f, sg = 0.f, sb = 0.f, sdepth = 0.f, sacc = 0.f;
-  // Samples are walked 8 chunks (256 samples) at a time: all of a group's loads are issued before its first use, so a ray
-  // of up to 256 samples pays one DRAM latency instead of one per chunk; z_{i+1} comes from the neighbouring lane.
-  constexpr int G = 8;
-  for (int base0 = 0; base0 < S; base0 += 32 * G) {
-    float4 rw[G];
-    float zz[G];
-#pragma unroll
-    for (int c = 0; c < G; ++c) {
-      const int i = base0 + 32 * c + lane;
-      const bool valid = i < S;
-      rw[c] = valid ? raw_r[i] : make_float4(0.f, 0.f, 0.f, 0.f);
-      zz[c] = valid ? z_r[i] : 0.f;
-    }
-    const int i_after = base0 + 32 * G;                 // first sample of the next group (only when S > 256)
-    const float z_after = (i_after < S) ? z_r[i_after] : 0.f;
-#pragma unroll
-    for (int c = 0; c < G; ++c) {
-      const int base = base0 + 32 * c;
-      if (base >= S) break;
-      const int i = base + lane;
-      const bool valid = i < S;
-      const float zi = zz[c];
-      const float z_next_chunk = (c + 1 < G) ? __shfl_sync(FULL, zz[c + 1 < G ? c + 1 : c], 0) : z_after;
-      float zn = __shfl_down_sync(FULL, zi, 1);
-      if (lane == 31) zn = z_next_chunk;
-      if (!(i + 1 < S)) zn = zi;
-      float nz = (noise != nullptr && valid) ? noise[r * S + i] : 0.f;
-      SampleTerms t = sample_terms(rw[c].w, nz, zi, zn, i == S - 1, norm);
-      float tf = valid ? t.tfac : 1.0f;
-      float incl = warp_scan_prod(tf, lane);
-      float excl = __shfl_up_sync(FULL, incl, 1);
-      if (lane == 0) excl = 1.0f;
-      float w = valid ? t.alpha * (carry * excl) : 0.f;
-      carry *= __shfl_sync(FULL, incl, 31);
-      if (valid && weights != nullptr) weights[r * S + i] = w;
-      sr += w * sigmoidf_(rw[c].x);                      // RS:543, RS:556
-      sg += w * sigmoidf_(rw[c].y);
-      sb += w * sigmoidf_(rw[c].z);
-      sdepth += w * zi;                                  // RS:558
-      sacc += w;                                         // RS:560
-    }
-  }
-  sr = warp_sum(sr); sg = warp_sum(sg); sb = warp_sum(sb); sdepth = warp_sum(sdepth); sacc = warp_sum(sacc);
-  if (lane == 0) {
-    if (rgb_map) { rgb_map[r * 3] = sr; rgb_map[r * 3 + 1] = sg; rgb_map[r * 3 + 2] = sb; }
-    if (depth_map) depth_map[r] = sdepth;
-    if (acc_map) acc_map[r] = sacc;
-    if (disp_map) {
-      float q = sdepth / sacc;                          // RS:559; torch.max propagates the nan of 0/0
-      disp_map[r] = (q != q) ? q : 1.0f / fmaxf(1e-10f, q);
-    }
-  }
+  composite_ray_fwd<false>(raw, z, rays_d, d_stride, noise, r, S, lane, rgb_map, disp_map, acc_map, weights, depth_map, nullptr,
+                           nullptr);
 }
 
 // Backward.  Pass 1 re-runs the forward scan and keeps T_i in shared memory;

@@ -8,7 +8,7 @@
 //               below/above gather and the linear interpolation with the denom<1e-5 -> 1 rule (H:368-381)
 //   merge     : bitonic sort of the S coarse + n importance values in shared memory (u may be unsorted)
 // HBM traffic is 4*(2S-3+2n) B/ray; everything else stays on chip.
-#include "common.cuh"
+#include "composite.cuh"
 
 namespace scade {
 
@@ -89,19 +89,17 @@ __device__ __forceinline__ void bitonic_sort_warp(float* s, int n_pow2, int lane
   }
 }
 
-__global__ void __launch_bounds__(SP_WARPS * 32)
-sample_pdf_kernel(RayPdfSource src, int64_t N, int n, const float* __restrict__ u, int u_is_joint,
-                  float* __restrict__ samples_out, float* __restrict__ u_out, float* __restrict__ z_merged,
-                  float* __restrict__ z_std, int sort_pow2) {
-  extern __shared__ float smem[];
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const int64_t r = (int64_t)blockIdx.x * SP_WARPS + wid;
-  if (r >= N) return;
+// Resampling of ONE ray by one warp: the body of sample_pdf_kernel.  `r_src` indexes the source arrays (0 when they are this
+// warp's shared-memory staging of the ray), `r` the outputs.  s_base: 2 B + 2 sort_pow2 floats of shared memory.
+__device__ __forceinline__ void resample_ray(const RayPdfSource& src, int64_t r_src, int64_t r, int n, const float* __restrict__ u,
+                                             int u_is_joint, float* __restrict__ samples_out, float* __restrict__ u_out,
+                                             float* __restrict__ z_merged, float* __restrict__ z_std, int sort_pow2, float* s_base,
+                                             int lane) {
   const int B = src.B;
-  float* s_cdf = smem + (size_t)wid * (2 * B + 2 * sort_pow2);     // cdf | bins | sort area | merge output
+  float* s_cdf = s_base;                                              // cdf | bins | sort area | merge output
   float* s_bins = s_cdf + B;
   float* s_sort = s_bins + B;
-  build_cdf(src, r, s_cdf, s_bins, lane);
+  build_cdf(src, r_src, s_cdf, s_bins, lane);
   float ssum = 0.f;
   for (int j = lane; j < n; j += 32) {
     float uj = fetch_u(u, u_is_joint, r, n, j);
@@ -131,7 +129,7 @@ sample_pdf_kernel(RayPdfSource src, int64_t N, int n, const float* __restrict__ 
   }
   if (z_merged != nullptr) {                            // RS:713  sort(cat([z_vals, z_samples]))
     const int S = B + 1, tot = S + n;
-    const float* z = src.bins + r * S;                  // from_z form only
+    const float* z = src.bins + r_src * S;              // from_z form only
     for (int i = lane; i < S; i += 32) s_sort[i] = z[i];
     __syncwarp();
     // Both lists are normally already sorted (the stratified z_vals always, the importance samples whenever u is -- det
@@ -171,6 +169,38 @@ sample_pdf_kernel(RayPdfSource src, int64_t N, int n, const float* __restrict__ 
       for (int i = lane; i < tot; i += 32) z_merged[r * tot + i] = s_sort[i];
     }
   }
+}
+
+__global__ void __launch_bounds__(SP_WARPS * 32)
+sample_pdf_kernel(RayPdfSource src, int64_t N, int n, const float* __restrict__ u, int u_is_joint,
+                  float* __restrict__ samples_out, float* __restrict__ u_out, float* __restrict__ z_merged,
+                  float* __restrict__ z_std, int sort_pow2) {
+  extern __shared__ float smem[];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int64_t r = (int64_t)blockIdx.x * SP_WARPS + wid;
+  if (r >= N) return;
+  resample_ray(src, r, r, n, u, u_is_joint, samples_out, u_out, z_merged, z_std, sort_pow2,
+               smem + (size_t)wid * (2 * src.B + 2 * sort_pow2), lane);
+}
+
+// Compositing + resampling of a ray in ONE kernel (RS:660 + RS:702-713, or RS:720 + RS:723-730): the weights and z values go
+// from the compositing scan to the inverse-CDF sampler through shared memory instead of a second kernel re-reading them.
+__global__ void __launch_bounds__(SP_WARPS * 32)
+composite_resample_kernel(const float4* __restrict__ raw, const float* __restrict__ z, const float* __restrict__ rays_d, int d_stride,
+                          int64_t N, int S, float* __restrict__ rgb_map, float* __restrict__ disp_map, float* __restrict__ acc_map,
+                          float* __restrict__ weights, float* __restrict__ depth_map, int n, const float* __restrict__ u,
+                          int u_is_joint, float* __restrict__ samples_out, float* __restrict__ u_out, float* __restrict__ z_merged,
+                          float* __restrict__ z_std, int sort_pow2) {
+  extern __shared__ float smem[];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int64_t r = (int64_t)blockIdx.x * SP_WARPS + wid;
+  if (r >= N) return;
+  float* s_z = smem + (size_t)wid * (2 * S + 2 * (S - 1) + 2 * sort_pow2);
+  float* s_w = s_z + S;
+  composite_ray_fwd<true>(raw, z, rays_d, d_stride, nullptr, r, S, lane, rgb_map, disp_map, acc_map, weights, depth_map, s_z, s_w);
+  __syncwarp();
+  RayPdfSource src{s_z, s_w, 1, S - 1};
+  resample_ray(src, 0, r, n, u, u_is_joint, samples_out, u_out, z_merged, z_std, sort_pow2, s_w + S, lane);
 }
 
 // d weights from d samples.  s = b_lo + (u - C_lo)/den * (b_hi - b_lo):
@@ -278,6 +308,25 @@ static int launch_sample(RayPdfSource src, int64_t N, int n, const float* u, int
   return SCADE_OK;
 }
 
+static int launch_composite_resample(const float* raw, const float* z, const float* rays_d, int d_stride, int64_t N, int S,
+                                     float* rgb_map, float* disp_map, float* acc_map, float* weights, float* depth_map, int n,
+                                     const float* u, int u_is_joint, float* samples_out, float* u_out, float* z_merged,
+                                     float* z_std, void* stream) {
+  int sort_pow2 = z_merged ? next_pow2(S + n) : 0;
+  size_t smem = (size_t)SP_WARPS * (2 * S + 2 * (S - 1) + 2 * sort_pow2) * sizeof(float);
+  if (smem > 200 * 1024) {
+    set_error("composite_resample: %d samples / %d importance samples exceed the shared-memory budget", S, n);
+    return SCADE_ERR_UNSUPPORTED;
+  }
+  if (smem > 48 * 1024)
+    SCADE_CUDA(cudaFuncSetAttribute(composite_resample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  composite_resample_kernel<<<(unsigned)ceil_div<int64_t>(N, SP_WARPS), SP_WARPS * 32, smem, as_stream(stream)>>>(
+      reinterpret_cast<const float4*>(raw), z, rays_d, d_stride, N, S, rgb_map, disp_map, acc_map, weights, depth_map, n, u,
+      u_is_joint, samples_out, u_out, z_merged, z_std, sort_pow2);
+  SCADE_LAUNCH_CHECK();
+  return SCADE_OK;
+}
+
 static int launch_sample_bwd(RayPdfSource src, int64_t N, int n, const float* u, const float* d_samples,
                              float* d_weights, int accumulate, void* stream) {
   size_t smem = (size_t)SP_WARPS * 3 * src.B * sizeof(float);
@@ -322,6 +371,18 @@ extern "C" int scade_resample_from_z(const float* z_vals, const float* weights_f
   if (N == 0) return SCADE_OK;
   RayPdfSource src{z_vals, weights_full, 1, S - 1};
   return launch_sample(src, N, n_samples, u, u_is_joint, samples_out, u_out, z_merged, z_std, stream);
+}
+
+extern "C" int scade_composite_resample(const float* raw, const float* z_vals, const float* rays_d, int d_stride, int64_t N, int S,
+                                        float* rgb_map, float* disp_map, float* acc_map, float* weights, float* depth_map,
+                                        int n_samples, const float* u, int u_is_joint, float* samples_out, float* u_out,
+                                        float* z_merged, float* z_std, void* stream) {
+  SCADE_CHECK_ARG(raw && z_vals && rays_d && weights && samples_out && N >= 0 && S >= 3 && n_samples > 0 && d_stride >= 3,
+                  "composite_resample: bad arguments");
+  SCADE_CHECK_ARG((reinterpret_cast<uintptr_t>(raw) & 15) == 0, "composite_resample: raw must be 16-byte aligned");
+  if (N == 0) return SCADE_OK;
+  return launch_composite_resample(raw, z_vals, rays_d, d_stride, N, S, rgb_map, disp_map, acc_map, weights, depth_map, n_samples,
+                                   u, u_is_joint, samples_out, u_out, z_merged, z_std, stream);
 }
 
 extern "C" int scade_resample_from_z_backward(const float* z_vals, const float* weights_full, const float* u,
