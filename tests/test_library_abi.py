@@ -72,3 +72,18 @@ def test_stash_image_helpers_roundtrip():
     one = np.zeros((1, 32), bool)
     one[0, 5] = True                                 # element 5 = 4*1 + 1 -> s = 1, g = 1 -> bit 31 - 8 - 1
     assert sign_mask_words(one)[0, 0] == np.uint32(1 << 22)
+
+
+def test_cpp_host_example_builds_against_the_header():
+    """examples/render_cabi.cpp is a host with no Python and no torch: it must compile against include/scade_b200.h and link
+    against the in-tree library (the GPU test runs it)."""
+    import os
+    import shutil
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if shutil.which("g++") is None:
+        pytest.skip("no g++")
+    _lib.load()
+    r = subprocess.run(["sh", os.path.join(root, "examples", "build.sh")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert os.path.exists(os.path.join(root, "examples", "render_cabi"))
