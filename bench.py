@@ -344,8 +344,8 @@ def run_train(args):
         from scade_b200.optim import FusedAdam, flatten_parameters
         net_params = [p for n in nets for p in n.parameters()]
         flat = flatten_parameters(net_params, [scale, shift])
-        opt = FusedAdam(net_params, lr=5e-4, betas=(0.9, 0.999), flat=flat)              # RS:469
-        opt_ss = FusedAdam([scale, shift], lr=1e-6, flat=flat)                           # RS:888
+        opt = FusedAdam(net_params, lr=5e-4, betas=(0.9, 0.999), flat=flat, capturable=args.train_graph)     # RS:469
+        opt_ss = FusedAdam([scale, shift], lr=1e-6, flat=flat, capturable=args.train_graph)                  # RS:888
     else:
         opt = torch.optim.Adam([p for n in nets for p in n.parameters()], lr=5e-4, betas=(0.9, 0.999))
         opt_ss = torch.optim.Adam([scale, shift], lr=1e-6)
@@ -355,14 +355,22 @@ def run_train(args):
     target_s, target_h = syn.make_train_targets(N, K=K, seed=82)
     target_s, target_h = to(target_s[lo:hi]), to(target_h[:, lo:hi])
 
+    graphed = None
+    if args.optimizer == "fused" and args.train_graph:
+        # the whole step (zero_grad, forward, losses, backward, all-reduce, both Adam launches) as one CUDA graph
+        from scade_b200.dist import GraphedTrainStep
+        graphed = GraphedTrainStep(kw, scale, shift, flat, [opt, opt_ss], n_global=N, warmup=3)
+
     def step():
+        if graphed is not None:
+            return graphed(rb, target_s, target_h)
         opt.zero_grad(set_to_none=False)
         opt_ss.zero_grad(set_to_none=False)
         losses = sharded_train_step(rb, target_s, target_h, scale, shift, kw, n_global=N, flat=flat)
         opt.step()
         opt_ss.step()
         return losses
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(max(args.warmup, 3) + (2 if graphed is not None else 0)):      # (3 eager steps, then the capturing one)
         step()
     if world > 1:
         dist.barrier()
@@ -391,7 +399,8 @@ def run_train(args):
             "config": {"workload": "BASELINE config 3 train step", "global_rays": N,
                        "precision": "tcgen05 fwd + dgrad + wgrad, fp32 master weights / gradients / Adam" if args.precision == "tc_f16"
                        else "fp32 FFMA GEMMs (fwd+bwd)",
-                       "collective": "1 NCCL all-reduce / step, flat fp32 buffer 4.72 MB", "optimizer": args.optimizer},
+                       "collective": "1 NCCL all-reduce / step, flat fp32 buffer 4.72 MB", "optimizer": args.optimizer,
+                       "launch": "one CUDA graph per step (scade_b200.dist.GraphedTrainStep)" if graphed is not None else "eager"},
             "gpu_launches": int(lib.scade_kernel_launch_count() - l0), "loss": float(losses["loss"]),
             "roofline": {"bound": "tensor", "achieved": flop_step / sec / 1e12 / world, "peak": sustained, "unit": "TFLOP/s per GPU",
                          "frac": flop_step / sec / 1e12 / world / sustained, "peak_source": f"{src} bf16 sustained", "traffic": None,
@@ -512,6 +521,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--optimizer", default="fused", choices=["fused", "torch"],
                     help="train workload: fused = flat parameters + scade_adam_step (default); torch = torch.optim.Adam on 48 tensors")
+    ap.add_argument("--train-graph", type=int, default=1, help="train workload: replay the step as one CUDA graph (0 = eager)")
     ap.add_argument("--workload", default="render", choices=["render", "train", "image", "video"],
                     help="render = BASELINE metric (default); train = config 3 (4096 rays, 64c+128f, K=20, fwd+loss+bwd+allreduce+Adam); "
                          "image / video = configs 4 / 5 (full 640x480 frames, pixels sharded across the GPUs)")

@@ -237,6 +237,12 @@ int scade_gather_train_batch(int H, int W, const float* intrinsic_host, const fl
 int scade_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, double lr,
                     double beta1, double beta2, double eps, int64_t step, void* stream);
 
+/* The same step with the step count and the learning rate in DEVICE memory, so that the launch can be captured in a CUDA graph
+ * and replayed every iteration: *step_dev is the number of steps taken so far (int64, incremented by the call), *lr_dev the
+ * current learning rate (double).  Bias corrections are formed on the device in double with the same expressions. */
+int scade_adam_step_graph(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
+                          const double* lr_dev, double beta1, double beta2, double eps, int64_t* step_dev, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Video / eval post-processing: render_video (RS:236-262), write_images_with_metrics (RS:395-405)
  * --------------------------------------------------------------------------------------------- */

@@ -79,6 +79,7 @@ _SIGNATURES = {
                                          c_int, _P, _P, c_int, _P, c_int, c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "scade_video_frame": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_float, _P, _P, _P, _P, _P, _P]),
     "scade_adam_step": (c_int, [_P, _P, _P, _P, c_int64, c_double, c_double, c_double, c_double, c_int64, _P]),
+    "scade_adam_step_graph": (c_int, [_P, _P, _P, _P, c_int64, _P, c_double, c_double, c_double, _P, _P]),
     "scade_render_rays_workspace_bytes": (c_size_t, [POINTER(RenderCfg), POINTER(NetDesc), POINTER(NetDesc), c_int64]),
     "scade_render_rays_forward": (c_int, [POINTER(RenderCfg), _P, c_int64, POINTER(Net), POINTER(Net), _P, _P, _P,
                                           POINTER(RenderOut), _P, c_size_t, _P]),

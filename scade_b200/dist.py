@@ -103,6 +103,66 @@ def sharded_train_step(ray_batch, target_s, target_h, scale, shift, render_kwarg
             "loss": losses[0] + space_carving_weight * losses[1] + losses[2]}
 
 
+class GraphedTrainStep:
+    """One SCADE training step (zero_grad, sharded_train_step, optimizer steps; RS:954-997) recorded once as a CUDA graph and
+    replayed: forward, losses, backward, the gradient all-reduce and the fused Adam launches cost one graph launch per step
+    instead of ~100 kernel / collective launches from Python (which is what bounds the step once the rays are sharded 8 ways).
+
+        step = GraphedTrainStep(render_kwargs, scale, shift, flat, [opt, opt_ss], n_global=4096)
+        losses = step(ray_batch, target_s, target_h)       # this rank's shard; shapes must not change between calls
+
+    Requirements: parameters and scale / shift in one FlatParams (`flat`), optimizers = FusedAdam(..., flat=flat,
+    capturable=True).  The first `warmup` calls run eagerly (they are real steps), the next call captures and replays.
+    Learning-rate changes through param_groups (update_learning_rate, RS:990) are uploaded before the next replay."""
+
+    def __init__(self, render_kwargs, scale, shift, flat, optimizers, n_global=None, space_carving_weight=0.007, threshold=0.0,
+                 group=None, warmup=3):
+        self.kw, self.scale, self.shift, self.flat, self.opts = render_kwargs, scale, shift, flat, list(optimizers)
+        self.n_global, self.scw, self.thr, self.group, self.warmup = n_global, space_carving_weight, threshold, group, int(warmup)
+        self.calls, self.graph, self.static, self.losses = 0, None, None, None
+        for o in self.opts:
+            if not getattr(o, "capturable", False):
+                raise ValueError("GraphedTrainStep needs FusedAdam(..., capturable=True) optimizers")
+
+    def _body(self, rb, ts, th):
+        for o in self.opts:
+            o.zero_grad(set_to_none=False)
+        losses = sharded_train_step(rb, ts, th, self.scale, self.shift, self.kw, n_global=self.n_global,
+                                    space_carving_weight=self.scw, threshold=self.thr, group=self.group, flat=self.flat)
+        for o in self.opts:
+            o.step()
+        return losses
+
+    def __call__(self, ray_batch, target_s, target_h):
+        from .optim import note_replay
+        self.calls += 1
+        if self.graph is None and self.calls <= self.warmup:
+            return self._body(ray_batch, target_s, target_h)
+        if self.graph is None:
+            self.static = (ray_batch.clone(), target_s.clone(), target_h.clone())
+            torch.cuda.synchronize()
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self.losses = self._body(*self.static)
+            for o in self.opts:
+                o._step -= 1                                 # the capture only recorded the step; the replay below takes it
+        else:
+            for dst, src in zip(self.static, (ray_batch, target_s, target_h)):
+                if dst.shape != src.shape:
+                    raise ValueError(f"GraphedTrainStep was captured for shapes {tuple(dst.shape)}, got {tuple(src.shape)}")
+        for dst, src in zip(self.static, (ray_batch, target_s, target_h)):
+            dst.copy_(src, non_blocking=True)
+        for o in self.opts:                                   # a learning rate changed through param_groups applies to THIS step
+            lr = float(o.param_groups[0]["lr"])
+            if o._lr_uploaded != lr:
+                o._lr_t.fill_(lr)
+                o._lr_uploaded = lr
+        self.graph.replay()
+        for o in self.opts:
+            note_replay(o, upload_lr=False)
+        return self.losses
+
+
 def flat_exchange(flat, partials, group=None):
     """Gradient exchange when parameters / gradients live in flat buffers (scade_b200.optim.FlatParams): the loss partial
     sums ride in the spare tail behind the gradients and the exchange is ONE in-place all-reduce of that buffer -- nothing

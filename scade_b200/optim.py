@@ -83,11 +83,15 @@ class FusedAdam(torch.optim.Optimizer):
     consecutive run of ``flat.params`` (e.g. the two networks, or scale / shift with their own learning rate, RS:888), one
     launch on that slice.  ``FusedAdam(params)``: any CUDA fp32 parameters, one launch each."""
 
-    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, flat=None):
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, flat=None, capturable=False):
+        """capturable: keep the step count and the learning rate in device memory (scade_adam_step_graph) so that step() can be
+        recorded in a CUDA graph (flat storage only); `param_groups[0]['lr']` is uploaded whenever it changed, outside captures."""
         if isinstance(params, FlatParams):
             flat, params = params, params.params
         plist = list(params)
         super().__init__(plist, dict(lr=lr, betas=betas, eps=eps))
+        self.capturable = bool(capturable)
+        self._step_t = self._lr_t = self._lr_uploaded = None
         self.flat, self._range = flat, None
         if flat is not None:
             ids = [id(p) for p in flat.params]
@@ -133,12 +137,29 @@ class FusedAdam(torch.optim.Optimizer):
         g0 = self.param_groups[0]
         if self.flat is not None and self.flat.intact() and len(self.param_groups) == 1:
             m, v = self._flat_state()
-            self._step += 1
             f = self.flat
             o0, o1, i0, i1 = self._range
-            check(L.scade_adam_step(ptr(f.flat[o0:o1]), ptr(f.flat_grad[o0:o1]), ptr(m), ptr(v), o1 - o0, float(g0["lr"]),
-                                    float(g0["betas"][0]), float(g0["betas"][1]), float(g0["eps"]), self._step, stream_ptr()),
-                  "scade_adam_step")
+            if self.capturable:
+                capturing = torch.cuda.is_current_stream_capturing()
+                if self._step_t is None:
+                    if capturing:
+                        raise _lib.ScadeError("FusedAdam(capturable=True): take one eager step before capturing")
+                    self._step_t = torch.full((1,), self._step, dtype=torch.int64, device=f.flat.device)
+                    self._lr_t = torch.zeros(1, dtype=torch.float64, device=f.flat.device)
+                if self._lr_uploaded != float(g0["lr"]):
+                    if capturing:
+                        raise _lib.ScadeError("FusedAdam(capturable=True): the learning rate changed inside a capture")
+                    self._lr_t.fill_(float(g0["lr"]))
+                    self._lr_uploaded = float(g0["lr"])
+                self._step += 1                               # host mirror (replays are counted by note_replay)
+                check(L.scade_adam_step_graph(ptr(f.flat[o0:o1]), ptr(f.flat_grad[o0:o1]), ptr(m), ptr(v), o1 - o0, ptr(self._lr_t),
+                                              float(g0["betas"][0]), float(g0["betas"][1]), float(g0["eps"]), ptr(self._step_t),
+                                              stream_ptr()), "scade_adam_step_graph")
+            else:
+                self._step += 1
+                check(L.scade_adam_step(ptr(f.flat[o0:o1]), ptr(f.flat_grad[o0:o1]), ptr(m), ptr(v), o1 - o0, float(g0["lr"]),
+                                        float(g0["betas"][0]), float(g0["betas"][1]), float(g0["eps"]), self._step, stream_ptr()),
+                      "scade_adam_step")
             for p in f.params[i0:i1]:
                 self.state[p]["step"] = self._step
             F_.mark_weights_changed()
@@ -158,6 +179,20 @@ class FusedAdam(torch.optim.Optimizer):
                                         st["step"], stream_ptr()), "scade_adam_step")
         F_.mark_weights_changed()
         return loss
+
+
+def note_replay(optimizer, upload_lr=True):
+    """Bookkeeping after a CUDA-graph replay that contained `optimizer.step()` (FusedAdam(capturable=True)): the host mirror of
+    the step count advances, a learning rate changed through param_groups is uploaded for the NEXT replay, and the fp16 weight
+    streams are marked stale for eager code."""
+    from . import functional as F_
+    optimizer._step += 1
+    if upload_lr and optimizer._lr_t is not None:
+        lr = float(optimizer.param_groups[0]["lr"])
+        if optimizer._lr_uploaded != lr:
+            optimizer._lr_t.fill_(lr)
+            optimizer._lr_uploaded = lr
+    F_.mark_weights_changed()
 
 
 def update_learning_rate(optimizer, learning_rate):

@@ -186,3 +186,62 @@ def test_tc_train_step_matches_fp32_path(dev):
         assert cosine(ga, gb) > 0.99
     for ga, gb in zip(a[3][1], b[3][1]):                     # fine network
         assert cosine(ga, gb) > 0.9
+
+
+def test_graphed_train_step_matches_eager(dev):
+    """GraphedTrainStep (the whole step as one CUDA graph: zero_grad, forward, losses, backward, exchange, capturable fused Adam)
+    follows the eager step: same losses and parameters after 7 steps (deterministic sampling; fp32 atomics in the weight
+    gradients reorder sums, hence a tolerance), and the device-side step count / learning-rate upload work."""
+    from scade_b200 import nerf_helpers as NH, render as R_
+    from scade_b200.dist import GraphedTrainStep, sharded_train_step
+    from scade_b200.optim import FusedAdam, flatten_parameters, update_learning_rate
+    from tests.golden.generate_goldens import net_pair
+    N, Nc, Nf, K = 256, 16, 32, 5
+    T = lambda a, d: torch.from_numpy(np.ascontiguousarray(a)).to(d)
+    rb = T(syn.make_ray_batch(N, seed=90), dev)
+    target_s, target_h = syn.make_train_targets(N, K=K, seed=91)
+    target_s, target_h = T(target_s, dev), T(target_h, dev)
+    bb_center, bb_scale = syn.bounding_box()
+    pc, pf = net_pair(8, 256)
+
+    def setup(capturable):
+        nets = []
+        for p in (pc, pf):
+            net = NH.NeRF(D=8, W=256, input_ch=57, input_ch_views=3, output_ch=5, skips=[4], use_viewdirs=True, precision="tc_f16")
+            net.load_state_dict({k: torch.from_numpy(v) for k, v in p.items()})
+            nets.append(net.to(dev))
+        qf = R_.NetworkQuery(NH.get_embedder(9, 0)[0], NH.get_embedder(0, 0)[0], bb_center, bb_scale, precision="tc_f16")
+        kw = dict(network_fn=nets[0], network_query_fn=qf, N_samples=Nc, embedded_cam=torch.tensor((), device=dev), perturb=0.0,
+                  N_importance=Nf, network_fine=nets[1], raw_noise_std=0.0)
+        scale = torch.ones(1, device=dev, requires_grad=True)
+        shift = torch.zeros(1, device=dev, requires_grad=True)
+        params = [p for n in nets for p in n.parameters()]
+        flat = flatten_parameters(params, [scale, shift])
+        opt = FusedAdam(params, lr=2e-5, flat=flat, capturable=capturable)        # small steps: a smooth, comparable trajectory
+        opt_ss = FusedAdam([scale, shift], lr=1e-4, flat=flat, capturable=capturable)
+        return kw, scale, shift, flat, opt, opt_ss
+
+    kw, scale, shift, flat, opt, opt_ss = setup(False)
+    ref_losses = []
+    for i in range(7):
+        if i == 5:
+            update_learning_rate(opt, 5e-6)
+        opt.zero_grad(); opt_ss.zero_grad()
+        ls = sharded_train_step(rb, target_s, target_h, scale, shift, kw, n_global=N, flat=flat)
+        opt.step(); opt_ss.step()
+        ref_losses.append(float(ls["loss"]))
+    ref_flat = flat.flat.detach().clone()
+
+    kw, scale, shift, flat, opt, opt_ss = setup(True)
+    step = GraphedTrainStep(kw, scale, shift, flat, [opt, opt_ss], n_global=N, warmup=2)
+    losses = []
+    for i in range(7):
+        if i == 5:
+            update_learning_rate(opt, 5e-6)
+        losses.append(float(step(rb, target_s, target_h)["loss"]))
+    assert step.graph is not None and opt._step == 7 and int(opt._step_t) == 7
+    # Adam normalises every gradient to ~lr per step, so the atomics-order noise of the weight gradients moves parameters whose
+    # gradient is ~0 by up to lr per step: the trajectories agree closely in the mean, not bit for bit
+    np.testing.assert_allclose(losses, ref_losses, rtol=1e-3)
+    diff = (flat.flat.detach() - ref_flat).abs()
+    assert float(diff.mean()) < 2e-6 and float(diff.max()) < 7 * 2e-5 * 2, (float(diff.mean()), float(diff.max()))
