@@ -401,14 +401,22 @@ def run_train(args):
                        else "fp32 FFMA GEMMs (fwd+bwd)",
                        "collective": "1 NCCL all-reduce / step, flat fp32 buffer 4.72 MB", "optimizer": args.optimizer,
                        "launch": "one CUDA graph per step (scade_b200.dist.GraphedTrainStep)" if graphed is not None else "eager"},
-            "gpu_launches": int(lib.scade_kernel_launch_count() - l0), "loss": float(losses["loss"]),
+            "gpu_launches": int(lib.scade_kernel_launch_count() - l0) if graphed is None else int(graphed.launches_per_step * args.steps),
+            "loss": float(losses["loss"]),
             "roofline": {"bound": "tensor", "achieved": flop_step / sec / 1e12 / world, "peak": sustained, "unit": "TFLOP/s per GPU",
                          "frac": flop_step / sec / 1e12 / world / sustained, "peak_source": f"{src} bf16 sustained", "traffic": None,
                          "note": "the dominant training kernels are HBM-bound (10 KB/point activation stash): wgrad runs at 99% of the "
                                  "measured HBM bandwidth (profiles/r01_v15_train_launches.csv, DESIGN.md 3.1b)"}}), flush=True)
     if world > 1:
+        # teardown must never hold the result hostage: the JSON line is out; if destroying the communicator hangs, leave anyway
+        killer = threading.Timer(20.0, os._exit, (0,))
+        killer.daemon = True
+        killer.start()
+        if graphed is not None:
+            graphed.release()
         dist.barrier()
         dist.destroy_process_group()
+        killer.cancel()
 
 
 def run_image(args):

@@ -120,9 +120,16 @@ class GraphedTrainStep:
         self.kw, self.scale, self.shift, self.flat, self.opts = render_kwargs, scale, shift, flat, list(optimizers)
         self.n_global, self.scw, self.thr, self.group, self.warmup = n_global, space_carving_weight, threshold, group, int(warmup)
         self.calls, self.graph, self.static, self.losses = 0, None, None, None
+        self.launches_per_step = None                     # library kernel launches recorded in the graph (diagnostic)
         for o in self.opts:
             if not getattr(o, "capturable", False):
                 raise ValueError("GraphedTrainStep needs FusedAdam(..., capturable=True) optimizers")
+
+    def release(self):
+        """Drop the graph (and its private memory pool).  Call before destroying the process group: a live graph holds captured
+        NCCL work."""
+        torch.cuda.synchronize()
+        self.graph, self.static, self.losses = None, None, None
 
     def _body(self, rb, ts, th):
         for o in self.opts:
@@ -141,9 +148,13 @@ class GraphedTrainStep:
         if self.graph is None:
             self.static = (ray_batch.clone(), target_s.clone(), target_h.clone())
             torch.cuda.synchronize()
+            from . import _lib
+            l0 = _lib.load().scade_kernel_launch_count()
             self.graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.graph):
+            # thread_local: other threads of the process (the NCCL watchdog polling its events) must not invalidate the capture
+            with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
                 self.losses = self._body(*self.static)
+            self.launches_per_step = int(_lib.load().scade_kernel_launch_count() - l0)
             for o in self.opts:
                 o._step -= 1                                 # the capture only recorded the step; the replay below takes it
         else:
