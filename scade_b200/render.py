@@ -224,7 +224,8 @@ class GraphedRenderRays:
         if self.host_outputs and self.out_host is None:
             self.out_host = {k: torch.empty(ret[k].shape, dtype=ret[k].dtype).pin_memory() for k in self.host_outputs}
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph), torch.no_grad():
+        # thread_local: CUDA calls of other threads (e.g. an NCCL watchdog polling its events) must not invalidate the capture
+        with torch.cuda.graph(self.graph, capture_error_mode="thread_local"), torch.no_grad():
             if self.host_outputs:
                 self.rays.copy_(self.rays_host, non_blocking=True)
             self.out = render_rays(self.rays, self.use_viewdirs, **self.kwargs)
