@@ -188,7 +188,7 @@ def render_rays(ray_batch, use_viewdirs, network_fn, network_query_fn, N_samples
 
 class GraphedRenderRays:
     """render_rays (RS:581-751, eval configuration: no autograd, deterministic sampling or injected uniforms) for a FIXED ray
-    count, replayed as one CUDA graph: the 7 kernel launches of the pass, their output allocations and the host-side argument
+    count, replayed as one CUDA graph: the 5 kernel launches of the pass, their output allocations and the host-side argument
     marshalling happen once at construction.  For loops that render many equal-sized chunks (RS:347, batchify_rays).
 
         g = GraphedRenderRays(n_rays, **render_kwargs_test)      # same kwargs as render_rays / create_nerf's dict
@@ -201,7 +201,8 @@ class GraphedRenderRays:
     def __init__(self, n_rays, use_viewdirs=True, device=None, host_outputs=None, **kwargs):
         """host_outputs: names of result tensors to be delivered in pinned host memory.  The graph then also contains the
         host->device copy of `self.rays_host` (pinned, [n_rays, 11]) and the device->host copies into `self.out_host[name]`:
-        fill `rays_host`, call `g()`, synchronise the stream, read `out_host`."""
+        fill `rays_host`, call `g()`, synchronise the stream, read `out_host` (and synchronise before refilling `rays_host`: the
+        copy inside the previous replay reads it asynchronously)."""
         self.n_rays, self.use_viewdirs, self.kwargs = int(n_rays), use_viewdirs, dict(kwargs)
         self.device = device or torch.device("cuda", torch.cuda.current_device())
         self.rays = torch.zeros((self.n_rays, 11), dtype=torch.float32, device=self.device)
