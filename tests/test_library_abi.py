@@ -87,3 +87,21 @@ def test_cpp_host_example_builds_against_the_header():
     r = subprocess.run(["sh", os.path.join(root, "examples", "build.sh")], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
     assert os.path.exists(os.path.join(root, "examples", "render_cabi"))
+
+
+def test_packed_stream_size_follows_the_stage_plan():
+    """scade_mlp_packed_bytes = (forward stages + dgrad stages) x 16 KB + the fp32 tail, for every depth / skip the tensor-core
+    kernel accepts; shapes it does not handle report 0 (the Python side then raises instead of falling back)."""
+    lib = _lib.load()
+    tail, stage = 17408, 16384
+    for D in range(2, 9):
+        for skip in (-1, 0, 2, 4):
+            if skip >= D - 1 and skip != -1:
+                continue                                   # a skip into the last layer is outside the kernel's plan
+            fwd = 2 + sum(10 if (i - 1 == skip) else 8 for i in range(1, D)) + 8 + 6
+            bwd = 4 + 8 + 8 * (D - 1)
+            got = lib.scade_mlp_packed_bytes(ctypes.byref(_lib.NetDesc(D, 256, 9, 0, skip)))
+            assert got == (fwd + bwd) * stage + tail, (D, skip, got)
+    assert lib.scade_mlp_packed_bytes(ctypes.byref(_lib.NetDesc(8, 128, 9, 0, 4))) == 0       # width 128: fp32 path only
+    assert lib.scade_mlp_packed_bytes(ctypes.byref(_lib.NetDesc(8, 256, 10, 0, 4))) == 0      # 63 encoding columns do not fit
+    assert lib.scade_mlp_packed_bytes(ctypes.byref(_lib.NetDesc(8, 256, 9, 2, 4))) == 0       # encoded view directions
