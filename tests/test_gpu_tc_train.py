@@ -244,4 +244,4 @@ def test_graphed_train_step_matches_eager(dev):
     # gradient is ~0 by up to lr per step: the trajectories agree closely in the mean, not bit for bit
     np.testing.assert_allclose(losses, ref_losses, rtol=1e-3)
     diff = (flat.flat.detach() - ref_flat).abs()
-    assert float(diff.mean()) < 2e-6 and float(diff.max()) < 7 * 2e-5 * 2, (float(diff.mean()), float(diff.max()))
+    assert float(diff.mean()) < 2e-6 and float(diff.max()) < 7 * 1e-4 * 2, (float(diff.mean()), float(diff.max()))   # <= 2 lr per step
