@@ -86,3 +86,17 @@ def test_learning_rate_schedule_matches_reference_formula():
     opt = torch.optim.SGD([torch.nn.Parameter(torch.zeros(1))], lr=1.0)
     update_learning_rate(opt, 0.25)
     assert all(g["lr"] == 0.25 for g in opt.param_groups)
+
+
+def test_graphed_train_step_requires_capturable_optimizers():
+    """Host-side contract of scade_b200.dist.GraphedTrainStep (the replay itself is a GPU test): optimizers whose step count
+    lives on the host cannot be recorded in a CUDA graph."""
+    from scade_b200.dist import GraphedTrainStep
+    lin = torch.nn.Linear(4, 4)
+    flat = flatten_parameters(lin)
+    eager = FusedAdam(list(lin.parameters()), lr=1e-3, flat=flat)
+    with pytest.raises(ValueError):
+        GraphedTrainStep({}, None, None, flat, [eager])
+    cap = FusedAdam(list(lin.parameters()), lr=1e-3, flat=flat, capturable=True)
+    step = GraphedTrainStep({}, None, None, flat, [cap], n_global=8, warmup=2)
+    assert step.graph is None and step.calls == 0 and cap.capturable
