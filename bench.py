@@ -45,14 +45,48 @@ def load_peaks():
 
 
 # ------------------------------------------------------------------------------------------------
-# reference arm / cpu baseline: torch-op port of the reference's CPU path (oracle/torch_port.py)
+# reference arm / cpu baseline: the UNMODIFIED reference (baseline/_ref, installed by __graft_entry__.build() from
+# /root/reference) on this box's host cores, in a subprocess whose thread environment is set explicitly (torchrun exports
+# OMP_NUM_THREADS=1 to its ranks).  Only if the reference did not travel: the torch-op port under oracle/.
 # ------------------------------------------------------------------------------------------------
-def cpu_arm(n_rays_sample, steps, warmup):
+def workload_config():
+    """`config` of the JSON line -- identical in both arms (the driver compares them)."""
+    return {"workload": WORKLOAD, "rays_per_step": N_RAYS, "samples": f"{N_COARSE}c+{N_FINE}f", "net": f"{NET_D}x{NET_W} x2",
+            "rays": "synthetic.make_ray_batch(4096, seed=50): 640x480 pinhole camera, near 0.1, far 5.0",
+            "weights": "Xavier-uniform random init (synthetic.make_nerf_params, seeds 10/11)", "sampling": "perturb=0 (deterministic)"}
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def cpu_arm(n_rays, steps, warmup):
+    cores = host_cores()
+    env = dict(os.environ)
+    for k in ("OMP_NUM_THREADS", "MKL_NUM_THREADS", "OPENBLAS_NUM_THREADS", "NUMEXPR_NUM_THREADS"):
+        env[k] = str(cores)
+    env["CUDA_VISIBLE_DEVICES"] = ""                     # the reference arm is the CPU path
+    script = os.path.join(ROOT, "baseline", "reference_arm.py")
+    sys.path.insert(0, os.path.join(ROOT, "baseline"))
+    import reference_arm
+    if reference_arm.locate() is not None:
+        r = subprocess.run([sys.executable, script, "--rays", str(n_rays), "--steps", str(steps), "--warmup", str(warmup),
+                            "--threads", str(cores)], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+        for line in reversed(r.stdout.strip().splitlines()):
+            if line.startswith("{"):
+                return json.loads(line)
+        sys.stderr.write("bench.py: reference arm failed, falling back to the oracle port\n" + r.stderr[-2000:] + "\n")
+    return cpu_arm_port(n_rays, steps, warmup, cores)
+
+
+def cpu_arm_port(n_rays_sample, steps, warmup, cores):
     import torch
     from oracle import torch_port as TP
     from scade_b200 import synthetic as syn
     from tests.golden.generate_goldens import net_pair
-    cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     pc, pf = net_pair(NET_D, NET_W)
     pc = {k: torch.from_numpy(v) for k, v in pc.items()}
@@ -71,19 +105,22 @@ def cpu_arm(n_rays_sample, steps, warmup):
     sec = float(np.mean(times))
     return {"value": n_rays_sample / sec, "unit": "rays/s", "cores": cores, "kind": "port",
             "sample": f"{n_rays_sample} of {N_RAYS} rays of the same workload per step, {steps} steps after {warmup} warm-up, "
-                      f"torch {torch.__version__} CPU fp32, {cores} threads (oracle/torch_port.py)",
+                      f"torch {torch.__version__} CPU fp32, {cores} threads (oracle/torch_port.py; the reference was not found)",
             "sec_per_step": sec}
 
 
 def run_reference(args):
+    """`--impl reference`: the reference's own CPU implementation on the host cores, the FULL 4096-ray workload per step.
+    Steps are bounded (a step is ~3-12 s of CPU work) so that the run ends within a few minutes."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    base = cpu_arm(256, max(1, min(args.steps, 5)), 1)
+    steps, warmup = max(1, min(args.steps, 5)), max(1, min(args.warmup, 1))
+    base = cpu_arm(N_RAYS, steps, warmup)
     line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": "rays/s", "n_gpus": args.gpus,
-            "steps": max(1, min(args.steps, 5)), "warmup": 1, "ms_per_step": base["sec_per_step"] * 1e3,
+            "steps": steps, "warmup": warmup, "ms_per_step": base["sec_per_step"] * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD}, "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "config": workload_config(), "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": base["value"], "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -264,6 +301,13 @@ def run_gpu(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dev_ms, e2e_ms = float(t[0]), float(t[1])
 
+    # ---- the path that has the collective: BASELINE config 3 train step, the 4096 rays split across the ranks ----
+    train_rec = None
+    if not args.no_train:
+        graphed.graph, graphed.out, flush = None, None, None      # free the render graph's pool before the train step allocates its stash
+        torch.cuda.empty_cache()
+        train_rec = measure_train(args, dev, rank, world, args.steps)
+
     if rank == 0:
         burst, sustained, hbm, src = load_peaks()
         total_rays = N_RAYS * world * args.steps
@@ -279,9 +323,10 @@ def run_gpu(args):
             "metric": METRIC, "value": total_rays / (dev_ms * 1e-3), "unit": "rays/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f16 operands / f32 accumulate (tcgen05)" if is_tc else "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "rays_per_gpu": N_RAYS, "precision": prec, "parallelism": f"rays x{world}",
-                       "l2": "flushed between steps (256 MiB memset, untimed); weights (2.3 MB fp16) are meant to be L2-resident",
-                       "weights": "Xavier-uniform random init (synthetic.make_nerf_params)"},
+            "config": workload_config(),
+            "arm": {"precision": prec, "rays_per_gpu": N_RAYS, "parallelism": f"rays x{world} (every rank renders its own 4096 rays, "
+                    "no data-path collective)",
+                    "l2": "flushed between steps (256 MiB memset, untimed); weights (2.3 MB fp16) are meant to be L2-resident"},
             "e2e": {"value": total_rays / (e2e_ms * 1e-3), "unit": "rays/s", "h2d_bytes_per_step": int(rb_host.numel() * 4),
                     "d2h_bytes_per_step": int(sum(b.numel() * 4 for b in out_host.values())),
                     "api": "scade_b200.render.GraphedRenderRays (render_rays for a fixed chunk size replayed as one CUDA graph that "
@@ -300,30 +345,26 @@ def run_gpu(args):
                          / (dev_ms / args.steps * 1e-3) / 1e12 / sustained},
             "clocks": clocks,
         }
+        if train_rec is not None:
+            line["train"] = train_rec
         if not args.no_cpu_baseline:
-            base = cpu_arm(256, 2, 1)
+            base = cpu_arm(N_RAYS, 2, 1)
             line["cpu_baseline"] = {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")}
         print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+    finish(world)
 
 
-def run_train(args):
+def measure_train(args, dev, rank, world, steps):
     """BASELINE config 3: train step on 4096 rays (global), 64 coarse + 128 importance, K=20 hypotheses:
-    forward + losses + backward + ONE NCCL all-reduce of the flat gradient buffer + Adam (RS:954-997).
-    Strong scaling: the 4096 rays of the step are split across ranks."""
+    forward + losses + backward + the NCCL all-reduce of the flat gradient buffer + Adam (RS:954-997).
+    Strong scaling: the 4096 rays of the step are split across ranks.  The process group (world > 1) is the caller's.
+    Returns the record on rank 0 (None elsewhere)."""
     import torch
     import torch.distributed as dist
     from scade_b200 import nerf_helpers as NH, render as R_, synthetic as syn
     from scade_b200 import _lib
     from scade_b200.dist import shard_range, sharded_train_step
     from tests.golden.generate_goldens import net_pair
-    rank, world, local = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
     N, Nc, Nf, K = 4096, 64, 128, 20
     pc, pf = net_pair(NET_D, NET_W)
@@ -378,7 +419,7 @@ def run_train(args):
     l0 = lib.scade_kernel_launch_count()
     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     s.record()
-    for _ in range(args.steps):
+    for _ in range(steps):
         losses = step()
     e.record()
     if world > 1:
@@ -387,33 +428,57 @@ def run_train(args):
     ms = torch.tensor([s.elapsed_time(e)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    rec = None
     if rank == 0:
-        flop_step = N * (Nc + Nc + Nf) * 3464448          # SURVEY §8(d): fwd + dgrad + wgrad per evaluation
+        flop_step = N * (Nc + Nc + Nf) * 3464448          # SURVEY 8(d): fwd + dgrad + wgrad per evaluation
         burst, sustained, _, src = load_peaks()
-        sec = float(ms) * 1e-3 / args.steps
-        print(json.dumps({
+        sec = float(ms) * 1e-3 / steps
+        rec = {
             "metric": "train rays/sec (4096 rays, 64c+128f, K=20, fwd+loss+bwd+allreduce+Adam)", "value": N / sec, "unit": "rays/s",
-            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": sec * 1e3, "higher_is_better": True,
+            "n_gpus": world, "steps": steps, "warmup": max(args.warmup, 3), "ms_per_step": sec * 1e3, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None,
             "dtype": "f16 operands / f32 accumulate (tcgen05 fwd+dgrad+wgrad)" if args.precision == "tc_f16" else "f32", "data": "synthetic",
-            "config": {"workload": "BASELINE config 3 train step", "global_rays": N,
+            "config": {"workload": "BASELINE config 3 train step", "global_rays": N, "rays_per_gpu": hi - lo,
                        "precision": "tcgen05 fwd + dgrad + wgrad, fp32 master weights / gradients / Adam" if args.precision == "tc_f16"
                        else "fp32 FFMA GEMMs (fwd+bwd)",
-                       "collective": "1 NCCL all-reduce / step, flat fp32 buffer 4.72 MB", "optimizer": args.optimizer,
+                       "collective": "NCCL all-reduce of the flat fp32 gradient buffer, fine-net bucket overlapped with the coarse-net backward"
+                       if world > 1 else "none (1 GPU)",
+                       "allreduce_bytes_per_step": int(flat.flat_grad.numel() * 4) if flat is not None else None,
+                       "optimizer": args.optimizer,
                        "launch": "one CUDA graph per step (scade_b200.dist.GraphedTrainStep)" if graphed is not None else "eager"},
-            "gpu_launches": int(lib.scade_kernel_launch_count() - l0) if graphed is None else int(graphed.launches_per_step * args.steps),
+            "gpu_launches": int(lib.scade_kernel_launch_count() - l0) if graphed is None else int(graphed.launches_per_step * steps),
             "loss": float(losses["loss"]),
             "roofline": {"bound": "tensor", "achieved": flop_step / sec / 1e12 / world, "peak": sustained, "unit": "TFLOP/s per GPU",
                          "frac": flop_step / sec / 1e12 / world / sustained, "peak_source": f"{src} bf16 sustained", "traffic": None,
                          "note": "the dominant training kernels are HBM-bound (10 KB/point activation stash): wgrad runs at 99% of the "
-                                 "measured HBM bandwidth (profiles/r01_v15_train_launches.csv, DESIGN.md 3.1b)"}}), flush=True)
+                                 "measured HBM bandwidth (profiles/r01_v15_train_launches.csv, DESIGN.md 3.1b)"}}
+    if graphed is not None:
+        graphed.release()                                   # a live graph holds captured NCCL work: drop it before the group goes
+    return rec
+
+
+def run_train(args):
+    import torch
+    import torch.distributed as dist
+    rank, world, local = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
     if world > 1:
-        # teardown must never hold the result hostage: the JSON line is out; if destroying the communicator hangs, leave anyway
+        dist.init_process_group("nccl", device_id=dev)
+    rec = measure_train(args, dev, rank, world, args.steps)
+    if rank == 0:
+        print(json.dumps(rec), flush=True)
+    finish(world)
+
+
+def finish(world):
+    """Tear the process group down without ever holding the result hostage: the JSON line is out; if destroying the
+    communicator hangs, leave anyway."""
+    if world > 1:
+        import torch.distributed as dist
         killer = threading.Timer(20.0, os._exit, (0,))
         killer.daemon = True
         killer.start()
-        if graphed is not None:
-            graphed.release()
         dist.barrier()
         dist.destroy_process_group()
         killer.cancel()
@@ -527,6 +592,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default="tc_f16", choices=["tc_f16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="render workload: skip the attached config-3 train-step record")
     ap.add_argument("--optimizer", default="fused", choices=["fused", "torch"],
                     help="train workload: fused = flat parameters + scade_adam_step (default); torch = torch.optim.Adam on 48 tensors")
     ap.add_argument("--train-graph", type=int, default=1, help="train workload: replay the step as one CUDA graph (0 = eager)")

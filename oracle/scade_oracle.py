@@ -433,10 +433,14 @@ def make_ray_batch(rays_o, rays_d, near, far, dtype=F32):
 def render_rays(ray_batch, params_coarse, params_fine, bb_center, bb_scale, N_samples, N_importance,
                 perturb=0.0, t_rand=None, u_coarse=None, u_fine=None, lindisp=False,
                 multires=9, multires_views=0, skips=(4,), is_joint=False, retraw=False,
-                dtype=F32, mlp=None):
+                dtype=F32, mlp=None, z_fine=None):
     """Returns the same dict as the reference (RS:733-744).  Random draws are explicit:
     t_rand [N,Nc] (RS:570), u_coarse [N,Nimp] (H:350 in the RS:705 call), u_fine = cached_u
-    (RS:726).  ``mlp`` optionally replaces run_network (used to emulate operand rounding)."""
+    (RS:726).  ``mlp`` optionally replaces run_network (used to emulate operand rounding).
+    ``z_fine`` [N,Nc+Nimp] (test infrastructure) teacher-forces the merged sample positions of RS:713:
+    the fine pass is then evaluated at exactly the positions another implementation chose, which
+    removes the (discontinuous, noise-amplifying) inverse-CDF resampling from a comparison of the
+    fine network, its compositing and its gradients."""
     rb = np.asarray(ray_batch, dtype)
     rays_o, rays_d = rb[:, 0:3], rb[:, 3:6]                                          # RS:628
     viewdirs = rb[:, 8:11]                                                           # RS:632
@@ -457,6 +461,8 @@ def render_rays(ray_batch, params_coarse, params_fine, bb_center, bb_scale, N_sa
     z_samples, _ = sample_pdf(mid, w0[:, 1:-1], N_importance, det=det,
                               u=None if det else u_coarse, dtype=dtype)              # RS:705
     z_vals = np.sort(np.concatenate([z_vals, z_samples], -1), -1)                    # RS:713
+    if z_fine is not None:
+        z_vals = np.asarray(z_fine, dtype)
     pts = rays_o[:, None, :] + rays_d[:, None, :] * z_vals[:, :, None]               # RS:714
     raw = net(pts, params_fine)                                                      # RS:718
     rgb, disp, acc, w, depth = raw2outputs(raw, z_vals, rays_d, 0.0, dtype)          # RS:720
@@ -476,7 +482,7 @@ def render_rays(ray_batch, params_coarse, params_fine, bb_center, bb_scale, N_sa
 def train_loss_and_grads(ray_batch, params_coarse, params_fine, bb_center, bb_scale, N_samples,
                          N_importance, target_s, target_h, t_rand, u_coarse, u_fine,
                          space_carving_weight=0.007, scale=1.0, shift=0.0, mask=None,
-                         threshold=0.0, multires=9, multires_views=0, skips=(4,), dtype=F32):
+                         threshold=0.0, multires=9, multires_views=0, skips=(4,), dtype=F32, z_fine=None):
     """One training step's loss and gradients (RS:954-985): loss = mse(rgb) + w_sc * space_carving
     + mse(rgb0).  Gradient reach follows the reference's autograd graph: the fine net gets grads from
     the fine MSE and from space carving through sample_pdf_return_u; the coarse net only from the
@@ -488,7 +494,7 @@ def train_loss_and_grads(ray_batch, params_coarse, params_fine, bb_center, bb_sc
     out = render_rays(rb, params_coarse, params_fine, bb_center, bb_scale, N_samples, N_importance,
                       perturb=1.0, t_rand=t_rand, u_coarse=u_coarse, u_fine=u_fine,
                       multires=multires, multires_views=multires_views, skips=skips, retraw=True,
-                      dtype=dtype)
+                      dtype=dtype, z_fine=z_fine)
     target_s = np.asarray(target_s, dtype)
     h_raw = np.asarray(target_h, dtype)
     h = h_raw * dtype(scale) + dtype(shift)                                          # RS:954
@@ -527,26 +533,37 @@ def train_loss_and_grads(ray_batch, params_coarse, params_fine, bb_center, bb_sc
 # --------------------------------------------------------------------------------------
 # operand-rounding emulation (documents the tensor-core mode's tolerance)
 # --------------------------------------------------------------------------------------
-def nerf_forward_f16(params, x, input_ch=57, skips=(4,)):
-    """The MLP as the tcgen05 kernel computes it: activations and weights of the wide layers rounded
+def nerf_forward_f16(params, x, input_ch=57, skips=(4,), split=False):
+    """The MLP as the tcgen05 kernels compute it: activations and weights of the wide layers rounded
     to fp16 before an fp32-accumulated product; bias/ReLU in fp32; alpha and rgb heads as fp32 dot
-    products of the UNROUNDED fp32 activations.  Used only to set/explain test tolerances."""
+    products of the UNROUNDED fp32 activations.  ``split=True`` emulates the tight mode
+    (SCADE_PREC_TC_F16X3): every operand is an fp16 (hi, lo) pair with lo = fp16(x - hi), and the product
+    is hi*hi + lo*hi + hi*lo (three tensor-core passes; the lo*lo term, ~2^-22 relative, is dropped).
+    Used only to set/explain test tolerances."""
     r16 = lambda a: np.asarray(a, np.float32).astype(np.float16).astype(np.float32)
+
+    def mm(a, w):
+        a, w = np.asarray(a, np.float32), np.asarray(w, np.float32)
+        ah, wh = r16(a).astype(np.float64), r16(w).astype(np.float64)
+        if not split:
+            return (ah @ wh.T).astype(np.float32)
+        al = r16(a - ah.astype(np.float32)).astype(np.float64)
+        wl = r16(w - wh.astype(np.float32)).astype(np.float64)
+        return (ah @ wh.T + al @ wh.T + ah @ wl.T).astype(np.float32)
     p = {k: np.asarray(v, np.float32) for k, v in params.items()}
     D = _num_pts_layers(p)
     x = np.asarray(x, np.float32)
     input_pts, input_views = x[:, :input_ch], x[:, input_ch:]
     h = input_pts
     for i in range(D):
-        z = (r16(h).astype(np.float64) @ r16(p[f"pts_linears.{i}.weight"]).T.astype(np.float64)).astype(np.float32)
+        z = mm(h, p[f"pts_linears.{i}.weight"])
         h = np.maximum(z + p[f"pts_linears.{i}.bias"], 0)
         if i in skips:
             h = np.concatenate([input_pts, h], -1)
     alpha = h @ p["alpha_linear.weight"].T + p["alpha_linear.bias"]
-    feature = (r16(h).astype(np.float64) @ r16(p["feature_linear.weight"]).T.astype(np.float64)).astype(np.float32) \
-        + p["feature_linear.bias"]
+    feature = mm(h, p["feature_linear.weight"]) + p["feature_linear.bias"]
     hv_in = np.concatenate([feature, input_views], -1)
-    zv = (r16(hv_in).astype(np.float64) @ r16(p["views_linears.0.weight"]).T.astype(np.float64)).astype(np.float32)
+    zv = mm(hv_in, p["views_linears.0.weight"])
     hv = np.maximum(zv + p["views_linears.0.bias"], 0)
     rgb = hv @ p["rgb_linear.weight"].T + p["rgb_linear.bias"]
     return np.concatenate([rgb, softplus_beta10(alpha)], -1).astype(np.float32)
