@@ -318,11 +318,14 @@ def run_gpu(args):
         if os.path.exists(tpath):
             with open(tpath) as f:
                 traffic = json.load(f).get("mlp_fine_dram_bytes_per_launch")
-        is_tc = prec == "tc_f16"
+        is_tc = prec in ("tc_f16", "tc_f16x3")
+        dtype = {"tc_f16": "f16 operands / f32 accumulate (tcgen05)", "fp32": "f32",
+                 "tc_f16x3": "f16 hi/lo operand pairs, 3 tcgen05 passes / f32 accumulate (fp32-level tolerance)"}[prec]
+        kernel = {"tc_f16": "nerf_mlp_tc_pp_kernel", "tc_f16x3": "nerf_mlp_tc_x3_kernel", "fp32": "sgemm_kernel chain"}[prec]
         line = {
             "metric": METRIC, "value": total_rays / (dev_ms * 1e-3), "unit": "rays/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f16 operands / f32 accumulate (tcgen05)" if is_tc else "f32", "data": "synthetic",
+            "vs_baseline": None, "dtype": dtype, "data": "synthetic",
             "config": workload_config(),
             "arm": {"precision": prec, "rays_per_gpu": N_RAYS, "parallelism": f"rays x{world} (every rank renders its own 4096 rays, "
                     "no data-path collective)",
@@ -336,8 +339,7 @@ def run_gpu(args):
                     "eager_api": "scade_b200.render.render_rays called eagerly every step (same copies; rank-0 clock)"},
             "gpu_launches": int(launches),
             "wall_ms_timed_region": wall * 1e3,
-            "roofline": {"bound": "tensor", "kernel": "nerf_mlp_tc_pp_kernel (fine pass, 4096x256 points)" if is_tc
-                         else "sgemm_kernel chain (fine pass)",
+            "roofline": {"bound": "tensor", "kernel": f"{kernel} (fine pass, 4096x256 points)",
                          "achieved": achieved, "peak": burst, "unit": "TFLOP/s", "frac": achieved / burst,
                          "peak_source": f"{src} bf16 dense burst (kernel timed alone)", "traffic": traffic,
                          "flop_per_launch": flop_launch, "ms_per_launch": mlp_ms,
@@ -590,7 +592,9 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default="tc_f16", choices=["tc_f16", "fp32"])
+    ap.add_argument("--precision", default="tc_f16", choices=["tc_f16", "tc_f16x3", "fp32"],
+                    help="tc_f16 = tcgen05, fp16 operands (fast, default); tc_f16x3 = tcgen05 at an fp32-level tolerance (fp16 hi/lo operand "
+                         "pairs, three MMA passes); fp32 = FFMA GEMMs (the reference's arithmetic)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train", action="store_true", help="render workload: skip the attached config-3 train-step record")
     ap.add_argument("--optimizer", default="fused", choices=["fused", "torch"],

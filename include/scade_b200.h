@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define SCADE_B200_VERSION 100
+#define SCADE_B200_VERSION 101
 
 typedef enum {
   SCADE_OK = 0,
@@ -37,7 +37,9 @@ typedef enum {
 /* Arithmetic used for the MLP's wide layers. */
 typedef enum {
   SCADE_PREC_FP32 = 0,   /* fp32 FFMA GEMMs: the reference's own arithmetic (cuBLAS SGEMM / MKL) */
-  SCADE_PREC_TC_F16 = 1  /* tcgen05 tensor cores, fp16 operands, fp32 accumulate in TMEM */
+  SCADE_PREC_TC_F16 = 1, /* tcgen05 tensor cores, fp16 operands, fp32 accumulate in TMEM (fast mode; forward + backward) */
+  SCADE_PREC_TC_F16X3 = 2 /* tcgen05 tensor cores at an fp32-level tolerance: every operand an fp16 (hi, lo) pair, three MMA
+                             passes per product (hi*hi + lo*hi + hi*lo) into one fp32 accumulator (tight mode; forward only) */
 } scade_precision;
 
 int scade_version(void);
@@ -65,7 +67,8 @@ typedef struct {
 typedef struct {
   scade_net_desc desc;
   const float* params[SCADE_MAX_PARAM_TENSORS]; /* HOST array of DEVICE pointers (fp32 master weights) */
-  const void* packed_f16;                       /* DEVICE buffer written by scade_mlp_pack_f16, or NULL */
+  const void* packed_f16;                       /* DEVICE buffer written by scade_mlp_pack_f16 / scade_mlp_pack for the
+                                                   precision the net is used with, or NULL */
 } scade_net;
 
 /* Bytes of the fp16 tile image used by SCADE_PREC_TC_F16 (0 if the shape is unsupported there). */
@@ -74,6 +77,12 @@ size_t scade_mlp_packed_bytes(const scade_net_desc* desc);
  * bulk-copies (call after every optimizer step).  Replaces nothing in the reference: torch keeps
  * fp32 weights and cuBLAS reads them directly (H:131, H:227). */
 int scade_mlp_pack_f16(const scade_net* net, void* packed_out, void* stream);
+
+/* The same two calls for a given tensor-core precision: SCADE_PREC_TC_F16 (identical to the two above) or
+ * SCADE_PREC_TC_F16X3, whose stream interleaves a W_hi and a W_lo = fp16(w - W_hi) stage per K stage.  A scade_net used with
+ * SCADE_PREC_TC_F16X3 points packed_f16 at a buffer packed for that precision. */
+size_t scade_mlp_packed_bytes_for(const scade_net_desc* desc, int precision);
+int scade_mlp_pack(const scade_net* net, int precision, void* packed_out, void* stream);
 
 /* Workspace bytes for scade_mlp_forward* on P points; save_for_backward adds the activation stash. */
 size_t scade_mlp_workspace_bytes(const scade_net_desc* desc, int64_t P, int precision, int save_for_backward);

@@ -16,6 +16,7 @@ from . import build as _build
 MAX_PARAM_TENSORS = 40
 PREC_FP32 = 0
 PREC_TC_F16 = 1
+PREC_TC_F16X3 = 2
 
 
 class NetDesc(Structure):
@@ -50,6 +51,8 @@ _SIGNATURES = {
     "scade_kernel_launch_count": (ctypes.c_uint64, []),
     "scade_mlp_packed_bytes": (c_size_t, [POINTER(NetDesc)]),
     "scade_mlp_pack_f16": (c_int, [POINTER(Net), _P, _P]),
+    "scade_mlp_packed_bytes_for": (c_size_t, [POINTER(NetDesc), c_int]),
+    "scade_mlp_pack": (c_int, [POINTER(Net), c_int, _P, _P]),
     "scade_mlp_workspace_bytes": (c_size_t, [POINTER(NetDesc), c_int64, c_int, c_int]),
     "scade_mlp_forward_rays": (c_int, [POINTER(Net), c_int, _P, c_int, _P, c_int64, c_int, POINTER(c_float), c_float,
                                        _P, _P, c_size_t, c_int, _P]),

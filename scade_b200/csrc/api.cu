@@ -31,13 +31,13 @@ static int check_net(const scade_net* net, int precision) {
   SCADE_CHECK_ARG(net != nullptr, "null network");
   SCADE_TRY(check_desc(net->desc));
   for (int i = 0; i < num_param_tensors(net->desc); ++i) SCADE_CHECK_ARG(net->params[i] != nullptr, "null parameter tensor %d", i);
-  if (precision == SCADE_PREC_TC_F16) {
+  if (precision == SCADE_PREC_TC_F16 || precision == SCADE_PREC_TC_F16X3) {
     if (!mlp_tc_supported(net->desc)) {
-      set_error("SCADE_PREC_TC_F16 supports W=256, 2<=D<=8, 3+6*multires+3+6*multires_views<=64; got D=%d W=%d", net->desc.D,
+      set_error("the tensor-core precisions support W=256, 2<=D<=8, 3+6*multires+3+6*multires_views<=60; got D=%d W=%d", net->desc.D,
                 net->desc.W);
       return SCADE_ERR_UNSUPPORTED;
     }
-    SCADE_CHECK_ARG(net->packed_f16 != nullptr, "SCADE_PREC_TC_F16 needs packed_f16 (call scade_mlp_pack_f16)");
+    SCADE_CHECK_ARG(net->packed_f16 != nullptr, "the tensor-core precisions need packed_f16 (call scade_mlp_pack)");
   } else {
     SCADE_CHECK_ARG(precision == SCADE_PREC_FP32, "unknown precision %d", precision);
   }
@@ -68,10 +68,29 @@ extern "C" int scade_mlp_pack_f16(const scade_net* net, void* packed_out, void* 
   return mlp_tc_pack(*net, packed_out, as_stream(stream));
 }
 
+extern "C" size_t scade_mlp_packed_bytes_for(const scade_net_desc* desc, int precision) {
+  if (!desc || check_desc(*desc) != SCADE_OK || !mlp_tc_supported(*desc)) return 0;
+  if (precision != SCADE_PREC_TC_F16 && precision != SCADE_PREC_TC_F16X3) return 0;
+  return mlp_tc_packed_bytes(*desc, precision == SCADE_PREC_TC_F16X3);
+}
+
+extern "C" int scade_mlp_pack(const scade_net* net, int precision, void* packed_out, void* stream) {
+  SCADE_CHECK_ARG(net && packed_out, "mlp_pack: null argument");
+  SCADE_CHECK_ARG(precision == SCADE_PREC_TC_F16 || precision == SCADE_PREC_TC_F16X3, "mlp_pack: precision %d has no packed stream", precision);
+  SCADE_TRY(check_desc(net->desc));
+  if (!mlp_tc_supported(net->desc)) {
+    set_error("mlp_pack: shape not supported by the tensor-core path");
+    return SCADE_ERR_UNSUPPORTED;
+  }
+  for (int i = 0; i < num_param_tensors(net->desc); ++i) SCADE_CHECK_ARG(net->params[i] != nullptr, "null parameter tensor %d", i);
+  return mlp_tc_pack(*net, packed_out, as_stream(stream), precision == SCADE_PREC_TC_F16X3);
+}
+
 extern "C" size_t scade_mlp_workspace_bytes(const scade_net_desc* desc, int64_t P, int precision, int save_for_backward) {
   if (!desc || check_desc(*desc) != SCADE_OK || P < 0) return 0;
   if (P == 0) return 256;
   if (precision == SCADE_PREC_TC_F16) return mlp_tc_workspace_bytes(*desc, P, save_for_backward);
+  if (precision == SCADE_PREC_TC_F16X3) return 256;
   return mlp_fp32_workspace_bytes(*desc, P, save_for_backward);
 }
 
@@ -86,9 +105,9 @@ extern "C" int scade_mlp_forward_rays(const scade_net* net, int precision, const
   SCADE_CHECK_ARG((reinterpret_cast<uintptr_t>(raw_out) & 15) == 0, "mlp_forward_rays: raw_out must be 16-byte aligned");
   if (N == 0) return SCADE_OK;
   SCADE_CHECK_ARG(workspace != nullptr, "mlp_forward_rays: null workspace");
-  if (precision == SCADE_PREC_TC_F16)
+  if (precision == SCADE_PREC_TC_F16 || precision == SCADE_PREC_TC_F16X3)
     return mlp_tc_forward(*net, rays, ray_stride, z_vals, nullptr, N, S, bb_center_host, bb_scale, raw_out, workspace,
-                          workspace_bytes, save_for_backward, as_stream(stream));
+                          workspace_bytes, save_for_backward, as_stream(stream), precision == SCADE_PREC_TC_F16X3);
   return mlp_fp32_forward_rays(*net, rays, ray_stride, z_vals, N, S, bb_center_host, bb_scale, raw_out, workspace,
                                workspace_bytes, save_for_backward, as_stream(stream));
 }
@@ -101,9 +120,9 @@ extern "C" int scade_mlp_forward_embedded(const scade_net* net, int precision, c
   SCADE_CHECK_ARG((reinterpret_cast<uintptr_t>(out) & 15) == 0, "mlp_forward_embedded: out must be 16-byte aligned");
   if (P == 0) return SCADE_OK;
   SCADE_CHECK_ARG(workspace != nullptr, "mlp_forward_embedded: null workspace");
-  if (precision == SCADE_PREC_TC_F16)
+  if (precision == SCADE_PREC_TC_F16 || precision == SCADE_PREC_TC_F16X3)
     return mlp_tc_forward(*net, nullptr, 0, nullptr, x, P, 1, nullptr, 1.0f, out, workspace, workspace_bytes,
-                          save_for_backward, as_stream(stream));
+                          save_for_backward, as_stream(stream), precision == SCADE_PREC_TC_F16X3);
   return mlp_fp32_forward_embedded(*net, x, P, out, workspace, workspace_bytes, save_for_backward, as_stream(stream));
 }
 
@@ -114,6 +133,10 @@ extern "C" int scade_mlp_backward(const scade_net* net, int precision, const flo
   SCADE_CHECK_ARG((reinterpret_cast<uintptr_t>(d_out) & 15) == 0, "mlp_backward: d_out must be 16-byte aligned");
   for (int i = 0; i < num_param_tensors(net->desc); ++i) SCADE_CHECK_ARG(grads_host[i] != nullptr, "null gradient tensor %d", i);
   if (P == 0) return SCADE_OK;
+  if (precision == SCADE_PREC_TC_F16X3) {
+    set_error("mlp_backward: SCADE_PREC_TC_F16X3 is forward-only");
+    return SCADE_ERR_UNSUPPORTED;
+  }
   if (precision == SCADE_PREC_TC_F16) return mlp_tc_backward(*net, d_out, P, grads_host, workspace, workspace_bytes, as_stream(stream));
   return mlp_fp32_backward(*net, d_out, P, grads_host, workspace, workspace_bytes, as_stream(stream));
 }

@@ -38,12 +38,12 @@ int embed_launch(const float* x, int64_t P, int multires, float* out, cudaStream
 
 // entry points implemented in mlp_tc.cu (tcgen05 path)
 bool mlp_tc_supported(const scade_net_desc& d);
-size_t mlp_tc_packed_bytes(const scade_net_desc& d);
-int mlp_tc_pack(const scade_net& net, void* packed_out, cudaStream_t st);
+size_t mlp_tc_packed_bytes(const scade_net_desc& d, bool x3 = false);
+int mlp_tc_pack(const scade_net& net, void* packed_out, cudaStream_t st, bool x3 = false);
 size_t mlp_tc_workspace_bytes(const scade_net_desc& d, int64_t P, int save);
 int mlp_tc_forward(const scade_net& net, const float* rays, int ray_stride, const float* z, const float* x_embedded,
                    int64_t N, int S, const float* bb_center, float bb_scale, float* raw_out, void* workspace,
-                   size_t ws_bytes, int save, cudaStream_t st);
+                   size_t ws_bytes, int save, cudaStream_t st, bool x3 = false);
 
 int mlp_tc_backward(const scade_net& net, const float* d_out, int64_t P, float* const* grads, void* workspace, size_t ws_bytes,
                     cudaStream_t st);

@@ -52,7 +52,7 @@ constexpr int STAGE_BYTES = STAGE_N * KCHUNK * 2;   // 16 KB
 constexpr int CHUNK_BYTES = TILE_M * KCHUNK * 2;    // 16 KB
 constexpr int NUM_STAGES = 4;
 constexpr int MAX_LAYERS = 12;           // D (<= 8) + feature + views
-constexpr int MAX_STAGE_DESCS = 96;
+constexpr int MAX_STAGE_DESCS = 160;         // the hi/lo stream of SCADE_PREC_TC_F16X3 has 148 stages for 8x256
 
 // shared-memory map (relative to a 1024-byte aligned base)
 constexpr int OFF_A = 0;                                 // [TILES][4 chunks]
@@ -110,6 +110,7 @@ struct StageDesc {
   const float* bias;
   int trans;                          // 1: element (n, k) = W[(col0 + k) * ld + row0 + n]  (dgrad: B = W^T)
   int n_blocks;
+  int lo;                             // 1: the stage holds the fp16 residuals fp16(w - fp16(w)) (SCADE_PREC_TC_F16X3), zeros at bias positions
   StageBlock blk[2];
 };
 struct PackPlan {
@@ -802,13 +803,17 @@ __global__ void pack_kernel(const __grid_constant__ PackPlan plan, uint8_t* __re
         continue;
       }
       const int sc = k - b.dst_col0;
-      if (sc >= 0 && sc < b.ncols)
-        hv = __float2half_rn(sd.trans ? sd.W[(int64_t)(b.col0 + sc) * sd.ld + sd.row0 + bn]
-                                      : sd.W[(int64_t)(sd.row0 + bn) * sd.ld + b.col0 + sc]);
+      if (sc >= 0 && sc < b.ncols) {
+        const float w = sd.trans ? sd.W[(int64_t)(b.col0 + sc) * sd.ld + sd.row0 + bn]
+                                 : sd.W[(int64_t)(sd.row0 + bn) * sd.ld + b.col0 + sc];
+        __half hi, lo;
+        split_f16(w, &hi, &lo);
+        hv = sd.lo ? lo : hi;
+      }
       if (b.bias_mode == 1 && (k == ONES_COL || k == ONES_COL + 1)) {
         __half hi, lo;
         split_f16(sd.bias[sd.row0 + bn], &hi, &lo);
-        hv = (k == ONES_COL) ? hi : lo;
+        hv = sd.lo ? __float2half_rn(0.f) : ((k == ONES_COL) ? hi : lo);      // both bias halves ride in the W_hi stage
       }
     }
     uint32_t off = sw128_offset(n, k >> 3) + (k & 7) * 2;
@@ -818,7 +823,7 @@ __global__ void pack_kernel(const __grid_constant__ PackPlan plan, uint8_t* __re
 
 // Build the layer table and the stage list for a network description.  Stage order = consumption order:
 // layer -> ring stage -> CTA (CTA 0's N half, CTA 1's N half).  A ring stage holds `kpack` K chunks of one CTA's N half.
-static void build_plans(const scade_net& net, NetPlan* np, PackPlan* pp) {
+static void build_plans(const scade_net& net, NetPlan* np, PackPlan* pp, bool x3 = false) {
   const scade_net_desc& d = net.desc;
   NetDims nd(d);
   NetPlan P{};
@@ -843,9 +848,10 @@ static void build_plans(const scade_net& net, NetPlan* np, PackPlan* pp) {
     L.emb_ks0 = with_emb ? emb_dst / 16 : 0;                   // K steps below the first mapped column hold only zero weights
     const int n_own = (nk + L.kpack - 1) / L.kpack;
     for (int i = 0; i < n_own; ++i)
+      for (int rep = 0; rep < (x3 ? 2 : 1); ++rep)              // x3: (W_hi stage, W_lo stage) per ring stage
       for (int h = 0; h < 2; ++h) {
         StageDesc s{};
-        s.W = Wt; s.ld = fan_in; s.row0 = h * rows; s.bias = bias; s.trans = 0;
+        s.W = Wt; s.ld = fan_in; s.row0 = h * rows; s.bias = bias; s.trans = 0; s.lo = rep;
         for (int j = 0; j < L.kpack; ++j) {
           const int kc = i * L.kpack + j;
           if (kc >= nk) break;
@@ -894,6 +900,7 @@ static int count_stages(const scade_net_desc& d) {
 
 
 #include "mlp_tc_train.cuh"
+#include "mlp_tc_x3.cuh"
 
 // ---- training: backward stream, stash layout ---------------------------------------------------------------------------
 // Backward weight stream (dgrad): layer j of the chain multiplies by W^T, so stage (K chunk kc, N half h) holds
@@ -934,8 +941,8 @@ static void build_bwd_plans(const scade_net& net, NetPlan* np, PackPlan* pp) {
   if (pp) *pp = Q;
 }
 
-static size_t fwd_stream_bytes(const scade_net_desc& d) {
-  return (size_t)count_stages(d) * STAGE_BYTES + align_up(sizeof(PackedTail), 1024);
+static size_t fwd_stream_bytes(const scade_net_desc& d, bool x3 = false) {
+  return (size_t)count_stages(d) * (x3 ? 2 : 1) * STAGE_BYTES + align_up(sizeof(PackedTail), 1024);
 }
 
 static TrainLayout train_layout(const scade_net_desc& d, int64_t P) {
@@ -990,6 +997,21 @@ static int encode_rows_tmap(CUtensorMap* tmap, const void* base, size_t bytes, i
   return SCADE_OK;
 }
 
+// cudaFuncSetAttribute is per device: remember which devices of this process have been configured
+static int set_kernel_attributes() {
+  static bool done[64] = {};
+  int dev = 0;
+  SCADE_CUDA(cudaGetDevice(&dev));
+  if (dev >= 0 && dev < 64 && done[dev]) return SCADE_OK;
+  SCADE_CUDA(cudaFuncSetAttribute(nerf_mlp_tc_pp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM_BYTES));
+  SCADE_CUDA(cudaFuncSetAttribute(nerf_mlp_tc_pp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM_BYTES));
+  SCADE_CUDA(cudaFuncSetAttribute(nerf_mlp_tc_x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM_BYTES));
+  SCADE_CUDA(cudaFuncSetAttribute(nerf_mlp_tc_dgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  SCADE_CUDA(cudaFuncSetAttribute(nerf_mlp_tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM_BYTES));
+  if (dev >= 0 && dev < 64) done[dev] = true;
+  return SCADE_OK;
+}
+
 static int launch_pair(const void* kern, int clusters, int threads, int smem, cudaStream_t st, void** args) {
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(2 * clusters);
@@ -1009,15 +1031,22 @@ static int launch_pair(const void* kern, int clusters, int threads, int smem, cu
 bool mlp_tc_supported(const scade_net_desc& d) {
   NetDims nd(d);
   return d.W == tc::W && d.D >= 2 && d.D <= 8 && nd.in_all <= tc::ONES_COL && d.multires <= 9 && d.multires_views == 0 &&
-         d.skip != d.D - 1 && tc::count_stages(d) <= tc::MAX_STAGE_DESCS;
+         d.skip != d.D - 1 && 2 * tc::count_stages(d) <= tc::MAX_STAGE_DESCS;
 }
 
-size_t mlp_tc_packed_bytes(const scade_net_desc& d) {
+size_t mlp_tc_packed_bytes(const scade_net_desc& d, bool x3) {
+  if (x3) return tc::fwd_stream_bytes(d, true);                                              // (W_hi, W_lo) forward stream + tail
   return tc::fwd_stream_bytes(d) + (size_t)tc::count_bwd_stages(d) * tc::STAGE_BYTES;      // forward stream + tail | dgrad stream
 }
 
-int mlp_tc_pack(const scade_net& net, void* packed_out, cudaStream_t st) {
+int mlp_tc_pack(const scade_net& net, void* packed_out, cudaStream_t st, bool x3) {
   tc::PackPlan pp;
+  if (x3) {
+    tc::build_plans(net, nullptr, &pp, true);
+    tc::pack_kernel<<<pp.n_stages + 1, 256, 0, st>>>(pp, reinterpret_cast<uint8_t*>(packed_out));
+    SCADE_LAUNCH_CHECK();
+    return SCADE_OK;
+  }
   tc::build_plans(net, nullptr, &pp);
   tc::pack_kernel<<<pp.n_stages + 1, 256, 0, st>>>(pp, reinterpret_cast<uint8_t*>(packed_out));
   SCADE_LAUNCH_CHECK();
@@ -1046,15 +1075,14 @@ int mlp_tc_stash_layout(const scade_net_desc& d, int64_t P, int64_t* out, int n)
 
 int mlp_tc_forward(const scade_net& net, const float* rays, int ray_stride, const float* z, const float* x_embedded,
                    int64_t N, int S, const float* bb_center, float bb_scale, float* raw_out, void* workspace,
-                   size_t ws_bytes, int save, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    SCADE_CUDA(cudaFuncSetAttribute(tc::nerf_mlp_tc_pp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::FWD_SMEM_BYTES));
-    SCADE_CUDA(cudaFuncSetAttribute(tc::nerf_mlp_tc_pp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::FWD_SMEM_BYTES));
-    attr_set = true;
+                   size_t ws_bytes, int save, cudaStream_t st, bool x3) {
+  if (x3 && save) {
+    set_error("mlp_forward (tc_f16x3): the tight tensor-core mode is forward-only; train through SCADE_PREC_FP32 or SCADE_PREC_TC_F16");
+    return SCADE_ERR_UNSUPPORTED;
   }
+  SCADE_TRY(tc::set_kernel_attributes());
   tc::NetPlan plan;
-  tc::build_plans(net, &plan, nullptr);
+  tc::build_plans(net, &plan, nullptr, x3);
   NetDims nd(net.desc);
   tc::FwdArgs a{};
   a.packed = reinterpret_cast<const uint8_t*>(net.packed_f16);
@@ -1085,6 +1113,14 @@ int mlp_tc_forward(const scade_net& net, const float* rays, int ray_stride, cons
     }
     sa.ws = reinterpret_cast<uint8_t*>(workspace);
   }
+  if (x3) {
+    const int64_t x3_steps = ceil_div<int64_t>(a.P, 2 * tc::TILE_M);
+    const int x3_clusters = (int)std::min<int64_t>(x3_steps, num_sms() / 2);
+    void* x3_args[] = {&a, &plan, &tmap};
+    SCADE_TRY(tc::launch_pair((const void*)tc::nerf_mlp_tc_x3_kernel, x3_clusters, tc::PP_THREADS, tc::FWD_SMEM_BYTES, st, x3_args));
+    SCADE_LAUNCH_CHECK();
+    return SCADE_OK;
+  }
   const int64_t n_steps = (a.n_pairs + 1) / 2;
   const int clusters = (int)std::min<int64_t>(n_steps, num_sms() / 2);
   void* args[] = {&a, &plan, &tmap, &sa};
@@ -1105,12 +1141,7 @@ int mlp_tc_backward(const scade_net& net, const float* d_out, int64_t P, float* 
     return SCADE_ERR_WORKSPACE;
   }
   uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
-  static bool attr_set = false;
-  if (!attr_set) {
-    SCADE_CUDA(cudaFuncSetAttribute(tc::nerf_mlp_tc_dgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
-    SCADE_CUDA(cudaFuncSetAttribute(tc::nerf_mlp_tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::WG_SMEM_BYTES));
-    attr_set = true;
-  }
+  SCADE_TRY(tc::set_kernel_attributes());
   // 1. gradient scale from max |d_out|
   SCADE_CUDA(cudaMemsetAsync(ws + L.gs, 0, 256, st));
   {

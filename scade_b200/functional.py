@@ -12,9 +12,13 @@ from ctypes import byref, c_void_p
 import torch
 
 from . import _lib
-from ._lib import PREC_FP32, PREC_TC_F16, check, f32, ptr, stream_ptr
+from ._lib import PREC_FP32, PREC_TC_F16, PREC_TC_F16X3, check, f32, ptr, stream_ptr
 
-PRECISIONS = {"fp32": PREC_FP32, "tc_f16": PREC_TC_F16, PREC_FP32: PREC_FP32, PREC_TC_F16: PREC_TC_F16}
+# "fp32": FFMA GEMMs (the reference's arithmetic).  "tc_f16": tcgen05, fp16 operands (fast mode, forward + backward).
+# "tc_f16x3": tcgen05 at an fp32-level tolerance, fp16 (hi, lo) operand pairs, three MMA passes (tight mode, forward only).
+PRECISIONS = {"fp32": PREC_FP32, "tc_f16": PREC_TC_F16, "tc_f16x3": PREC_TC_F16X3, PREC_FP32: PREC_FP32,
+              PREC_TC_F16: PREC_TC_F16, PREC_TC_F16X3: PREC_TC_F16X3}
+TC_PRECISIONS = (PREC_TC_F16, PREC_TC_F16X3)
 
 
 def _L():
@@ -49,8 +53,8 @@ class NetHandle:
         if len(self.params) != 2 * D + 8:
             raise ValueError(f"expected {2 * D + 8} parameter tensors, got {len(self.params)}")
         self.desc = _lib.NetDesc(D, W, multires, multires_views, skip)
-        self._packed = None
-        self._packed_key = None
+        self._packed = {}                # precision -> packed weight stream (uint8 tensor)
+        self._packed_key = {}            # precision -> key the stream was packed for
         self._struct_key = None          # (data pointers) the cached scade_net structs were built from
         self._structs = {}
 
@@ -74,23 +78,31 @@ class NetHandle:
                 net.params[i] = ptr_
             net.packed_f16 = None
             self._structs[precision] = net
-        if precision == PREC_TC_F16:
-            net.packed_f16 = self.packed().data_ptr()
+        if precision in TC_PRECISIONS:
+            net.packed_f16 = self.packed(precision).data_ptr()
         return net
 
-    def packed(self):
+    def invalidate_packed(self):
+        """Force a re-pack of every tensor-core weight stream on next use (e.g. right before a CUDA-graph capture, so that
+        the pack launches are recorded inside the graph)."""
+        self._packed_key = {}
+
+    def packed(self, precision=PREC_TC_F16):
+        """The packed fp16 weight stream of a tensor-core precision, re-packed (scade_mlp_pack) whenever a parameter's version
+        counter, its storage or the global weights epoch moved."""
         key = (_weights_epoch, self._struct_key if self._struct_key is not None else tuple(p.data_ptr() for p in self.params)) \
             + tuple(p._version for p in self.params)
-        if self._packed is None or key != self._packed_key:
-            nbytes = _L().scade_mlp_packed_bytes(byref(self.desc))
+        buf = self._packed.get(precision)
+        if buf is None or key != self._packed_key.get(precision):
+            nbytes = _L().scade_mlp_packed_bytes_for(byref(self.desc), precision)
             if nbytes == 0:
-                raise _lib.ScadeError("this network shape is not supported by the tensor-core (tc_f16) path")
-            if self._packed is None or self._packed.numel() != nbytes or self._packed.device != self.params[0].device:
-                self._packed = torch.empty(nbytes, dtype=torch.uint8, device=self.params[0].device)
+                raise _lib.ScadeError("this network shape is not supported by the tensor-core (tc_f16 / tc_f16x3) paths")
+            if buf is None or buf.numel() != nbytes or buf.device != self.params[0].device:
+                buf = self._packed[precision] = torch.empty(nbytes, dtype=torch.uint8, device=self.params[0].device)
             net = self.struct(PREC_FP32)
-            check(_L().scade_mlp_pack_f16(byref(net), ptr(self._packed), stream_ptr()), "scade_mlp_pack_f16")
-            self._packed_key = key
-        return self._packed
+            check(_L().scade_mlp_pack(byref(net), precision, ptr(buf), stream_ptr()), "scade_mlp_pack")
+            self._packed_key[precision] = key
+        return buf
 
     def workspace_bytes(self, P, precision, save):
         return _L().scade_mlp_workspace_bytes(byref(self.desc), int(P), int(precision), int(save))
@@ -180,13 +192,24 @@ class _MLPEmbeddedFn(torch.autograd.Function):
         return (None, None, None, None, *grads)
 
 
+def _train_precision(handle, precision, need_grad):
+    """Arithmetic of a forward that must be differentiable: the tight mode (tc_f16x3) is forward-only, so gradients at an fp32
+    tolerance come from the fp32 FFMA path (any D / W / multires); tc_f16 trains on the tensor cores when the shape allows."""
+    if not need_grad:
+        return precision
+    if precision == PREC_TC_F16X3:
+        return PREC_FP32
+    if precision == PREC_TC_F16 and not (tc_train_enabled() and handle.tc_supported()):
+        return PREC_FP32
+    return precision
+
+
 def mlp_forward_rays(handle, rays, z_vals, bb_center, bb_scale, precision=PREC_FP32):
     """run_network fused with pts = o + d*z (RS:48-63, 657): rays [N,>=11], z [N,S] -> raw [N,S,4]."""
     precision = PRECISIONS[precision]
     rays, z_vals = f32(rays), f32(z_vals)
     need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in handle.params)
-    if precision == PREC_TC_F16 and need_grad and not (tc_train_enabled() and handle.tc_supported()):
-        precision = PREC_FP32      # fp32 FFMA training path (any D / W / multires)
+    precision = _train_precision(handle, precision, need_grad)
     if rays.shape[0] == 0:
         return torch.empty((0, z_vals.shape[1], 4), dtype=torch.float32, device=z_vals.device)
     return _MLPRaysFn.apply(rays, z_vals, handle, precision, [float(c) for c in bb_center], float(bb_scale),
@@ -199,8 +222,7 @@ def mlp_forward_embedded(handle, x, precision=PREC_FP32):
     lead = x.shape[:-1]
     x2 = f32(x).reshape(-1, x.shape[-1])
     need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in handle.params)
-    if precision == PREC_TC_F16 and need_grad and not (tc_train_enabled() and handle.tc_supported()):
-        precision = PREC_FP32
+    precision = _train_precision(handle, precision, need_grad)
     if x2.shape[0] == 0:
         return torch.empty((*lead, 4), dtype=torch.float32, device=x2.device)
     return _MLPEmbeddedFn.apply(x2, handle, precision, need_grad, *handle.params).reshape(*lead, 4)

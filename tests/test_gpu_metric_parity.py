@@ -36,11 +36,15 @@ PARITY_TOL = {
                     "weights": (2e-6, 5e-8), "pred_hyp": (0.1, 5e-5)},
         "e2e": {"rgb_psnr": 70.0, "depth_mean": 3e-5, "pred_hyp_mean": 1e-4},
     },
+    # measured: rgb0 5.8e-5/1.3e-6, raw 3.9e-4/5.9e-5, rgb_map 4.0e-6/7.5e-7, depth_map 7.9e-6/2.6e-6, PSNR 75.9 dB (the fp32 path
+    # itself: 75.6 dB -- the end-to-end figure is the workload's discontinuity floor, not the arithmetic).  The operand split
+    # alone would give raw 7e-5 (oracle.nerf_forward_f16(split=True)); the rest is the tensor core's fp32 accumulator, which
+    # truncates (round-toward-zero) at each of the 48 accumulation steps of a 256-wide layer.
     "tc_f16x3": {
-        "coarse": {"rgb0": (1e-4, 3e-6), "depth0": (5e-4, 2e-5), "acc0": (1e-4, 3e-6), "weights0": (1e-4, 2e-7)},
-        "teacher": {"raw": (5e-4, 5e-5), "rgb_map": (2e-5, 2e-6), "depth_map": (2e-5, 3e-6), "acc_map": (5e-6, 1e-6),
-                    "weights": (1e-5, 1e-7), "pred_hyp": (0.2, 5e-5)},
-        "e2e": {"rgb_psnr": 70.0, "depth_mean": 5e-5, "pred_hyp_mean": 1e-4},
+        "coarse": {"rgb0": (1.5e-4, 4e-6), "depth0": (1e-3, 3e-5), "acc0": (2e-4, 5e-6), "weights0": (2e-4, 2e-7)},
+        "teacher": {"raw": (1e-3, 1.5e-4), "rgb_map": (1.2e-5, 2e-6), "depth_map": (2.5e-5, 8e-6), "acc_map": (2e-6, 5e-7),
+                    "weights": (5e-6, 1e-7), "pred_hyp": (0.1, 5e-5)},
+        "e2e": {"rgb_psnr": 70.0, "depth_mean": 6e-5, "pred_hyp_mean": 1e-4},
     },
     # measured: rgb0 1.7e-2/3.9e-4, raw 7.1e-2/8.5e-3, rgb_map 1.5e-3/1.5e-4, depth_map 2.3e-3/4.4e-4, PSNR 49.4 dB
     "tc_f16": {
@@ -182,3 +186,43 @@ def test_train_step_c3_vs_oracle(dev, precision):
         ok &= worst <= tol[which]
     print("\n" + "\n".join(report))
     assert ok, "\n".join(report)
+
+
+@pytest.mark.parametrize("P", [700, 33000])
+def test_mlp_x3_vs_oracle(dev, P):
+    """The tight tensor-core mode on identical inputs (NeRF.forward, H:223-247): against the fp32 oracle (float64-accumulated)
+    and against the CPU emulation of the same hi/lo operand split.  P = 700 leaves a ragged last 256-point step and fewer
+    steps than SM pairs; 33000 gives every SM pair several steps (ring wrap-around, accumulator ping-pong across steps).
+    Tolerance: max |raw - oracle| <= 1e-3, mean <= 1.5e-4 -- two orders below single-pass fp16 (7e-2 / 8e-3); the operand
+    split alone gives 7e-5 in emulation, the rest is the tensor core's truncating fp32 accumulator."""
+    from scade_b200 import functional as F_, nerf_helpers as NH
+    params = syn.make_nerf_params(seed=10, D=8, W=256, bias_scale=0.05, alpha_bias=0.5, weight_gain=1.3)
+    net = NH.NeRF(D=8, W=256, input_ch=57, input_ch_views=3, output_ch=5, skips=[4], use_viewdirs=True, precision="tc_f16x3")
+    net.load_state_dict({k: torch.from_numpy(v) for k, v in params.items()})
+    net = net.to(dev).requires_grad_(False)
+    rng = np.random.default_rng(7)
+    x = rng.uniform(-1, 1, (P, 60)).astype(np.float32)
+    with torch.no_grad():
+        out = npy(net(T(x, dev)))
+    ref = O.nerf_forward(params, x, dtype=np.float64).astype(np.float32)
+    d = np.abs(out - ref)
+    print(f"\nmlp x3, P={P}: max |raw - fp64 oracle| = {d.max():.3e}, mean {d.mean():.3e}")
+    assert np.isfinite(out).all()
+    assert d.max() <= 1e-3 and d.mean() <= 1.5e-4, (d.max(), d.mean())
+    if P <= 1000:
+        emu = O.nerf_forward_f16(params, x, split=True)
+        de = np.abs(out - emu)
+        print(f"mlp x3, P={P}: max |raw - hi/lo emulation| = {de.max():.3e}")
+        assert de.max() <= 1e-3
+    # rays mode (positional encoding in the prologue) agrees with the embedded mode on the same points
+    if P <= 1000:
+        bb_center, bb_scale = syn.bounding_box()
+        rb = syn.make_ray_batch(5, seed=3)
+        z = np.linspace(0.1, 5.0, 140, dtype=np.float32)[None, :].repeat(5, 0)
+        raw = npy(F_.mlp_forward_rays(net.handle(), T(rb, dev), T(z, dev), bb_center, bb_scale, "tc_f16x3"))
+        pts = rb[:, None, 0:3] + rb[:, None, 3:6] * z[:, :, None]
+        xin = O.network_inputs(pts, rb[:, 8:11], bb_center, bb_scale)
+        ref_r = O.nerf_forward(params, xin.reshape(-1, 60), dtype=np.float64).astype(np.float32).reshape(5, 140, 4)
+        dr = np.abs(raw - ref_r)
+        print(f"mlp x3 rays mode: max |raw - oracle| = {dr.max():.3e}")
+        assert dr.max() <= 1e-3
