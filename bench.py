@@ -385,7 +385,8 @@ def measure_train(args, dev, rank, world, steps):
     if args.optimizer == "fused":
         # parameters of both networks + scale / shift as views of one flat buffer: one memset, one all-reduce, one Adam launch
         from scade_b200.optim import FusedAdam, flatten_parameters
-        net_params = [p for n in nets for p in n.parameters()]
+        # fine net first: its gradient range is all-reduced early (under the coarse backward), the rest in one piece
+        net_params = [p for n in (nets[1], nets[0]) for p in n.parameters()]
         flat = flatten_parameters(net_params, [scale, shift])
         opt = FusedAdam(net_params, lr=5e-4, betas=(0.9, 0.999), flat=flat, capturable=args.train_graph)     # RS:469
         opt_ss = FusedAdam([scale, shift], lr=1e-6, flat=flat, capturable=args.train_graph)                  # RS:888

@@ -213,6 +213,20 @@ int scade_space_carving_loss(const float* pred, const float* hyp, int hyp_full, 
                              float* loss_out, float* d_pred, float* d_hyp, void* workspace,
                              size_t workspace_bytes, void* stream);
 
+/* The joint branch (H:115-119: mean over rays BEFORE the min over k) for a ray-sharded step (SURVEY 8(e) "Exception"), in two
+ * halves around one all-reduce of K*P floats:
+ *   accumulate: qsum_out[k,p] = sum over this rank's N rays of dist[k,n,p]  (zeroed first);
+ *   (caller: sum qsum over the ranks)
+ *   finish    : per p, k*(p) = first arg-min of qsum[k,p] / N_global; loss_out = mean_p min_k  (the GLOBAL loss, identical on every
+ *               rank); d_pred / d_hyp (nullable) = gradient of grad_scale * loss w.r.t. this rank's N rays.
+ * kstar_workspace: P int32.  With N_global == N and no all-reduce this is scade_space_carving_loss(is_joint=1). */
+int scade_space_carving_joint_accumulate(const float* pred, const float* hyp, int hyp_full, const float* mask, int K,
+                                         int64_t N, int P, float threshold, float* qsum_out, void* stream);
+int scade_space_carving_joint_finish(const float* pred, const float* hyp, int hyp_full, const float* mask,
+                                     const float* qsum, int K, int64_t N, int64_t N_global, int P, float threshold,
+                                     float grad_scale, float* loss_out, float* d_pred, float* d_hyp,
+                                     int32_t* kstar_workspace, void* stream);
+
 /* img2mse (H:11): loss_out = mean((x-y)^2) over n elements; d_x (nullable) = grad_scale * d loss/d x.
  * `denominator` overrides n in the mean when > 0 (ray-sharded training divides by the GLOBAL count). */
 int scade_img2mse(const float* x, const float* y, int64_t n, int64_t denominator, float grad_scale,

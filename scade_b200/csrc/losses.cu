@@ -14,7 +14,8 @@
 
 namespace scade {
 
-constexpr int SC_WARPS = 4;
+constexpr int SC_WARPS = 8;
+constexpr int SC_RAYS = 32;         // rays per block: hyp[k, r0 .. r0+31] is one 128-byte line per hypothesis
 
 __device__ __forceinline__ float sc_dist(float pred, float h, float m, float thr, float& sgn) {
   float diff = pred - h;
@@ -24,30 +25,45 @@ __device__ __forceinline__ float sc_dist(float pred, float h, float m, float thr
   return d;
 }
 
+// Block = 8 warps x 32 consecutive rays (4 rays per warp, one after the other).  The [K x 32 rays] tile of hypotheses is
+// staged in shared memory by loads that run along N (hyp is [K, N, 1]: ray r of hypothesis k sits at k*N + r, so a per-ray
+// walk over k is K scattered 4-byte loads -- 4.6% of the HBM roofline in round 1), and the hypothesis gradients leave the same way.
+// Per ray: lanes walk the P samples, min over K in registers, gradient in the same pass, no [K,N,P] tensor.
 __global__ void __launch_bounds__(SC_WARPS * 32)
 space_carving_ray_kernel(const float* __restrict__ pred, const float* __restrict__ hyp, int hyp_full,
-                         const float* __restrict__ mask, int K, int64_t N, int P, float thr, float gscale,
+                         const float* __restrict__ mask, int K, int64_t N, int P, float thr, float gscale, float inv_n,
                          float* __restrict__ loss_out, float* __restrict__ d_pred, float* __restrict__ d_hyp) {
-  extern __shared__ float smem[];   // per warp: K hypotheses + K*32 lane-private gradient accumulators
+  extern __shared__ float smem[];   // s_h[K][32 rays] | s_dh[K][32 rays] | per warp: K*32 lane-private gradient accumulators
   __shared__ float s_part[SC_WARPS];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const int64_t r = (int64_t)blockIdx.x * SC_WARPS + wid;
-  float ray_sum = 0.f;
-  if (r < N) {
-    float* s_h = smem + (size_t)wid * (K + K * 32);
-    float* s_g = s_h + K;
+  const int64_t r0 = (int64_t)blockIdx.x * SC_RAYS;
+  float* s_h = smem;
+  float* s_dh = s_h + K * SC_RAYS;
+  float* s_g = s_dh + K * SC_RAYS + (size_t)wid * K * 32;
+  const bool want_dh = d_hyp != nullptr;
+  if (!hyp_full) {
+    for (int k = wid; k < K; k += SC_WARPS) {
+      const int64_t r = r0 + lane;
+      s_h[k * SC_RAYS + lane] = r < N ? hyp[(int64_t)k * N + r] : 0.f;
+    }
+  }
+  __syncthreads();
+  const float gval = gscale * inv_n / (float)P;
+  float warp_total = 0.f;
+  for (int j = 0; j < SC_RAYS / SC_WARPS; ++j) {
+    const int lr = wid * (SC_RAYS / SC_WARPS) + j;
+    const int64_t r = r0 + lr;
+    if (r >= N) break;
     const float m = mask ? mask[r] : 1.0f;
-    const bool want_dh = d_hyp != nullptr;
-    if (!hyp_full) for (int k = lane; k < K; k += 32) s_h[k] = hyp[(int64_t)k * N + r];
     if (want_dh && !hyp_full) for (int i = lane; i < K * 32; i += 32) s_g[i] = 0.f;
     __syncwarp();
-    const float gval = gscale / ((float)N * (float)P);
+    float ray_sum = 0.f;
     for (int p = lane; p < P; p += 32) {
       float pr = pred[r * P + p];
       float best = 0.f, bsgn = 0.f;
       int bk = 0;
       for (int k = 0; k < K; ++k) {
-        float h = hyp_full ? hyp[((int64_t)k * N + r) * P + p] : s_h[k];
+        float h = hyp_full ? hyp[((int64_t)k * N + r) * P + p] : s_h[k * SC_RAYS + lr];
         float sg;
         float d = sc_dist(pr, h, m, thr, sg);
         if (k == 0 || d < best) { best = d; bsgn = sg; bk = k; }   // H:124 (first arg-min)
@@ -67,17 +83,24 @@ space_carving_ray_kernel(const float* __restrict__ pred, const float* __restrict
       __syncwarp();
       for (int k = 0; k < K; ++k) {
         float v = warp_sum(s_g[k * 32 + lane]);
-        if (lane == 0) d_hyp[(int64_t)k * N + r] = v;
+        if (lane == 0) s_dh[k * SC_RAYS + lr] = v;
       }
+      __syncwarp();
     }
-    ray_sum = warp_sum(ray_sum) / (float)P;              // H:125
+    warp_total += warp_sum(ray_sum) / (float)P;          // H:125
   }
-  if (lane == 0) s_part[wid] = ray_sum;
+  if (lane == 0) s_part[wid] = warp_total;
   __syncthreads();
+  if (want_dh && !hyp_full) {
+    for (int k = wid; k < K; k += SC_WARPS) {
+      const int64_t r = r0 + lane;
+      if (r < N) d_hyp[(int64_t)k * N + r] = s_dh[k * SC_RAYS + lane];
+    }
+  }
   if (threadIdx.x == 0) {
     float s = 0.f;
     for (int w = 0; w < SC_WARPS; ++w) s += s_part[w];
-    atomicAdd(loss_out, s / (float)N);                   // H:126
+    atomicAdd(loss_out, s * inv_n);                      // H:126
   }
 }
 
@@ -100,7 +123,7 @@ __global__ void sc_joint_accumulate_kernel(const float* __restrict__ pred, const
   }
 }
 
-__global__ void sc_joint_select_kernel(const float* __restrict__ qsum, int K, int64_t N, int P, int* __restrict__ kstar,
+__global__ void sc_joint_select_kernel(const float* __restrict__ qsum, int K, float inv_n, int P, int* __restrict__ kstar,
                                        float* __restrict__ loss_out) {
   // single block; per p: min over k of qsum/N (H:117-118), then mean over p (H:119)
   __shared__ float s_red[32];
@@ -109,7 +132,7 @@ __global__ void sc_joint_select_kernel(const float* __restrict__ qsum, int K, in
     float best = 0.f;
     int bk = 0;
     for (int k = 0; k < K; ++k) {
-      float v = qsum[k * P + p] / (float)N;
+      float v = qsum[k * P + p] * inv_n;
       if (k == 0 || v < best) { best = v; bk = k; }
     }
     kstar[p] = bk;
@@ -127,14 +150,14 @@ __global__ void sc_joint_select_kernel(const float* __restrict__ qsum, int K, in
 
 __global__ void sc_joint_grad_kernel(const float* __restrict__ pred, const float* __restrict__ hyp, int hyp_full,
                                      const float* __restrict__ mask, const int* __restrict__ kstar, int K, int64_t N,
-                                     int P, float thr, float gscale, float* __restrict__ d_pred,
+                                     int P, float thr, float gscale, float inv_n, float* __restrict__ d_pred,
                                      float* __restrict__ d_hyp) {
   // one warp per ray (d_hyp [K,N,1] needs a reduction over p)
   const int lane = threadIdx.x & 31;
   const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (r >= N) return;
   const float m = mask ? mask[r] : 1.0f;
-  const float gval = gscale / ((float)N * (float)P);
+  const float gval = gscale * inv_n / (float)P;
   if (d_hyp && hyp_full)
     for (int k = 0; k < K; ++k)
       for (int p = lane; p < P; p += 32) d_hyp[((int64_t)k * N + r) * P + p] = 0.f;
@@ -187,6 +210,31 @@ extern "C" size_t scade_space_carving_workspace_bytes(int K, int64_t N, int P) {
   return align_up((size_t)K * P * sizeof(float)) + align_up((size_t)P * sizeof(int));
 }
 
+static int sc_joint_accumulate(const float* pred, const float* hyp, int hyp_full, const float* mask, int K, int64_t N, int P,
+                               float threshold, float* qsum, cudaStream_t st) {
+  SCADE_CUDA(cudaMemsetAsync(qsum, 0, (size_t)K * P * sizeof(float), st));
+  if (N == 0) return SCADE_OK;
+  int64_t rays_per_block = 64;
+  sc_joint_accumulate_kernel<<<(unsigned)ceil_div<int64_t>(N, rays_per_block), 256, 0, st>>>(
+      pred, hyp, hyp_full, mask, K, N, P, threshold, rays_per_block, qsum);
+  SCADE_LAUNCH_CHECK();
+  return SCADE_OK;
+}
+
+static int sc_joint_finish(const float* pred, const float* hyp, int hyp_full, const float* mask, const float* qsum, int* kstar,
+                           int K, int64_t N, int64_t n_global, int P, float threshold, float grad_scale, float* loss_out,
+                           float* d_pred, float* d_hyp, cudaStream_t st) {
+  const float inv_n = 1.0f / (float)n_global;
+  sc_joint_select_kernel<<<1, 256, 0, st>>>(qsum, K, inv_n, P, kstar, loss_out);
+  SCADE_LAUNCH_CHECK();
+  if ((d_pred || d_hyp) && N > 0) {
+    sc_joint_grad_kernel<<<(unsigned)ceil_div<int64_t>(N, 4), 128, 0, st>>>(pred, hyp, hyp_full, mask, kstar, K, N, P,
+                                                                           threshold, grad_scale, inv_n, d_pred, d_hyp);
+    SCADE_LAUNCH_CHECK();
+  }
+  return SCADE_OK;
+}
+
 extern "C" int scade_space_carving_loss(const float* pred, const float* hyp, int hyp_full, const float* mask, int K,
                                         int64_t N, int P, int is_joint, float threshold, float grad_scale,
                                         float* loss_out, float* d_pred, float* d_hyp, void* workspace,
@@ -195,12 +243,12 @@ extern "C" int scade_space_carving_loss(const float* pred, const float* hyp, int
   cudaStream_t st = as_stream(stream);
   SCADE_CUDA(cudaMemsetAsync(loss_out, 0, sizeof(float), st));
   if (!is_joint) {
-    size_t smem = (size_t)SC_WARPS * (K + K * 32) * sizeof(float);
+    size_t smem = ((size_t)2 * K * SC_RAYS + (size_t)SC_WARPS * K * 32) * sizeof(float);
     SCADE_CHECK_ARG(smem <= 160 * 1024, "space_carving_loss: K=%d too large", K);
     if (smem > 48 * 1024)
       SCADE_CUDA(cudaFuncSetAttribute(space_carving_ray_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    space_carving_ray_kernel<<<(unsigned)ceil_div<int64_t>(N, SC_WARPS), SC_WARPS * 32, smem, st>>>(
-        pred, hyp, hyp_full, mask, K, N, P, threshold, grad_scale, loss_out, d_pred, d_hyp);
+    space_carving_ray_kernel<<<(unsigned)ceil_div<int64_t>(N, SC_RAYS), SC_WARPS * 32, smem, st>>>(
+        pred, hyp, hyp_full, mask, K, N, P, threshold, grad_scale, 1.0f / (float)N, loss_out, d_pred, d_hyp);
     SCADE_LAUNCH_CHECK();
     return SCADE_OK;
   }
@@ -211,19 +259,26 @@ extern "C" int scade_space_carving_loss(const float* pred, const float* hyp, int
   }
   float* qsum = reinterpret_cast<float*>(workspace);
   int* kstar = reinterpret_cast<int*>(reinterpret_cast<char*>(workspace) + align_up((size_t)K * P * sizeof(float)));
-  SCADE_CUDA(cudaMemsetAsync(qsum, 0, (size_t)K * P * sizeof(float), st));
-  int64_t rays_per_block = 64;
-  sc_joint_accumulate_kernel<<<(unsigned)ceil_div<int64_t>(N, rays_per_block), 256, 0, st>>>(
-      pred, hyp, hyp_full, mask, K, N, P, threshold, rays_per_block, qsum);
-  SCADE_LAUNCH_CHECK();
-  sc_joint_select_kernel<<<1, 256, 0, st>>>(qsum, K, N, P, kstar, loss_out);
-  SCADE_LAUNCH_CHECK();
-  if (d_pred || d_hyp) {
-    sc_joint_grad_kernel<<<(unsigned)ceil_div<int64_t>(N, 4), 128, 0, st>>>(pred, hyp, hyp_full, mask, kstar, K, N, P,
-                                                                           threshold, grad_scale, d_pred, d_hyp);
-    SCADE_LAUNCH_CHECK();
-  }
-  return SCADE_OK;
+  SCADE_TRY(sc_joint_accumulate(pred, hyp, hyp_full, mask, K, N, P, threshold, qsum, st));
+  return sc_joint_finish(pred, hyp, hyp_full, mask, qsum, kstar, K, N, N, P, threshold, grad_scale, loss_out, d_pred, d_hyp, st);
+}
+
+extern "C" int scade_space_carving_joint_accumulate(const float* pred, const float* hyp, int hyp_full, const float* mask, int K,
+                                                    int64_t N, int P, float threshold, float* qsum_out, void* stream) {
+  SCADE_CHECK_ARG(pred && hyp && qsum_out && K > 0 && N >= 0 && P > 0, "space_carving_joint_accumulate: bad arguments");
+  return sc_joint_accumulate(pred, hyp, hyp_full, mask, K, N, P, threshold, qsum_out, as_stream(stream));
+}
+
+extern "C" int scade_space_carving_joint_finish(const float* pred, const float* hyp, int hyp_full, const float* mask,
+                                                const float* qsum, int K, int64_t N, int64_t N_global, int P, float threshold,
+                                                float grad_scale, float* loss_out, float* d_pred, float* d_hyp,
+                                                int32_t* kstar_workspace, void* stream) {
+  SCADE_CHECK_ARG(pred && hyp && qsum && loss_out && kstar_workspace && K > 0 && N >= 0 && N_global >= N && N_global > 0 && P > 0,
+                  "space_carving_joint_finish: bad arguments");
+  cudaStream_t st = as_stream(stream);
+  SCADE_CUDA(cudaMemsetAsync(loss_out, 0, sizeof(float), st));
+  return sc_joint_finish(pred, hyp, hyp_full, mask, qsum, kstar_workspace, K, N, N_global, P, threshold, grad_scale, loss_out,
+                         d_pred, d_hyp, st);
 }
 
 extern "C" int scade_img2mse(const float* x, const float* y, int64_t n, int64_t denominator, float grad_scale,

@@ -63,67 +63,151 @@ class FlatAllReduce:
         return self.flat
 
 
+def _nets_of(render_kwargs):
+    from . import render as R_
+    coarse = R_._unwrap(render_kwargs["network_fn"])
+    fine = R_._unwrap(render_kwargs.get("network_fine") or render_kwargs["network_fn"])
+    return coarse, fine
+
+
+class _BucketOverlap:
+    """Gradient exchange of a flat-storage train step in two buckets: the fine network's gradient range
+    is all-reduced asynchronously the moment its backward kernels are enqueued (functional._mlp_backward calls the hook), so
+    the transfer runs on NCCL's stream under the coarse network's backward; everything else (coarse gradients, scale /
+    shift, the loss partial sums in the tail) follows in ONE in-place all-reduce when backward() returns -- or two, if the
+    fine range does not sit at one end of the flat buffer.  Autograd runs the fine branch first (its nodes are younger)."""
+
+    def __init__(self, flat, fine_net, group):
+        self.flat, self.group, self.work, self.handle = flat, group, None, None
+        self.range = flat.range_of(list(fine_net.parameters())) if fine_net is not None else None
+        total = flat.flat_grad.numel()
+        if self.range is not None and _world(group)[1] > 1:
+            self.handle = fine_net.handle()
+            self.handle.grad_ready_hook = self._launch
+        lo, hi = self.range if self.range is not None else (0, 0)
+        self.rest = [(a, b) for a, b in ((0, lo), (hi, total)) if b > a] if self.range is not None else [(0, total)]
+
+    def _launch(self, _handle):
+        lo, hi = self.range
+        self.work = dist.all_reduce(self.flat.flat_grad[lo:hi], op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+
+    def finish(self):
+        """The remaining range(s) + the stream-level wait for the early bucket.  Returns the number of all-reduce calls."""
+        if self.handle is not None:
+            self.handle.grad_ready_hook = None
+        calls = 0
+        if _world(self.group)[1] > 1:
+            pieces = self.rest if self.work is not None else [(0, self.flat.flat_grad.numel())]
+            for lo, hi in pieces:
+                dist.all_reduce(self.flat.flat_grad[lo:hi], op=dist.ReduceOp.SUM, group=self.group)
+                calls += 1
+            if self.work is not None:
+                self.work.wait()                         # current stream waits for the early bucket (no host block)
+                calls += 1
+        return calls
+
+
 def sharded_train_step(ray_batch, target_s, target_h, scale, shift, render_kwargs, n_global=None,
                        space_carving_weight=0.007, threshold=0.0, mask=None, t_rand=None, u_coarse=None, u_fine=None,
-                       group=None, flat=None):
-    """One SCADE training step (RS:954-985) on this rank's ray shard, followed by the single gradient all-reduce.
+                       group=None, flat=None, is_joint=False, extra_params=None, overlap=True):
+    """One SCADE training step (RS:954-985) on this rank's ray shard, followed by the gradient all-reduce.
 
     ray_batch [n_local,11], target_s [n_local,3], target_h [K,n_local,1] are this rank's slices of the step's
     N_rand rays (all from one image, same scale/shift on every rank, RS:945-952).  After the call every rank holds
     the global gradient in ``.grad`` of the network parameters / scale / shift, exactly as after ``loss.backward()``
-    on one GPU.  Returns a dict of GLOBAL losses (tensors).  `flat`: the FlatParams holding the networks' parameters and
-    scale / shift, if the caller flattened them (then the all-reduce is in place on its gradient buffer)."""
+    on one GPU.  Returns a dict of GLOBAL losses (tensors).
+
+    flat         the FlatParams holding the networks' parameters and scale / shift, if the caller flattened them: the
+                 exchange is then in place on its gradient buffer, in two buckets (fine net early, see _BucketOverlap).
+    is_joint     RS:963 passes args.is_joint: the space-carving loss averages over ALL rays before the min over K
+                 (H:115-119), which costs one extra all-reduce of [K, N_importance] partial sums.  As in the
+                 reference the flag also reaches render_rays, where it only selects joint uniforms when perturb > 0.
+    extra_params leaf tensors whose .grad must be reduced as well when the step's scale / shift are NOT leaves -- the
+                 reference idiom ``DEPTH_SCALES[img_i]`` (RS:945-954) hands a view to the loss and autograd fills
+                 ``DEPTH_SCALES.grad``; pass ``[DEPTH_SCALES, DEPTH_SHIFTS]`` (not needed when they live in `flat`)."""
+    from . import functional as F_
     from . import nerf_helpers as NH
     from . import render as R_
     rank, world = _world(group)
     n_local = ray_batch.shape[0]
     n_global = int(n_global if n_global is not None else n_local * world)
+    coarse, fine = _nets_of(render_kwargs)
+    use_flat = flat is not None and flat.intact()
+    if not use_flat:
+        leaves = list(extra_params or [])
+        for t in (scale, shift):
+            if torch.is_tensor(t) and t.requires_grad:
+                if t.is_leaf:
+                    leaves.append(t)
+                elif not extra_params:
+                    raise ValueError("sharded_train_step: scale / shift require grad but are not leaf tensors (e.g. "
+                                     "DEPTH_SCALES[img_i]); pass the leaves as extra_params=[DEPTH_SCALES, DEPTH_SHIFTS] or keep "
+                                     "them in a FlatParams -- their gradients would otherwise stay rank-local")
     th = target_h * scale + shift                                                       # RS:954
-    ret = R_.render_rays(ray_batch, True, cached_u=u_fine, t_rand=t_rand, u_coarse=u_coarse, retraw=False, **render_kwargs)
+    bucket = _BucketOverlap(flat, fine if (overlap and fine is not coarse) else None, group) if use_flat else None
+    ret = R_.render_rays(ray_batch, True, cached_u=u_fine, t_rand=t_rand, u_coarse=u_coarse, retraw=False, is_joint=is_joint,
+                         **render_kwargs)
     # local sums divided by the global count: sum over ranks == the single-GPU mean (H:11, H:125-126)
     img_loss = F_img2mse(ret["rgb_map"], target_s, n_global * 3)
     img_loss0 = F_img2mse(ret["rgb0"], target_s, n_global * 3)
-    sc = NH.compute_space_carving_loss(ret["pred_hyp"], th, is_joint=False, mask=mask, threshold=threshold) \
-        * (float(n_local) / float(n_global))
+    if is_joint:
+        # the GLOBAL loss on every rank (one [K,P] all-reduce inside); its share of the rank-summed partials is 1/world
+        sc_full = F_.space_carving_loss_joint_sharded(ret["pred_hyp"], th, n_global, mask=mask, threshold=threshold, group=group)
+        sc, sc_part = sc_full, sc_full.detach() / float(world)
+    else:
+        sc = NH.compute_space_carving_loss(ret["pred_hyp"], th, is_joint=False, mask=mask, threshold=threshold) \
+            * (float(n_local) / float(n_global))
+        sc_part = sc.detach()
     loss = img_loss + space_carving_weight * sc + img_loss0                             # RS:976,983
     loss.backward()                                                                     # RS:985
-    losses = torch.stack([img_loss.detach(), sc.detach(), img_loss0.detach()])
-    if flat is not None and flat.intact():
-        losses = flat_exchange(flat, losses, group)
-        return {"img_loss": losses[0], "space_carving": losses[1], "img_loss0": losses[2],
-                "loss": losses[0] + space_carving_weight * losses[1] + losses[2]}
-    nets = [R_._unwrap(render_kwargs["network_fn"]), R_._unwrap(render_kwargs["network_fine"] or render_kwargs["network_fn"])]
-    params = [p for net in dict.fromkeys(nets) for p in net.parameters() if p.requires_grad]
-    for p in params:
-        if p.grad is None:
-            p.grad = torch.zeros_like(p)
-    extras = [t.grad for t in (scale, shift) if torch.is_tensor(t) and t.requires_grad and t.grad is not None]
-    FlatAllReduce([p.grad for p in params] + extras + [losses]).all_reduce(group)
+    losses = torch.stack([img_loss.detach(), sc_part, img_loss0.detach()])
+    if use_flat:
+        k = losses.numel()
+        tail = flat.tail()
+        tail[:k].copy_(losses)
+        bucket.finish()
+        losses = tail[:k].clone()
+    else:
+        params = [p for net in dict.fromkeys([coarse, fine]) for p in net.parameters() if p.requires_grad]
+        for p in params + leaves:
+            if p.grad is None:
+                p.grad = torch.zeros_like(p)
+        FlatAllReduce([p.grad for p in params] + [t.grad for t in leaves] + [losses]).all_reduce(group)
     return {"img_loss": losses[0], "space_carving": losses[1], "img_loss0": losses[2],
             "loss": losses[0] + space_carving_weight * losses[1] + losses[2]}
 
 
 class GraphedTrainStep:
     """One SCADE training step (zero_grad, sharded_train_step, optimizer steps; RS:954-997) recorded once as a CUDA graph and
-    replayed: forward, losses, backward, the gradient all-reduce and the fused Adam launches cost one graph launch per step
+    replayed: forward, losses, backward, the gradient all-reduces and the fused Adam launches cost one graph launch per step
     instead of ~100 kernel / collective launches from Python (which is what bounds the step once the rays are sharded 8 ways).
 
-        step = GraphedTrainStep(render_kwargs, scale, shift, flat, [opt, opt_ss], n_global=4096)
-        losses = step(ray_batch, target_s, target_h)       # this rank's shard; shapes must not change between calls
+        step = GraphedTrainStep(render_kwargs, DEPTH_SCALES, DEPTH_SHIFTS, flat, [opt, opt_ss], n_global=4096)
+        losses = step(ray_batch, target_s, target_h, img_i)   # this rank's shard; shapes must not change between calls
 
-    Requirements: parameters and scale / shift in one FlatParams (`flat`), optimizers = FusedAdam(..., flat=flat,
+    scale / shift are either single-element tensors (one global scale / shift) or the reference's per-image tables
+    ``DEPTH_SCALES`` / ``DEPTH_SHIFTS`` of shape [n_img, 1] (RS:878-879): then every call names the step's image `img_i`
+    (RS:945-948) and the graph gathers row img_i through a device-side index, so replays follow the image; the gradient
+    lands in row img_i of the table's .grad like ``DEPTH_SCALES[img_i]`` does under autograd.
+
+    Requirements: parameters and scale / shift tables in one FlatParams (`flat`), optimizers = FusedAdam(..., flat=flat,
     capturable=True).  The first `warmup` calls run eagerly (they are real steps), the next call captures and replays.
     Learning-rate changes through param_groups (update_learning_rate, RS:990) are uploaded before the next replay."""
 
     def __init__(self, render_kwargs, scale, shift, flat, optimizers, n_global=None, space_carving_weight=0.007, threshold=0.0,
-                 group=None, warmup=3):
+                 group=None, warmup=3, is_joint=False, overlap=True):
         self.kw, self.scale, self.shift, self.flat, self.opts = render_kwargs, scale, shift, flat, list(optimizers)
         self.n_global, self.scw, self.thr, self.group, self.warmup = n_global, space_carving_weight, threshold, group, int(warmup)
+        self.is_joint, self.overlap = bool(is_joint), bool(overlap)
         self.calls, self.graph, self.static, self.losses = 0, None, None, None
         self.launches_per_step = None                     # library kernel launches recorded in the graph (diagnostic)
         for o in self.opts:
             if not getattr(o, "capturable", False):
                 raise ValueError("GraphedTrainStep needs FusedAdam(..., capturable=True) optimizers")
+        self.per_image = torch.is_tensor(scale) and scale.numel() > 1
+        if self.per_image and (scale.dim() != 2 or shift.shape != scale.shape):
+            raise ValueError("per-image scale / shift tables must both have shape [n_img, 1] (RS:878-879)")
+        self.img_index = torch.zeros(1, dtype=torch.int64, device=scale.device) if self.per_image else None
 
     def release(self):
         """Drop the graph (and its private memory pool).  Call before destroying the process group: a live graph holds captured
@@ -134,19 +218,33 @@ class GraphedTrainStep:
     def _body(self, rb, ts, th):
         for o in self.opts:
             o.zero_grad(set_to_none=False)
-        losses = sharded_train_step(rb, ts, th, self.scale, self.shift, self.kw, n_global=self.n_global,
-                                    space_carving_weight=self.scw, threshold=self.thr, group=self.group, flat=self.flat)
+        if self.per_image:                                  # curr_scale = DEPTH_SCALES[img_i] (RS:947-948), index on the device
+            scale = self.scale.index_select(0, self.img_index).reshape(1)
+            shift = self.shift.index_select(0, self.img_index).reshape(1)
+        else:
+            scale, shift = self.scale, self.shift
+        losses = sharded_train_step(rb, ts, th, scale, shift, self.kw, n_global=self.n_global,
+                                    space_carving_weight=self.scw, threshold=self.thr, group=self.group, flat=self.flat,
+                                    is_joint=self.is_joint, overlap=self.overlap)
         for o in self.opts:
             o.step()
         return losses
 
-    def __call__(self, ray_batch, target_s, target_h):
+    def __call__(self, ray_batch, target_s, target_h, img_i=None):
         from .optim import note_replay
+        if self.per_image:
+            if img_i is None:
+                raise ValueError("GraphedTrainStep with per-image scale / shift tables needs img_i on every call")
+            self.img_index.fill_(int(img_i))
         self.calls += 1
         if self.graph is None and self.calls <= self.warmup:
             return self._body(ray_batch, target_s, target_h)
         if self.graph is None:
             self.static = (ray_batch.clone(), target_s.clone(), target_h.clone())
+            # the fp16 weight streams must be re-packed INSIDE the graph (every replay follows an optimizer step): drop the
+            # cached streams so that the capture below records the pack launches whatever ran between the last step and now
+            for net in _nets_of(self.kw):
+                net.handle().invalidate_packed()
             torch.cuda.synchronize()
             from . import _lib
             l0 = _lib.load().scade_kernel_launch_count()

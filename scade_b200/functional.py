@@ -125,12 +125,26 @@ def stash_layout(handle, P):
     return out
 
 
+_direct_grad_ids = set()      # id(param) of parameters whose owner opted in to in-place gradient accumulation
+
+
+def enable_direct_grads(params, on=True):
+    """Opt in (scade_b200.optim.FlatParams does) to having the backward kernels accumulate straight into ``p.grad`` instead of
+    returning gradients through autograd.  Explicit because it bypasses autograd's own accumulation: tensor hooks on the
+    parameters do not fire and torch.autograd.grad() would still write .grad."""
+    for p in params:
+        (_direct_grad_ids.add if on else _direct_grad_ids.discard)(id(p))
+
+
 def _mlp_backward(handle, precision, d_out, P, ws, device):
-    """scade_mlp_backward ACCUMULATES.  When every parameter already owns a contiguous fp32 .grad (the training loop's state
-    after zero_grad(set_to_none=False), or scade_b200.optim.FlatParams views) the kernels add straight into it and autograd gets
-    None for the parameters; otherwise one zeroed flat buffer is carved into per-parameter gradients and returned."""
+    """scade_mlp_backward ACCUMULATES.  For parameters that opted in (enable_direct_grads: FlatParams views), all of which
+    require grad and own a contiguous fp32 .grad, the kernels add straight into .grad and autograd gets None; otherwise one
+    zeroed flat buffer is carved into per-parameter gradients and returned through autograd.  `handle.grad_ready_hook`, if
+    set, is called once the backward kernels of this network are enqueued (scade_b200.dist launches that network's gradient
+    bucket all-reduce from it, overlapping the rest of the backward)."""
     params = handle.params
-    direct = all(p.grad is not None and p.grad.is_contiguous() and p.grad.dtype == torch.float32 and p.grad.is_cuda for p in params)
+    direct = all(id(p) in _direct_grad_ids and p.requires_grad and p.grad is not None and p.grad.is_contiguous()
+                 and p.grad.dtype == torch.float32 and p.grad.is_cuda for p in params)
     if direct:
         grads = [p.grad for p in params]
     else:
@@ -144,6 +158,9 @@ def _mlp_backward(handle, precision, d_out, P, ws, device):
     arr = (c_void_p * len(grads))(*[g.data_ptr() for g in grads])
     check(_L().scade_mlp_backward(byref(net), precision, ptr(d_out), P, arr, ptr(ws), ws.numel(), stream_ptr()),
           "scade_mlp_backward")
+    hook = getattr(handle, "grad_ready_hook", None)
+    if hook is not None and direct:
+        hook(handle)
     return [None] * len(params) if direct else grads
 
 
@@ -446,6 +463,48 @@ def space_carving_loss(pred, hyp, is_joint=False, mask=None, threshold=0.0):
     mask = None if mask is None else f32(mask)
     want = torch.is_grad_enabled() and (pred.requires_grad or hyp.requires_grad)
     return _SpaceCarvingFn.apply(pred, hyp, mask, bool(is_joint), float(threshold), want)
+
+
+class _SpaceCarvingJointShardedFn(torch.autograd.Function):
+    """Joint branch (H:115-119) on a ray shard: local [K,P] distance sums -> ONE all-reduce of K*P floats -> arg-min over k of
+    the GLOBAL means -> loss (global, identical on every rank) and this shard's gradients (SURVEY 8(e) "Exception")."""
+
+    @staticmethod
+    def forward(ctx, pred, hyp, mask, threshold, n_global, group, want):
+        import torch.distributed as dist
+        N, P = pred.shape
+        K = hyp.shape[0]
+        full = hyp.shape[-1] != 1
+        dev = pred.device
+        qsum = torch.empty((K, P), dtype=torch.float32, device=dev)
+        check(_L().scade_space_carving_joint_accumulate(ptr(pred), ptr(hyp), int(full), ptr(mask), K, N, P, float(threshold),
+                                                        ptr(qsum), stream_ptr()), "scade_space_carving_joint_accumulate")
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            dist.all_reduce(qsum, op=dist.ReduceOp.SUM, group=group)
+        loss = torch.empty((1,), dtype=torch.float32, device=dev)
+        d_pred = torch.empty_like(pred) if want else None
+        d_hyp = torch.empty_like(hyp) if want else None
+        kstar = torch.empty((P,), dtype=torch.int32, device=dev)
+        check(_L().scade_space_carving_joint_finish(ptr(pred), ptr(hyp), int(full), ptr(mask), ptr(qsum), K, N, int(n_global), P,
+                                                    float(threshold), 1.0, ptr(loss), ptr(d_pred), ptr(d_hyp), ptr(kstar),
+                                                    stream_ptr()), "scade_space_carving_joint_finish")
+        if want:
+            ctx.save_for_backward(d_pred, d_hyp)
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        d_pred, d_hyp = ctx.saved_tensors
+        return d_pred * g, d_hyp * g, None, None, None, None, None
+
+
+def space_carving_loss_joint_sharded(pred, hyp, n_global, mask=None, threshold=0.0, group=None):
+    """compute_space_carving_loss(is_joint=True) (H:115-119) when `pred` / `hyp` hold this rank's rays of a step whose rays are
+    split across the ranks of `group`: returns the GLOBAL loss; backward yields this shard's part of its gradient."""
+    pred, hyp = f32(pred), f32(hyp)
+    mask = None if mask is None else f32(mask)
+    want = torch.is_grad_enabled() and (pred.requires_grad or hyp.requires_grad)
+    return _SpaceCarvingJointShardedFn.apply(pred, hyp, mask, float(threshold), int(n_global), group, want)
 
 
 class _MseFn(torch.autograd.Function):

@@ -47,6 +47,20 @@ class FlatParams:
                 self.flat[o:o + n].copy_(p.data.reshape(-1))
                 p.data = self.flat[o:o + n].view(p.shape)
                 p.grad = self.flat_grad[o:o + n].view(p.shape)
+        from . import functional as F_
+        F_.enable_direct_grads(self.params)         # the CUDA backward kernels accumulate straight into these .grad views
+
+    def range_of(self, params):
+        """[lo, hi) float offsets of `params` inside the flat buffers, or None unless they are a consecutive run of self.params."""
+        ids = [id(p) for p in self.params]
+        want = [id(p) for p in params]
+        if not want or want[0] not in ids:
+            return None
+        i0 = ids.index(want[0])
+        if ids[i0:i0 + len(want)] != want:
+            return None
+        hi = self.offsets[i0 + len(want)] if i0 + len(want) < len(ids) else self.numel
+        return self.offsets[i0], hi
 
     def grads(self):
         return self.flat_grad[:self.numel]
@@ -119,6 +133,48 @@ class FusedAdam(torch.optim.Optimizer):
                 st["exp_avg"], st["exp_avg_sq"] = self._m[o:o + n].view(p.shape), self._v[o:o + n].view(p.shape)
         return self._m, self._v
 
+    def _sync_state_steps(self):
+        if self.flat is not None and self._range is not None:
+            for p in self.flat.params[self._range[2]:self._range[3]]:
+                if p in self.state:
+                    self.state[p]["step"] = self._step
+
+    def state_dict(self):
+        """torch.optim.Adam's layout.  The step count written is the CURRENT one (graph replays advance it on the device and in
+        the host mirror, not in `state`), so a checkpoint taken after replays resumes with the right bias correction."""
+        if self._m is not None:
+            self._sync_state_steps()
+        return super().state_dict()
+
+    def load_state_dict(self, state_dict):
+        """Adopts exp_avg / exp_avg_sq / step into the flat moment buffers at any time (not only before the first step), and
+        resets the device-side step count of the capturable variant."""
+        super().load_state_dict(state_dict)
+        if self.flat is None or self._range is None:
+            return
+        o0, o1, i0, i1 = self._range
+        params = self.flat.params[i0:i1]
+        if not any("exp_avg" in self.state.get(p, {}) for p in params):
+            return
+        if self._m is None:
+            self._m = torch.zeros(o1 - o0, dtype=torch.float32, device=self.flat.flat.device)
+            self._v = torch.zeros_like(self._m)
+        step = self._step
+        with torch.no_grad():
+            for p, o in zip(params, self.flat.offsets[i0:i1]):
+                st = self.state[p]
+                n, o = p.numel(), o - o0
+                if "exp_avg" in st:
+                    self._m[o:o + n].copy_(st["exp_avg"].reshape(-1))
+                    self._v[o:o + n].copy_(st["exp_avg_sq"].reshape(-1))
+                    step = int(st.get("step", step))
+                st["exp_avg"], st["exp_avg_sq"] = self._m[o:o + n].view(p.shape), self._v[o:o + n].view(p.shape)
+        self._step = step
+        if self._step_t is not None:
+            self._step_t.fill_(self._step)
+        self._lr_uploaded = None                       # param_groups came from the checkpoint: upload the rate again
+        self._sync_state_steps()
+
     def zero_grad(self, set_to_none=False):
         if self.flat is not None and self.flat.intact():
             o0, o1 = self._range[:2]
@@ -146,7 +202,7 @@ class FusedAdam(torch.optim.Optimizer):
                         raise _lib.ScadeError("FusedAdam(capturable=True): take one eager step before capturing")
                     self._step_t = torch.full((1,), self._step, dtype=torch.int64, device=f.flat.device)
                     self._lr_t = torch.zeros(1, dtype=torch.float64, device=f.flat.device)
-                if self._lr_uploaded != float(g0["lr"]):
+                if self._lr_uploaded is None or self._lr_uploaded != float(g0["lr"]):
                     if capturing:
                         raise _lib.ScadeError("FusedAdam(capturable=True): the learning rate changed inside a capture")
                     self._lr_t.fill_(float(g0["lr"]))
@@ -187,6 +243,7 @@ def note_replay(optimizer, upload_lr=True):
     streams are marked stale for eager code."""
     from . import functional as F_
     optimizer._step += 1
+    optimizer._sync_state_steps()
     if upload_lr and optimizer._lr_t is not None:
         lr = float(optimizer.param_groups[0]["lr"])
         if optimizer._lr_uploaded != lr:

@@ -86,3 +86,46 @@ def test_flat_allreduce_world2(tmp_path):
         for a, b in zip(got["grads"], [p.grad for p in flat.params]):
             assert torch.allclose(a, b, rtol=1e-5, atol=1e-6)
         assert torch.allclose(got["red"], torch.stack([loss.detach(), torch.tensor(float(world))]), rtol=1e-5)
+
+
+def _bucket_worker(rank, world, port, out_dir):
+    """The two-bucket gradient exchange of a flat-storage train step (scade_b200.dist._BucketOverlap): fine-net range early and
+    asynchronously, the rest (coarse net, scale / shift, loss partials in the tail) afterwards -- for the fine net at the
+    front, in the middle and at the end of the flat buffer."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from scade_b200.dist import _BucketOverlap
+    from scade_b200.nerf_helpers import NeRF
+    from scade_b200.optim import flatten_parameters
+    results = {}
+    for order in ("fine_first", "fine_middle", "fine_last"):
+        torch.manual_seed(1)
+        mk = lambda: NeRF(D=2, W=8, input_ch=9, input_ch_views=3, output_ch=5, skips=[4], use_viewdirs=True)
+        coarse, fine = mk(), mk()
+        scale, shift = torch.ones(1, requires_grad=True), torch.zeros(1, requires_grad=True)
+        groups = {"fine_first": (fine, coarse, [scale, shift]), "fine_middle": (coarse, fine, [scale, shift]),
+                  "fine_last": (coarse, [scale, shift], fine)}[order]
+        flat = flatten_parameters(*groups)
+        g = torch.Generator().manual_seed(50 + rank)
+        flat.flat_grad.copy_(torch.randn(flat.flat_grad.numel(), generator=g))
+        sent = flat.flat_grad.clone()
+        b = _BucketOverlap(flat, fine, None)
+        assert b.range is not None and b.handle is not None and fine.handle().grad_ready_hook is not None
+        fine.handle().grad_ready_hook(fine.handle())          # what functional._mlp_backward does after the fine backward
+        calls = b.finish()
+        assert fine.handle().grad_ready_hook is None
+        results[order] = {"sent": sent, "got": flat.flat_grad.clone(), "calls": calls, "range": b.range, "intact": flat.intact()}
+    torch.save(results, os.path.join(out_dir, f"bucket{rank}.pt"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_bucketed_gradient_exchange_world2(tmp_path):
+    world = 2
+    mp.spawn(_bucket_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    res = [torch.load(os.path.join(tmp_path, f"bucket{r}.pt")) for r in range(world)]
+    for order, want_calls in (("fine_first", 2), ("fine_middle", 3), ("fine_last", 3)):
+        want = sum(r[order]["sent"] for r in res)
+        for r in res:
+            assert r[order]["intact"] and r[order]["calls"] == want_calls, (order, r[order]["calls"])
+            assert torch.allclose(r[order]["got"], want, rtol=1e-6, atol=1e-6), order

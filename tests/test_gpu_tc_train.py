@@ -245,3 +245,117 @@ def test_graphed_train_step_matches_eager(dev):
     np.testing.assert_allclose(losses, ref_losses, rtol=1e-3)
     diff = (flat.flat.detach() - ref_flat).abs()
     assert float(diff.mean()) < 2e-6 and float(diff.max()) < 7 * 1e-4 * 2, (float(diff.mean()), float(diff.max()))   # <= 2 lr per step
+
+
+def test_graphed_train_step_per_image_scale_shift_and_checkpoint(dev):
+    """(1) the graphed step follows the step's image: DEPTH_SCALES / DEPTH_SHIFTS are [n_img, 1] tables (RS:878-879),
+    the graph gathers row img_i through a device-side index and the gradient lands in that row only; (2) the weight streams are
+    re-packed inside the graph even when an eval render ran right before the capture; (3) optimizer.state_dict() after replays
+    carries the current step count, and load_state_dict() on a used FusedAdam adopts moments and step."""
+    from scade_b200 import nerf_helpers as NH, render as R_
+    from scade_b200.dist import GraphedTrainStep
+    from scade_b200.optim import FusedAdam, flatten_parameters
+    from tests.golden.generate_goldens import net_pair
+    N, Nc, Nf, K, n_img = 256, 16, 32, 5, 3
+    T = lambda a, d: torch.from_numpy(np.ascontiguousarray(a)).to(d)
+    rb = T(syn.make_ray_batch(N, seed=90), dev)
+    target_s, target_h = syn.make_train_targets(N, K=K, seed=91)
+    target_s, target_h = T(target_s, dev), T(target_h, dev)
+    bb_center, bb_scale = syn.bounding_box()
+    pc, pf = net_pair(8, 256)
+    nets = []
+    for p in (pc, pf):
+        net = NH.NeRF(D=8, W=256, input_ch=57, input_ch_views=3, output_ch=5, skips=[4], use_viewdirs=True, precision="tc_f16")
+        net.load_state_dict({k: torch.from_numpy(v) for k, v in p.items()})
+        nets.append(net.to(dev))
+    qf = R_.NetworkQuery(NH.get_embedder(9, 0)[0], NH.get_embedder(0, 0)[0], bb_center, bb_scale, precision="tc_f16")
+    kw = dict(network_fn=nets[0], network_query_fn=qf, N_samples=Nc, embedded_cam=torch.tensor((), device=dev), perturb=0.0,
+              N_importance=Nf, network_fine=nets[1], raw_noise_std=0.0)
+    scales = torch.nn.Parameter(torch.tensor([[1.0], [1.3], [0.8]], device=dev))                # DEPTH_SCALES (RS:878)
+    shifts = torch.nn.Parameter(torch.tensor([[0.0], [-0.1], [0.2]], device=dev))               # DEPTH_SHIFTS (RS:879)
+    params = [p for n in (nets[1], nets[0]) for p in n.parameters()]
+    flat = flatten_parameters(params, [scales, shifts])
+    opt = FusedAdam(params, lr=2e-5, flat=flat, capturable=True)
+    opt_ss = FusedAdam([scales, shifts], lr=1e-3, flat=flat, capturable=True)
+    step = GraphedTrainStep(kw, scales, shifts, flat, [opt, opt_ss], n_global=N, warmup=2)
+    with pytest.raises(ValueError):
+        step(rb, target_s, target_h)                                                              # per-image tables need img_i
+    step.calls = 0
+    s0, h0 = scales.detach().clone(), shifts.detach().clone()
+    losses = []
+    for i, img in enumerate([1, 1, 2, 0, 2]):                                                     # 2 eager steps, capture, 2 replays
+        if i == 2:
+            with torch.no_grad():                                                                 # an eval render right before the capture
+                R_.render_rays(rb[:64], True, **kw)
+        before_s = scales.detach().clone()
+        losses.append(float(step(rb, target_s, target_h, img)["loss"]))
+        moved = (scales.detach() - before_s).abs().reshape(-1) > 0
+        # Adam moves every row that has ever had a gradient (momentum); rows never selected stay put
+        seen = sorted(set([1, 1, 2, 0, 2][:i + 1]))
+        assert all(bool(moved[j]) == (j in seen) for j in range(n_img)), (i, img, moved.tolist())
+        g = scales.grad.detach().reshape(-1)
+        assert float(g[img].abs()) > 0 and all(float(g[j]) == 0.0 for j in range(n_img) if j != img), (i, img, g.tolist())
+    assert step.graph is not None and np.isfinite(losses).all()
+    # (2) the captured graph contains the two weight re-packs (fast stream: 2 launches per net)
+    assert step.launches_per_step is not None and step.launches_per_step >= 4
+    w_before = nets[1].pts_linears[3].weight.detach().clone()
+    l_a = float(step(rb, target_s, target_h, 1)["loss"])
+    l_b = float(step(rb, target_s, target_h, 1)["loss"])
+    assert not torch.equal(w_before, nets[1].pts_linears[3].weight.detach()) and l_a != l_b      # replays see the updated weights
+    # (3) checkpoint round trip
+    import copy
+    sd = copy.deepcopy(opt.state_dict())                    # what torch.save / torch.load do (state_dict() aliases the live moments)
+    steps = {int(v["step"]) for v in sd["state"].values()}
+    assert steps == {7} and opt._step == 7 and int(opt._step_t) == 7
+    m_saved = opt._m.clone()
+    opt._m.zero_(); opt._v.mul_(0.5); opt._step = 3
+    opt.load_state_dict(sd)
+    assert opt._step == 7 and int(opt._step_t) == 7 and torch.equal(opt._m, m_saved)
+    assert all(st["exp_avg"].data_ptr() >= opt._m.data_ptr() for st in opt.state.values())        # state views alias the flat moments
+    step.release()
+
+
+@pytest.mark.parametrize("hyp_full", [False, True])
+def test_space_carving_joint_sharded_matches_full_batch(dev, hyp_full):
+    """is_joint=True (H:115-119) on a ray-sharded step (SURVEY 8(e) "Exception"): per-shard [K,P] sums, their sum over the
+    shards (the all-reduce, done by hand here), then per-shard finish with the GLOBAL ray count == the full-batch loss and
+    the corresponding slices of its gradient; and both == the oracle."""
+    from scade_b200 import _lib, functional as F_
+    L = _lib.load()
+    rng = np.random.default_rng(3)
+    N, P, K = 1000, 96, 7
+    pred = rng.uniform(0.5, 4.5, (N, P)).astype(np.float32)
+    hyp = rng.uniform(0.1, 5.0, (K, N, P if hyp_full else 1)).astype(np.float32)
+    mask = (rng.random(N) > 0.2).astype(np.float32)
+    T = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    p_t, h_t, m_t = T(pred).requires_grad_(True), T(hyp).requires_grad_(True), T(mask)
+    full = F_.space_carving_loss(p_t, h_t, is_joint=True, mask=m_t, threshold=0.05)
+    full.backward()
+    ref = O.space_carving_loss(pred, hyp, True, mask, 0.05)
+    np.testing.assert_allclose(float(full), float(ref), rtol=2e-5)
+    cuts = [(0, 333), (333, 1000)]                                                               # two "ranks"
+    qs, parts = [], []
+    for lo, hi in cuts:
+        pp, hh, mm = T(pred[lo:hi]), T(hyp[:, lo:hi]), T(mask[lo:hi])
+        q = torch.empty((K, P), dtype=torch.float32, device=dev)
+        _lib.check(L.scade_space_carving_joint_accumulate(_lib.ptr(pp), _lib.ptr(hh), int(hyp_full), _lib.ptr(mm), K, hi - lo, P, 0.05,
+                                                          _lib.ptr(q), _lib.stream_ptr()), "accumulate")
+        qs.append(q)
+        parts.append((pp, hh, mm))
+    qsum = qs[0] + qs[1]                                                                          # dist.all_reduce(SUM)
+    for (lo, hi), (pp, hh, mm) in zip(cuts, parts):
+        loss = torch.empty(1, dtype=torch.float32, device=dev)
+        d_p, d_h = torch.empty_like(pp), torch.empty_like(hh)
+        ks = torch.empty(P, dtype=torch.int32, device=dev)
+        _lib.check(L.scade_space_carving_joint_finish(_lib.ptr(pp), _lib.ptr(hh), int(hyp_full), _lib.ptr(mm), _lib.ptr(qsum), K, hi - lo, N,
+                                                      P, 0.05, 1.0, _lib.ptr(loss), _lib.ptr(d_p), _lib.ptr(d_h), _lib.ptr(ks),
+                                                      _lib.stream_ptr()), "finish")
+        np.testing.assert_allclose(float(loss), float(full), rtol=1e-5)
+        np.testing.assert_allclose(d_p.cpu().numpy(), p_t.grad[lo:hi].cpu().numpy(), rtol=1e-5, atol=1e-12)
+        np.testing.assert_allclose(d_h.cpu().numpy(), h_t.grad[:, lo:hi].cpu().numpy(), rtol=1e-5, atol=1e-10)
+    # world-1 autograd wrapper == the one-call joint loss
+    p2, h2 = T(pred).requires_grad_(True), T(hyp).requires_grad_(True)
+    l2 = F_.space_carving_loss_joint_sharded(p2, h2, N, mask=m_t, threshold=0.05)
+    l2.backward()
+    assert float(l2) == float(full)
+    torch.testing.assert_close(p2.grad, p_t.grad, rtol=1e-6, atol=0)

@@ -100,3 +100,30 @@ def test_graphed_train_step_requires_capturable_optimizers():
     cap = FusedAdam(list(lin.parameters()), lr=1e-3, flat=flat, capturable=True)
     step = GraphedTrainStep({}, None, None, flat, [cap], n_global=8, warmup=2)
     assert step.graph is None and step.calls == 0 and cap.capturable
+
+
+def test_fused_adam_load_state_dict_adopts_moments_and_step():
+    """load_state_dict() on a flat FusedAdam copies exp_avg / exp_avg_sq into the flat moment buffers and takes the
+    step count, also after the optimizer has been used; state_dict() reports the live step (host logic, no kernel needed)."""
+    torch.manual_seed(0)
+    lin = torch.nn.Linear(4, 3)
+    ref = torch.optim.Adam(lin.parameters(), lr=1e-3)
+    for _ in range(5):
+        ref.zero_grad()
+        lin(torch.randn(2, 4)).pow(2).sum().backward()
+        ref.step()
+    sd = ref.state_dict()
+    lin2 = torch.nn.Linear(4, 3)
+    flat = flatten_parameters(lin2)
+    opt = FusedAdam(list(lin2.parameters()), lr=1e-3, flat=flat)
+    opt._flat_state()                                   # as after a first step: the flat moment buffers exist
+    opt._step = 2
+    opt.load_state_dict(sd)
+    assert opt._step == 5
+    w, b = list(lin2.parameters())
+    assert torch.equal(opt._m[:w.numel()].view_as(w), sd["state"][0]["exp_avg"])
+    assert torch.equal(opt._v[flat.offsets[1]:flat.offsets[1] + b.numel()].view_as(b), sd["state"][1]["exp_avg_sq"])
+    assert opt.state[w]["exp_avg"].data_ptr() == opt._m.data_ptr()
+    opt._step = 9                                       # what graph replays do (note_replay)
+    out = opt.state_dict()
+    assert {int(v["step"]) for v in out["state"].values()} == {9}
