@@ -96,6 +96,18 @@ int scade_mlp_forward_rays(const scade_net* net, int precision, const float* ray
                            float bb_scale, float* raw_out, void* workspace, size_t workspace_bytes,
                            int save_for_backward, void* stream);
 
+/* scade_mlp_forward_rays followed by scade_raw2outputs (RS:659-660 / RS:718-720) as ONE kernel: the alpha compositing
+ * (compute_weights' exclusive transmittance product + the weighted sums of raw2outputs, RS:511-562) runs in the epilogue of the
+ * last tensor-core layer on the (rgb_raw, sigma) values it just produced, so `raw` never travels through memory
+ * (raw_out may be NULL; pass a buffer for retraw).  Bit-identical to the two calls.  SCADE_PREC_TC_F16 only, and S must be 64, 128
+ * or 256 (a ray is then a whole number of 32-sample warps inside one CTA's 256 points); otherwise SCADE_ERR_UNSUPPORTED
+ * (scade_mlp_forward_rays_composite_supported tells beforehand).  weights [N,S] is required; the maps are nullable. */
+int scade_mlp_forward_rays_composite_supported(const scade_net_desc* desc, int precision, int S);
+int scade_mlp_forward_rays_composite(const scade_net* net, int precision, const float* rays, int ray_stride,
+                                     const float* z_vals, int64_t N, int S, const float* bb_center_host, float bb_scale,
+                                     float* raw_out, float* weights, float* rgb_map, float* disp_map, float* acc_map,
+                                     float* depth_map, void* stream);
+
 /* NeRF.forward (H:223-247) on an already embedded input x [P, input_ch + input_ch_views]. */
 int scade_mlp_forward_embedded(const scade_net* net, int precision, const float* x, int64_t P,
                                float* out, void* workspace, size_t workspace_bytes,

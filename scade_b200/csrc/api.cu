@@ -112,6 +112,29 @@ extern "C" int scade_mlp_forward_rays(const scade_net* net, int precision, const
                                workspace_bytes, save_for_backward, as_stream(stream));
 }
 
+extern "C" int scade_mlp_forward_rays_composite_supported(const scade_net_desc* desc, int precision, int S) {
+  return desc != nullptr && precision == SCADE_PREC_TC_F16 && check_desc(*desc) == SCADE_OK && mlp_tc_supported(*desc) &&
+         mlp_tc_composite_supported(S);
+}
+
+extern "C" int scade_mlp_forward_rays_composite(const scade_net* net, int precision, const float* rays, int ray_stride,
+                                                const float* z_vals, int64_t N, int S, const float* bb_center_host,
+                                                float bb_scale, float* raw_out, float* weights, float* rgb_map,
+                                                float* disp_map, float* acc_map, float* depth_map, void* stream) {
+  SCADE_TRY(check_net(net, precision));
+  if (N == 0) return SCADE_OK;
+  SCADE_CHECK_ARG(rays && z_vals && bb_center_host && weights && N > 0 && S > 0 && ray_stride >= 11,
+                  "mlp_forward_rays_composite: bad arguments");
+  SCADE_CHECK_ARG((reinterpret_cast<uintptr_t>(raw_out) & 15) == 0, "mlp_forward_rays_composite: raw_out must be 16-byte aligned");
+  if (!scade_mlp_forward_rays_composite_supported(&net->desc, precision, S)) {
+    set_error("mlp_forward_rays_composite: needs SCADE_PREC_TC_F16 and S in {64, 128, 256} (precision %d, S=%d)", precision, S);
+    return SCADE_ERR_UNSUPPORTED;
+  }
+  MlpCompositeOut co{weights, rgb_map, disp_map, acc_map, depth_map};
+  return mlp_tc_forward(*net, rays, ray_stride, z_vals, nullptr, N, S, bb_center_host, bb_scale, raw_out, nullptr, 0, 0,
+                        as_stream(stream), false, &co);
+}
+
 extern "C" int scade_mlp_forward_embedded(const scade_net* net, int precision, const float* x, int64_t P, float* out,
                                           void* workspace, size_t workspace_bytes, int save_for_backward, void* stream) {
   SCADE_TRY(check_net(net, precision));
@@ -216,17 +239,33 @@ extern "C" int scade_render_rays_forward(const scade_render_cfg* cfg, const floa
   float* hyp = out->pred_hyp ? out->pred_hyp : f(L.hyp);
   // coarse pass                                                                   RS:640-660
   SCADE_TRY(scade_coarse_z_vals(ray_batch, rs, N, Nc, cfg->lindisp, t_rand, z0, stream));
-  SCADE_TRY(scade_mlp_forward_rays(coarse, cfg->precision, ray_batch, rs, z0, N, Nc, cfg->bb_center, cfg->bb_scale,
-                                   f(L.raw0), ws + L.mlp, L.mlp_bytes, 0, stream));
-  // compositing (RS:660) + importance sampling + sort-merge (RS:702-713) in one launch
-  SCADE_TRY(scade_composite_resample(f(L.raw0), z0, ray_batch + 3, rs, N, Nc, out->rgb0, out->disp0, out->acc0, w0, out->depth0,
-                                     Nf, perturbed ? u_coarse : nullptr, cfg->is_joint, f(L.zs), nullptr, zf, nullptr, stream));
+  if (scade_mlp_forward_rays_composite_supported(&coarse->desc, cfg->precision, Nc)) {
+    // network + compositing in one kernel (raw never reaches memory), then importance sampling + sort-merge (RS:702-713)
+    SCADE_TRY(scade_mlp_forward_rays_composite(coarse, cfg->precision, ray_batch, rs, z0, N, Nc, cfg->bb_center, cfg->bb_scale,
+                                               nullptr, w0, out->rgb0, out->disp0, out->acc0, out->depth0, stream));
+    SCADE_TRY(scade_resample_from_z(z0, w0, N, Nc, Nf, perturbed ? u_coarse : nullptr, cfg->is_joint, f(L.zs), nullptr, zf, nullptr,
+                                    stream));
+  } else {
+    SCADE_TRY(scade_mlp_forward_rays(coarse, cfg->precision, ray_batch, rs, z0, N, Nc, cfg->bb_center, cfg->bb_scale,
+                                     f(L.raw0), ws + L.mlp, L.mlp_bytes, 0, stream));
+    // compositing (RS:660) + importance sampling + sort-merge (RS:702-713) in one launch
+    SCADE_TRY(scade_composite_resample(f(L.raw0), z0, ray_batch + 3, rs, N, Nc, out->rgb0, out->disp0, out->acc0, w0, out->depth0,
+                                       Nf, perturbed ? u_coarse : nullptr, cfg->is_joint, f(L.zs), nullptr, zf, nullptr, stream));
+  }
   // fine pass                                                                     RS:714-720
-  SCADE_TRY(scade_mlp_forward_rays(fine, cfg->precision, ray_batch, rs, zf, N, S, cfg->bb_center, cfg->bb_scale, rawf,
-                                   ws + L.mlp, L.mlp_bytes, 0, stream));
-  // compositing (RS:720) + depth hypotheses from the fine distribution (RS:723-730, 744) in one launch
-  SCADE_TRY(scade_composite_resample(rawf, zf, ray_batch + 3, rs, N, S, out->rgb_map, out->disp_map, out->acc_map, wf,
-                                     out->depth_map, Nf, perturbed ? u_fine : nullptr, cfg->is_joint, hyp, out->u, nullptr,
-                                     out->z_std, stream));
+  if (scade_mlp_forward_rays_composite_supported(&fine->desc, cfg->precision, S)) {
+    SCADE_TRY(scade_mlp_forward_rays_composite(fine, cfg->precision, ray_batch, rs, zf, N, S, cfg->bb_center, cfg->bb_scale,
+                                               out->raw, wf, out->rgb_map, out->disp_map, out->acc_map, out->depth_map, stream));
+    // depth hypotheses from the fine distribution (RS:723-730, 744)
+    SCADE_TRY(scade_resample_from_z(zf, wf, N, S, Nf, perturbed ? u_fine : nullptr, cfg->is_joint, hyp, out->u, nullptr, out->z_std,
+                                    stream));
+  } else {
+    SCADE_TRY(scade_mlp_forward_rays(fine, cfg->precision, ray_batch, rs, zf, N, S, cfg->bb_center, cfg->bb_scale, rawf,
+                                     ws + L.mlp, L.mlp_bytes, 0, stream));
+    // compositing (RS:720) + depth hypotheses from the fine distribution (RS:723-730, 744) in one launch
+    SCADE_TRY(scade_composite_resample(rawf, zf, ray_batch + 3, rs, N, S, out->rgb_map, out->disp_map, out->acc_map, wf,
+                                       out->depth_map, Nf, perturbed ? u_fine : nullptr, cfg->is_joint, hyp, out->u, nullptr,
+                                       out->z_std, stream));
+  }
   return SCADE_OK;
 }

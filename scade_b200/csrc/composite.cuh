@@ -71,10 +71,12 @@ __device__ __forceinline__ void composite_ray_fwd(const float4* __restrict__ raw
       carry *= __shfl_sync(FULL, incl, 31);
       if (valid && weights != nullptr) weights[r * S + i] = w;
       if (kStage && valid) { s_z[i] = zi; s_w[i] = w; }
-      sr += w * sigmoidf_(rw[c].x);                      // RS:543, RS:556
-      sg += w * sigmoidf_(rw[c].y);
-      sb += w * sigmoidf_(rw[c].z);
-      sdepth += w * zi;                                  // RS:558
+      // explicit fmaf: the compositing fused into the tensor-core MLP epilogue (mlp_tc.cu, kComp) repeats exactly this
+      // arithmetic in exactly this order and must produce the same bits
+      sr = fmaf(w, sigmoidf_(rw[c].x), sr);              // RS:543, RS:556
+      sg = fmaf(w, sigmoidf_(rw[c].y), sg);
+      sb = fmaf(w, sigmoidf_(rw[c].z), sb);
+      sdepth = fmaf(w, zi, sdepth);                      // RS:558
       sacc += w;                                         // RS:560
     }
   }

@@ -36,6 +36,17 @@ int mlp_fp32_backward(const scade_net& net, const float* d_out, int64_t P, float
                       size_t ws_bytes, cudaStream_t st);
 int embed_launch(const float* x, int64_t P, int multires, float* out, cudaStream_t st);
 
+// Outputs of the alpha compositing fused into the tensor-core forward (compute_weights + raw2outputs, RS:511-562)
+struct MlpCompositeOut {
+  float* weights;     // [N,S] required
+  float* rgb_map;     // [N,3] nullable
+  float* disp_map;    // [N]   nullable
+  float* acc_map;     // [N]   nullable
+  float* depth_map;   // [N]   nullable
+};
+// ray-aligned sample counts the fused epilogue handles (a ray = 2, 4 or 8 whole warps inside one CTA's 256 points)
+inline bool mlp_tc_composite_supported(int S) { return S == 64 || S == 128 || S == 256; }
+
 // entry points implemented in mlp_tc.cu (tcgen05 path)
 bool mlp_tc_supported(const scade_net_desc& d);
 size_t mlp_tc_packed_bytes(const scade_net_desc& d, bool x3 = false);
@@ -43,7 +54,7 @@ int mlp_tc_pack(const scade_net& net, void* packed_out, cudaStream_t st, bool x3
 size_t mlp_tc_workspace_bytes(const scade_net_desc& d, int64_t P, int save);
 int mlp_tc_forward(const scade_net& net, const float* rays, int ray_stride, const float* z, const float* x_embedded,
                    int64_t N, int S, const float* bb_center, float bb_scale, float* raw_out, void* workspace,
-                   size_t ws_bytes, int save, cudaStream_t st, bool x3 = false);
+                   size_t ws_bytes, int save, cudaStream_t st, bool x3 = false, const MlpCompositeOut* comp = nullptr);
 
 int mlp_tc_backward(const scade_net& net, const float* d_out, int64_t P, float* const* grads, void* workspace, size_t ws_bytes,
                     cudaStream_t st);

@@ -36,6 +36,7 @@
 #include <algorithm>
 #include <type_traits>
 
+#include "composite.cuh"
 #include "mlp_common.cuh"
 #include "tc_ptx.cuh"
 
@@ -65,6 +66,11 @@ constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;         // barriers + alignment
 constexpr int OFF_BIAS = OFF_BAR + 256;
 constexpr int FWD_SMEM_BYTES = OFF_BIAS + TILES * W * 4;
 static_assert(FWD_SMEM_BYTES <= 227 * 1024, "forward kernel shared memory exceeds the 227 KB per-CTA limit");
+// kComp (compositing fused into the views epilogue): per-chunk transmittance products of the CTA's 8 row-warps, and the
+// tile 0 -> tile 1 hand-over of a 256-sample ray (carry + 5 x 32 per-lane partial sums) in the last 768 bytes
+constexpr int OFF_COMP = FWD_SMEM_BYTES;
+constexpr int COMP_SMEM_BYTES = FWD_SMEM_BYTES + 768;      // s_prod[8] | carry (8 floats) | [5][32] partial sums = 704 B
+static_assert(COMP_SMEM_BYTES <= 227 * 1024, "kComp shared memory exceeds the 227 KB per-CTA limit");
 
 enum ASrc : int { SRC_EMB = 4 };         // 0..3 = activation chunk c
 
@@ -156,6 +162,18 @@ __device__ __forceinline__ void sincos_reduced(float arg, float* s, float* c) {
 }
 
 // ---- the kernel ------------------------------------------------------------------------------------
+// Alpha compositing (compute_weights + raw2outputs, run_scade_scannet.py:511-562) fused into the views epilogue (kComp):
+// requires rays mode and S in {64, 128, 256} (a ray is then a whole number of 32-row warps inside one CTA's 256 points).
+struct CompArgs {
+  float* weights;                 // [N,S]
+  float* rgb_map;                 // [N,3]  nullable
+  float* disp_map;                // [N]    nullable
+  float* acc_map;                 // [N]    nullable
+  float* depth_map;               // [N]    nullable
+  int write_raw;                  // also store raw [N,S,4] (retraw)
+  int pad;
+};
+
 struct FwdArgs {
   const uint8_t* packed;          // stage images, consumption order
   const float* rays; int ray_stride; const float* z; int S;     // rays mode
@@ -167,6 +185,7 @@ struct FwdArgs {
   int64_t n_pairs;
   int dbg;              // trace build only -- timing ablations (results are WRONG when set): 1 = ignore weight arrival,
                         // 2 = ignore operand readiness, 32 = no epilogue work
+  CompArgs comp;        // kComp only
 };
 
 // Activation / gradient stash of the tensor-core training path (workspace of a forward call with save_for_backward=1).
@@ -403,7 +422,7 @@ __device__ __forceinline__ void named_bar_arrive(int id, int threads) { asm vola
 
 // kStash: additionally write every layer's fp16 output chunk (TMA bulk store of the shared-memory image the next layer's
 // MMAs read anyway), the ReLU sign masks and the alpha pre-activation to the training stash.
-template <bool kStash>
+template <bool kStash, bool kComp = false>
 __global__ void __launch_bounds__(PP_THREADS, 1) nerf_mlp_tc_pp_kernel(const __grid_constant__ FwdArgs a,
                                                                        const __grid_constant__ NetPlan plan,
                                                                        const __grid_constant__ CUtensorMap tmap,
@@ -646,6 +665,17 @@ __global__ void __launch_bounds__(PP_THREADS, 1) nerf_mlp_tc_pp_kernel(const __g
 #pragma unroll
             for (int i = 0; i < 3; ++i) wst[i] = __ldg(reinterpret_cast<const float4*>(&tail->w_rgb_p[0][0]) + i * 32 + lane);
           }
+          // kComp: this sample's z, its successor's and the ray's direction norm, fetched under the MMAs (RS:514-516)
+          float c_z = 0.f, c_zn = 0.f, c_norm = 0.f;
+          if (kComp && half == 0) {
+            const int64_t pc = live ? p_raw : 0;
+            const int si = (int)(pc & (int64_t)(a.S - 1));
+            c_z = a.z[pc];
+            c_zn = (si + 1 < a.S) ? a.z[pc + 1] : c_z;
+            const float* rd = a.rays + (pc / a.S) * a.ray_stride + 3;
+            const float dx = rd[0], dy = rd[1], dz = rd[2];
+            c_norm = sqrtf(dx * dx + dy * dy + dz * dz);
+          }
           mbar_wait(my_acc, acc_phase);
           acc_phase ^= 1;
           tc_fence_after();
@@ -724,11 +754,82 @@ __global__ void __launch_bounds__(PP_THREADS, 1) nerf_mlp_tc_pp_kernel(const __g
             named_bar_sync(pair_bar, 64);
             const float4 o = *scratch;
             const float al = (alpha + o.w) + __ldg(&tail->b_alpha);
-            if (live) {
-              a.out[p_raw] = make_float4((pr + o.x) + __ldg(&tail->b_rgb[0]), (pg + o.y) + __ldg(&tail->b_rgb[1]),
-                                         (pb + o.z) + __ldg(&tail->b_rgb[2]), softplus_beta10(al));
-            }
+            const float4 rawv = make_float4((pr + o.x) + __ldg(&tail->b_rgb[0]), (pg + o.y) + __ldg(&tail->b_rgb[1]),
+                                            (pb + o.z) + __ldg(&tail->b_rgb[2]), softplus_beta10(al));
+            if (live && (!kComp || a.comp.write_raw)) a.out[p_raw] = rawv;
             if (kStash) reinterpret_cast<float*>(sa.ws + sa.L.alpha)[tile_g * TILE_M + row] = al;
+            if (kComp) {
+              // ---- compute_weights + raw2outputs (RS:511-562) on the rows of this tile: warp == 32 consecutive samples of one ray.
+              // Same device functions, same operation order as composite_ray_fwd (composite.cuh): bit-identical results.
+              const int S = a.S, cpr = S >> 5;                   // chunks (warps) per ray: 2, 4 or 8
+              const int cc = tile * 4 + quarter;                 // this warp's chunk among the CTA's 256 points
+              const int cl = cc & (cpr - 1);                     // ... and within its ray
+              const int nch = cpr < 4 ? cpr : 4;                 // chunks of a ray inside one tile
+              const int clt = cl & 3;                            // chunk within the ray's part of this tile
+              float* s_prod = reinterpret_cast<float*>(smem + OFF_COMP);             // [8]
+              float* s_hand = s_prod + 8;                                            // [0] carry, [8 + 32 k + lane] per-lane partial sums (k < 5): 704 B in all
+              float* s_terms = reinterpret_cast<float*>(a_tile + CHUNK_BYTES);      // [4 warps][5][32] in the tile's dead chunk 1
+              const int comp_bar = 11 + tile, x_bar = 13;
+              const int si = (int)(p_raw & (int64_t)(S - 1));
+              const SampleTerms t = sample_terms(rawv.w, 0.f, c_z, c_zn, si == S - 1, c_norm);
+              const float tf = live ? t.tfac : 1.0f;
+              const float incl = warp_scan_prod(tf, lane);
+              float excl = __shfl_up_sync(FULL, incl, 1);
+              if (lane == 0) excl = 1.0f;
+              const float pwarp = __shfl_sync(FULL, incl, 31);
+              if (lane == 0) s_prod[cc] = pwarp;
+              named_bar_sync(comp_bar, 128);
+              float carry = 1.0f;
+              if (cpr == 8 && tile == 1) {                       // 256-sample ray: tile 0 holds its first four chunks
+                named_bar_sync(x_bar, 160);
+                carry = s_hand[0];
+              }
+              for (int k = 0; k < clt; ++k) carry *= s_prod[cc - clt + k];
+              const float w = live ? t.alpha * (carry * excl) : 0.f;
+              if (live) a.comp.weights[p_raw] = w;
+              float* st = s_terms + quarter * 160;
+              st[lane] = w;
+              st[32 + lane] = sigmoidf_(rawv.x);                 // RS:543
+              st[64 + lane] = sigmoidf_(rawv.y);
+              st[96 + lane] = sigmoidf_(rawv.z);
+              st[128 + lane] = c_z;
+              named_bar_sync(comp_bar, 128);
+              if (clt == nch - 1) {                              // the warp holding the ray's last chunk in this tile sums the ray
+                float sr = 0.f, sg = 0.f, sb = 0.f, sdepth = 0.f, sacc = 0.f;
+                if (cpr == 8 && tile == 1) {
+                  sr = s_hand[8 + lane]; sg = s_hand[40 + lane]; sb = s_hand[72 + lane];
+                  sdepth = s_hand[104 + lane]; sacc = s_hand[136 + lane];
+                }
+                for (int k = 0; k < nch; ++k) {
+                  const float* q = s_terms + (quarter - (nch - 1) + k) * 160;
+                  const float wk = q[lane];
+                  sr = fmaf(wk, q[32 + lane], sr);               // RS:556
+                  sg = fmaf(wk, q[64 + lane], sg);
+                  sb = fmaf(wk, q[96 + lane], sb);
+                  sdepth = fmaf(wk, q[128 + lane], sdepth);      // RS:558
+                  sacc += wk;                                    // RS:560
+                }
+                if (cpr == 8 && tile == 0) {
+                  if (lane == 0) s_hand[0] = carry * pwarp;      // ((p0 p1) p2) p3
+                  s_hand[8 + lane] = sr; s_hand[40 + lane] = sg; s_hand[72 + lane] = sb;
+                  s_hand[104 + lane] = sdepth; s_hand[136 + lane] = sacc;
+                  __threadfence_block();
+                  named_bar_arrive(x_bar, 160);
+                } else {
+                  sr = warp_sum(sr); sg = warp_sum(sg); sb = warp_sum(sb); sdepth = warp_sum(sdepth); sacc = warp_sum(sacc);
+                  if (lane == 0 && live) {
+                    const int64_t r = p_raw / S;
+                    if (a.comp.rgb_map) { a.comp.rgb_map[r * 3] = sr; a.comp.rgb_map[r * 3 + 1] = sg; a.comp.rgb_map[r * 3 + 2] = sb; }
+                    if (a.comp.depth_map) a.comp.depth_map[r] = sdepth;
+                    if (a.comp.acc_map) a.comp.acc_map[r] = sacc;
+                    if (a.comp.disp_map) {
+                      const float q = sdepth / sacc;             // RS:559; torch.max propagates the nan of 0/0
+                      a.comp.disp_map[r] = (q != q) ? q : 1.0f / fmaxf(1e-10f, q);
+                    }
+                  }
+                }
+              }
+            }
           }
           if (kStash) {
             *reinterpret_cast<uint2*>(sa.ws + sa.L.maskv + (size_t)(tile_g * TILE_M + row) * 16 + half * 8) = make_uint2(sgn[0], sgn[1]);
@@ -1005,6 +1106,7 @@ static int set_kernel_attributes() {
   if (dev >= 0 && dev < 64 && done[dev]) return SCADE_OK;
   SCADE_CUDA(cudaFuncSetAttribute(nerf_mlp_tc_pp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM_BYTES));
   SCADE_CUDA(cudaFuncSetAttribute(nerf_mlp_tc_pp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM_BYTES));
+  SCADE_CUDA(cudaFuncSetAttribute(nerf_mlp_tc_pp_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, COMP_SMEM_BYTES));
   SCADE_CUDA(cudaFuncSetAttribute(nerf_mlp_tc_x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM_BYTES));
   SCADE_CUDA(cudaFuncSetAttribute(nerf_mlp_tc_dgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
   SCADE_CUDA(cudaFuncSetAttribute(nerf_mlp_tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM_BYTES));
@@ -1075,7 +1177,11 @@ int mlp_tc_stash_layout(const scade_net_desc& d, int64_t P, int64_t* out, int n)
 
 int mlp_tc_forward(const scade_net& net, const float* rays, int ray_stride, const float* z, const float* x_embedded,
                    int64_t N, int S, const float* bb_center, float bb_scale, float* raw_out, void* workspace,
-                   size_t ws_bytes, int save, cudaStream_t st, bool x3) {
+                   size_t ws_bytes, int save, cudaStream_t st, bool x3, const MlpCompositeOut* comp) {
+  if (comp != nullptr && (x3 || save || rays == nullptr || !mlp_tc_composite_supported(S) || comp->weights == nullptr)) {
+    set_error("mlp_forward: fused compositing needs SCADE_PREC_TC_F16 without save_for_backward, rays mode and S in {64,128,256} (S=%d)", S);
+    return SCADE_ERR_UNSUPPORTED;
+  }
   if (x3 && save) {
     set_error("mlp_forward (tc_f16x3): the tight tensor-core mode is forward-only; train through SCADE_PREC_FP32 or SCADE_PREC_TC_F16");
     return SCADE_ERR_UNSUPPORTED;
@@ -1094,6 +1200,11 @@ int mlp_tc_forward(const scade_net& net, const float* rays, int ray_stride, cons
   a.multires = net.desc.multires; a.multires_views = net.desc.multires_views;
   a.out = reinterpret_cast<float4*>(raw_out);
   a.n_pairs = ceil_div<int64_t>(a.P, tc::TILES * tc::TILE_M);
+  if (comp != nullptr) {
+    a.comp.weights = comp->weights; a.comp.rgb_map = comp->rgb_map; a.comp.disp_map = comp->disp_map;
+    a.comp.acc_map = comp->acc_map; a.comp.depth_map = comp->depth_map;
+    a.comp.write_raw = raw_out != nullptr;
+  }
 #if SCADE_TC_TRACE
   { const char* e = getenv("SCADE_TC_DBG"); a.dbg = e ? atoi(e) : 0; }
 #endif
@@ -1124,8 +1235,11 @@ int mlp_tc_forward(const scade_net& net, const float* rays, int ray_stride, cons
   const int64_t n_steps = (a.n_pairs + 1) / 2;
   const int clusters = (int)std::min<int64_t>(n_steps, num_sms() / 2);
   void* args[] = {&a, &plan, &tmap, &sa};
-  SCADE_TRY(tc::launch_pair(save ? (const void*)tc::nerf_mlp_tc_pp_kernel<true> : (const void*)tc::nerf_mlp_tc_pp_kernel<false>,
-                            clusters, tc::PP_THREADS, tc::FWD_SMEM_BYTES, st, args));
+  if (comp != nullptr)
+    SCADE_TRY(tc::launch_pair((const void*)tc::nerf_mlp_tc_pp_kernel<false, true>, clusters, tc::PP_THREADS, tc::COMP_SMEM_BYTES, st, args));
+  else
+    SCADE_TRY(tc::launch_pair(save ? (const void*)tc::nerf_mlp_tc_pp_kernel<true> : (const void*)tc::nerf_mlp_tc_pp_kernel<false>,
+                              clusters, tc::PP_THREADS, tc::FWD_SMEM_BYTES, st, args));
   SCADE_LAUNCH_CHECK();
   return SCADE_OK;
 }

@@ -233,6 +233,30 @@ def mlp_forward_rays(handle, rays, z_vals, bb_center, bb_scale, precision=PREC_F
                             need_grad, *handle.params)
 
 
+def composite_fusable(handle, precision, S):
+    """True when scade_mlp_forward_rays_composite handles this (network, precision, samples-per-ray) combination."""
+    return bool(_L().scade_mlp_forward_rays_composite_supported(byref(handle.desc), PRECISIONS[precision], int(S)))
+
+
+def mlp_forward_rays_composite(handle, rays, z_vals, bb_center, bb_scale, precision=PREC_TC_F16, retraw=False):
+    """run_network + raw2outputs (RS:659-660 / RS:718-720) as one kernel (no autograd): the alpha compositing runs in the
+    epilogue of the last tensor-core layer.  Returns (rgb_map, disp_map, acc_map, weights, depth_map, raw or None)."""
+    precision = PRECISIONS[precision]
+    rays, z_vals = f32(rays), f32(z_vals)
+    N, S = z_vals.shape
+    dev = z_vals.device
+    rgb = torch.empty((N, 3), dtype=torch.float32, device=dev)
+    disp, acc, depth = (torch.empty((N,), dtype=torch.float32, device=dev) for _ in range(3))
+    w = torch.empty((N, S), dtype=torch.float32, device=dev)
+    raw = torch.empty((N, S, 4), dtype=torch.float32, device=dev) if retraw else None
+    net = handle.struct(precision)
+    check(_L().scade_mlp_forward_rays_composite(byref(net), precision, ptr(rays), rays.shape[1], ptr(z_vals), N, S,
+                                                _lib.host_floats([float(c) for c in bb_center]), float(bb_scale), ptr(raw), ptr(w),
+                                                ptr(rgb), ptr(disp), ptr(acc), ptr(depth), stream_ptr()),
+          "scade_mlp_forward_rays_composite")
+    return rgb, disp, acc, w, depth, raw
+
+
 def mlp_forward_embedded(handle, x, precision=PREC_FP32):
     """NeRF.forward (H:223-247) on embedded inputs [..., in_ch + in_views] -> [..., 4]."""
     precision = PRECISIONS[precision]

@@ -226,3 +226,37 @@ def test_mlp_x3_vs_oracle(dev, P):
         dr = np.abs(raw - ref_r)
         print(f"mlp x3 rays mode: max |raw - oracle| = {dr.max():.3e}")
         assert dr.max() <= 1e-3
+
+
+@pytest.mark.parametrize("S,N", [(64, 37), (128, 19), (256, 5), (256, 300), (128, 1)])
+def test_fused_compositing_is_bit_identical(dev, S, N):
+    """north_star: the cumprod alpha-composite fused into the epilogue of the last GEMM.  scade_mlp_forward_rays_composite
+    (one kernel: raw never reaches memory) against scade_mlp_forward_rays + scade_raw2outputs (RS:659-660, RS:511-562):
+    every output bit-identical, for 2, 4 and 8 warps per ray, ragged last tiles and retraw on / off."""
+    from scade_b200 import functional as F_, nerf_helpers as NH
+    params = syn.make_nerf_params(seed=11, D=8, W=256, bias_scale=0.05, alpha_bias=0.5, weight_gain=1.3)
+    net = NH.NeRF(D=8, W=256, input_ch=57, input_ch_views=3, output_ch=5, skips=[4], use_viewdirs=True, precision="tc_f16")
+    net.load_state_dict({k: torch.from_numpy(v) for k, v in params.items()})
+    net = net.to(dev).requires_grad_(False)
+    h = net.handle()
+    assert F_.composite_fusable(h, "tc_f16", S) and not F_.composite_fusable(h, "tc_f16", 192) and not F_.composite_fusable(h, "fp32", S)
+    bb_center, bb_scale = syn.bounding_box()
+    rb = T(syn.make_ray_batch(N, seed=60 + S), dev)
+    rng = np.random.default_rng(S + N)
+    z = np.sort(rng.uniform(0.1, 5.0, (N, S)).astype(np.float32), -1)
+    z_t = T(z, dev)
+    with torch.no_grad():
+        raw = F_.mlp_forward_rays(h, rb, z_t, bb_center, bb_scale, "tc_f16")
+        ref = F_.raw2outputs(raw, z_t, rb[:, 3:6].contiguous())                     # (rgb, disp, acc, weights, depth)
+        for retraw in (False, True):
+            rgb, disp, acc, w, depth, raw2 = F_.mlp_forward_rays_composite(h, rb, z_t, bb_center, bb_scale, "tc_f16", retraw=retraw)
+            torch.cuda.synchronize()
+            for name, a, b in (("weights", w, ref[3]), ("rgb_map", rgb, ref[0]), ("depth_map", depth, ref[4]), ("acc_map", acc, ref[2])):
+                np.testing.assert_array_equal(npy(a), npy(b), err_msg=f"{name} S={S} N={N} retraw={retraw}")
+            np.testing.assert_array_equal(npy(disp), npy(ref[1]))                   # NaN where acc == 0 on both sides (RS:559)
+            if retraw:
+                np.testing.assert_array_equal(npy(raw2), npy(raw))
+    # and against the oracle's compositing of the same raw values (fp32 tolerance)
+    o = O.raw2outputs(npy(raw), z, npy(rb)[:, 3:6])
+    np.testing.assert_allclose(npy(w), o[3], rtol=2e-5, atol=2e-7)
+    np.testing.assert_allclose(npy(rgb), o[0], rtol=2e-5, atol=2e-6)

@@ -357,5 +357,5 @@ def test_space_carving_joint_sharded_matches_full_batch(dev, hyp_full):
     p2, h2 = T(pred).requires_grad_(True), T(hyp).requires_grad_(True)
     l2 = F_.space_carving_loss_joint_sharded(p2, h2, N, mask=m_t, threshold=0.05)
     l2.backward()
-    assert float(l2) == float(full)
+    np.testing.assert_allclose(float(l2.detach()), float(full.detach()), rtol=1e-6)    # the [K,P] sums are float atomics: order varies
     torch.testing.assert_close(p2.grad, p_t.grad, rtol=1e-6, atol=0)
