@@ -353,6 +353,15 @@ def run_gpu(args):
             base = cpu_arm(N_RAYS, 2, 1)
             line["cpu_baseline"] = {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")}
         print(json.dumps(line), flush=True)
+    if world > 1:
+        # the other ranks must not busy-wait in an NCCL barrier (one spinning host thread each) while rank 0 times the CPU
+        # baseline on the same cores: they block on the rendezvous store's socket instead
+        import datetime
+        store = dist.distributed_c10d._get_default_store()
+        if rank == 0:
+            store.set("scade_bench_rank0_done", "1")
+        else:
+            store.wait(["scade_bench_rank0_done"], datetime.timedelta(minutes=15))
     finish(world)
 
 

@@ -503,7 +503,8 @@ class _SpaceCarvingJointShardedFn(torch.autograd.Function):
         qsum = torch.empty((K, P), dtype=torch.float32, device=dev)
         check(_L().scade_space_carving_joint_accumulate(ptr(pred), ptr(hyp), int(full), ptr(mask), K, N, P, float(threshold),
                                                         ptr(qsum), stream_ptr()), "scade_space_carving_joint_accumulate")
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        from .dist import _world
+        if _world(group)[1] > 1:
             dist.all_reduce(qsum, op=dist.ReduceOp.SUM, group=group)
         loss = torch.empty((1,), dtype=torch.float32, device=dev)
         d_pred = torch.empty_like(pred) if want else None

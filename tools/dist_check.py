@@ -73,6 +73,37 @@ if rank == 0:
           f"worst gradient rel err {worst:.2e}", flush=True)
 ok &= dl < 1e-5 and worst < 2e-3     # fp32 summation order (atomics / split-K over different row counts)
 
+# ---- (1b) flat storage: two-bucket exchange (fine net early, under the coarse backward), default and is_joint loss ----
+from scade_b200.optim import flatten_parameters  # noqa: E402
+
+
+def run_flat(lo, hi, n_global, group_reduce, is_joint):
+    kw = make(8, 256, "fp32", True)
+    scale = torch.tensor([1.1], device=dev, requires_grad=True)
+    shift = torch.tensor([-0.05], device=dev, requires_grad=True)
+    flat = flatten_parameters(kw["network_fine"], kw["network_fn"], [scale, shift])
+    import scade_b200.dist as D_
+    saved = D_._world
+    if not group_reduce:
+        D_._world = lambda group=None: (0, 1)
+    losses = sharded_train_step(T(rb[lo:hi]), T(target_s[lo:hi]), T(target_h[:, lo:hi]), scale, shift, kw, n_global=n_global,
+                                t_rand=T(t_rand[lo:hi]), u_coarse=T(u_c[lo:hi]), u_fine=T(u_f[lo:hi]), flat=flat, is_joint=is_joint)
+    D_._world = saved
+    torch.cuda.synchronize()
+    return losses, flat.flat_grad[:flat.numel].clone()
+
+
+for is_joint in (False, True):
+    l_sh, g_sh = run_flat(lo, hi, N, True, is_joint)
+    l_1, g_1 = run_flat(0, N, N, False, is_joint)
+    worst = float((g_sh - g_1).abs().max() / g_1.abs().max())
+    dl = max(abs(float(l_sh[k]) - float(l_1[k])) / abs(float(l_1[k])) for k in ("loss", "space_carving", "img_loss", "img_loss0"))
+    if rank == 0:
+        print(f"flat two-bucket train step x{world} (is_joint={is_joint}): loss {float(l_sh['loss']):.6f} vs single {float(l_1['loss']):.6f}, "
+              f"space_carving {float(l_sh['space_carving']):.6f} vs {float(l_1['space_carving']):.6f} (worst rel {dl:.2e}); "
+              f"flat gradient rel err {worst:.2e}", flush=True)
+    ok &= dl < 1e-5 and worst < 2e-3
+
 # ---- (2) image render ----
 kw = make(8, 256, "tc_f16", False)
 c2w = torch.from_numpy(syn.spiral_poses(8)[3])
