@@ -96,12 +96,14 @@ def main():
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--warmup", type=int, default=1)
     ap.add_argument("--threads", type=int, default=0)
+    ap.add_argument("--coarse", type=int, default=128)
+    ap.add_argument("--fine", type=int, default=128)
     a = ap.parse_args()
     if a.install:
         print(install() or "no reference at " + REF_SRC)
         return
     threads = a.threads or len(os.sched_getaffinity(0))
-    print(json.dumps(run(a.rays, a.steps, a.warmup, threads)), flush=True)
+    print(json.dumps(run(a.rays, a.steps, a.warmup, threads, a.coarse, a.fine)), flush=True)
 
 
 if __name__ == "__main__":

@@ -35,6 +35,14 @@ WORKLOAD = f"render_rays fwd, {N_RAYS} rays x ({N_COARSE}c+{N_FINE}f), {NET_D}x{
 METRIC = "rays/sec (4096 rays x 256 samples, 8x256 MLP)"
 
 
+def set_shape(n_rays, n_coarse, n_fine, tag):
+    """Re-point the render workload at another BASELINE config (C2: 1024 rays x (64c + 128f))."""
+    global N_RAYS, N_COARSE, N_FINE, WORKLOAD, METRIC
+    N_RAYS, N_COARSE, N_FINE = n_rays, n_coarse, n_fine
+    WORKLOAD = f"{tag}: render_rays fwd, {N_RAYS} rays x ({N_COARSE}c+{N_FINE}f), {NET_D}x{NET_W} MLP x2 nets, det sampling"
+    METRIC = f"rays/sec ({N_RAYS} rays x {N_COARSE + N_FINE} samples, 8x256 MLP)"
+
+
 def load_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -52,7 +60,7 @@ def load_peaks():
 def workload_config():
     """`config` of the JSON line -- identical in both arms (the driver compares them)."""
     return {"workload": WORKLOAD, "rays_per_step": N_RAYS, "samples": f"{N_COARSE}c+{N_FINE}f", "net": f"{NET_D}x{NET_W} x2",
-            "rays": "synthetic.make_ray_batch(4096, seed=50): 640x480 pinhole camera, near 0.1, far 5.0",
+            "rays": f"synthetic.make_ray_batch(4096, seed=50)[:{N_RAYS}]: 640x480 pinhole camera, near 0.1, far 5.0",
             "weights": "Xavier-uniform random init (synthetic.make_nerf_params, seeds 10/11)", "sampling": "perturb=0 (deterministic)"}
 
 
@@ -74,7 +82,7 @@ def cpu_arm(n_rays, steps, warmup):
     import reference_arm
     if reference_arm.locate() is not None:
         r = subprocess.run([sys.executable, script, "--rays", str(n_rays), "--steps", str(steps), "--warmup", str(warmup),
-                            "--threads", str(cores)], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+                            "--threads", str(cores), "--coarse", str(N_COARSE), "--fine", str(N_FINE)], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
         for line in reversed(r.stdout.strip().splitlines()):
             if line.startswith("{"):
                 return json.loads(line)
@@ -208,7 +216,7 @@ def run_gpu(args):
     qf = R_.NetworkQuery(NH.get_embedder(9, 0)[0], NH.get_embedder(0, 0)[0], bb_center, bb_scale, precision=prec)
     kwargs = dict(network_fn=netc, network_query_fn=qf, N_samples=N_COARSE, embedded_cam=torch.tensor((), device=dev),
                   retraw=False, perturb=0.0, N_importance=N_FINE, network_fine=netf, raw_noise_std=0.0)
-    rb_host = torch.from_numpy(syn.make_ray_batch(N_RAYS, seed=50 + rank)).pin_memory()
+    rb_host = torch.from_numpy(np.ascontiguousarray(syn.make_ray_batch(4096, seed=50 + rank)[:N_RAYS])).pin_memory()
     rb_dev = rb_host.to(dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
 
@@ -283,12 +291,16 @@ def run_gpu(args):
 
     # ---- dominant kernel alone: fine-pass MLP launch (4096 x 256 points) ----
     z_f = step_resident()["z_vals"]
+    fused_comp = F_.composite_fusable(netf.handle(), prec, N_COARSE + N_FINE)
     mlp_ev = []
     for i in range(3 + args.steps):
         flush.zero_()
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record()
-        F_.mlp_forward_rays(netf.handle(), rb_dev, z_f, bb_center, bb_scale, prec)
+        if fused_comp:       # the launch the step actually makes: network + alpha compositing in one kernel
+            F_.mlp_forward_rays_composite(netf.handle(), rb_dev, z_f, bb_center, bb_scale, prec)
+        else:
+            F_.mlp_forward_rays(netf.handle(), rb_dev, z_f, bb_center, bb_scale, prec)
         e.record()
         if i >= 3:
             mlp_ev.append((s, e))
@@ -321,7 +333,8 @@ def run_gpu(args):
         is_tc = prec in ("tc_f16", "tc_f16x3")
         dtype = {"tc_f16": "f16 operands / f32 accumulate (tcgen05)", "fp32": "f32",
                  "tc_f16x3": "f16 hi/lo operand pairs, 3 tcgen05 passes / f32 accumulate (fp32-level tolerance)"}[prec]
-        kernel = {"tc_f16": "nerf_mlp_tc_pp_kernel", "tc_f16x3": "nerf_mlp_tc_x3_kernel", "fp32": "sgemm_kernel chain"}[prec]
+        kernel = {"tc_f16": "nerf_mlp_tc_pp_kernel<false,true> = field network + alpha compositing" if fused_comp else "nerf_mlp_tc_pp_kernel",
+                  "tc_f16x3": "nerf_mlp_tc_x3_kernel", "fp32": "sgemm_kernel chain"}[prec]
         line = {
             "metric": METRIC, "value": total_rays / (dev_ms * 1e-3), "unit": "rays/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -339,7 +352,7 @@ def run_gpu(args):
                     "eager_api": "scade_b200.render.render_rays called eagerly every step (same copies; rank-0 clock)"},
             "gpu_launches": int(launches),
             "wall_ms_timed_region": wall * 1e3,
-            "roofline": {"bound": "tensor", "kernel": f"{kernel} (fine pass, 4096x256 points)",
+            "roofline": {"bound": "tensor", "kernel": f"{kernel} (fine pass, {N_RAYS}x{N_COARSE + N_FINE} points)",
                          "achieved": achieved, "peak": burst, "unit": "TFLOP/s", "frac": achieved / burst,
                          "peak_source": f"{src} bf16 dense burst (kernel timed alone)", "traffic": traffic,
                          "flop_per_launch": flop_launch, "ms_per_launch": mlp_ms,
@@ -565,13 +578,21 @@ def run_image(args):
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     psnr = None
-    if video and args.precision == "tc_f16":
-        kw32 = make_kwargs("fp32")
+    if video:
+        # BASELINE config 5 "PSNR vs reference": the rendered frames against the fp32 ORACLE (oracle/scade_oracle.py, the CPU
+        # restatement pinned to the reference's goldens) on a random 1024-pixel sub-sample of three frames -- the checker leg
+        from oracle import scade_oracle as O
+        from scade_b200 import functional as F_
         vals = []
         for i in (0, 40, 80):
-            a = frame(i)["rgb_map"]
-            b = frame(i, kw32)["rgb_map"]
-            vals.append(float(-10.0 * torch.log10(torch.mean((a - b) ** 2))))
+            a = frame(i)["rgb_map"].reshape(H * W, 3)
+            if rank == 0:
+                pix = np.random.default_rng(1000 + i).choice(H * W, 1024, replace=False)
+                rays = F_.camera_ray_batch(H, W, syn.CAM_INTRINSIC, poses[i % len(poses)], 0.1, 5.0, device=dev)
+                rb_np = rays[torch.from_numpy(pix).to(dev)].cpu().numpy()
+                ref = O.render_rays(rb_np, pc, pf, bb_center, bb_scale, Nc, Nf)["rgb_map"]
+                got = a[torch.from_numpy(pix).to(dev)].cpu().numpy()
+                vals.append(float(-10.0 * np.log10(np.mean((got.astype(np.float64) - ref) ** 2) + 1e-30)))
         psnr = vals
     if rank == 0:
         sec = float(ms) * 1e-3 / args.steps
@@ -589,7 +610,8 @@ def run_image(args):
                 "roofline": {"bound": "tensor", "achieved": flop_frame / sec / 1e12 / world, "peak": sustained, "unit": "TFLOP/s per GPU",
                              "frac": flop_frame / sec / 1e12 / world / sustained, "peak_source": f"{src} bf16 sustained", "traffic": None}}
         if psnr is not None:
-            line["psnr_vs_fp32_path_db"] = psnr
+            line["psnr_vs_oracle_db"] = psnr
+            line["psnr_note"] = "rgb of frames 0 / 40 / 80 vs the fp32 CPU oracle on 1024 random pixels per frame"
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
@@ -610,10 +632,13 @@ def main():
     ap.add_argument("--optimizer", default="fused", choices=["fused", "torch"],
                     help="train workload: fused = flat parameters + scade_adam_step (default); torch = torch.optim.Adam on 48 tensors")
     ap.add_argument("--train-graph", type=int, default=1, help="train workload: replay the step as one CUDA graph (0 = eager)")
-    ap.add_argument("--workload", default="render", choices=["render", "train", "image", "video"],
-                    help="render = BASELINE metric (default); train = config 3 (4096 rays, 64c+128f, K=20, fwd+loss+bwd+allreduce+Adam); "
+    ap.add_argument("--workload", default="render", choices=["render", "render_c2", "train", "image", "video"],
+                    help="render = BASELINE metric (default); render_c2 = config 2 (1024 rays x (64c+128f), 1 GPU); train = config 3 (4096 rays, 64c+128f, K=20, fwd+loss+bwd+allreduce+Adam); "
                          "image / video = configs 4 / 5 (full 640x480 frames, pixels sharded across the GPUs)")
     args = ap.parse_args()
+    if args.workload == "render_c2":
+        set_shape(1024, 64, 128, "BASELINE config 2")
+        args.no_train = True
     if args.impl == "reference":
         run_reference(args)
     elif args.workload == "train":

@@ -261,6 +261,18 @@ int scade_gather_train_batch(int H, int W, const float* intrinsic_host, const fl
                              float* ray_batch, float* rays_o_d, float* target_s, float* target_d,
                              uint8_t* target_vd, float* target_h, float* mask, float* u_out, void* stream);
 
+/* The same with the K hypotheses read from the resident fp16 store ("<img>_<k>.npy hypotheses -> pinned /
+ * GPU-resident fp16 store"): hypotheses_f16 [K,H,W] IEEE half; target_h receives the exact fp32 value of each half. */
+int scade_gather_train_batch_h16(int H, int W, const float* intrinsic_host, const float* c2w_host,
+                                 const int64_t* select_inds, int64_t N, float near, float far, const float* image,
+                                 const float* depth, int depth_channels, const uint8_t* valid_depth,
+                                 const uint16_t* hypotheses_f16, int K, const float* cached_u, int n_u, int mask_corners,
+                                 float* ray_batch, float* rays_o_d, float* target_s, float* target_d,
+                                 uint8_t* target_vd, float* target_h, float* mask, float* u_out, void* stream);
+
+/* Builds the store: out[i] = half(clip(hyp[i], near, far)) (the clip of data/load_scene.py:348), n elements. */
+int scade_pack_hypotheses_f16(const float* hyp, int64_t n, float near, float far, uint16_t* out, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Optimizer: torch.optim.Adam(grad_vars, lr, betas=(0.9, 0.999)).step()  (RS:469, RS:993)
  * --------------------------------------------------------------------------------------------- */

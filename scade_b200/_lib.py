@@ -86,6 +86,9 @@ _SIGNATURES = {
     "scade_img2mse": (c_int, [_P, _P, c_int64, c_int64, c_float, _P, _P, _P]),
     "scade_gather_train_batch": (c_int, [c_int, c_int, POINTER(c_float), POINTER(c_float), _P, c_int64, c_float, c_float, _P, _P,
                                          c_int, _P, _P, c_int, _P, c_int, c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "scade_gather_train_batch_h16": (c_int, [c_int, c_int, POINTER(c_float), POINTER(c_float), _P, c_int64, c_float, c_float, _P, _P,
+                                             c_int, _P, _P, c_int, _P, c_int, c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "scade_pack_hypotheses_f16": (c_int, [_P, c_int64, c_float, c_float, _P, _P]),
     "scade_video_frame": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_float, _P, _P, _P, _P, _P, _P]),
     "scade_adam_step": (c_int, [_P, _P, _P, _P, c_int64, c_double, c_double, c_double, c_double, c_int64, _P]),
     "scade_adam_step_graph": (c_int, [_P, _P, _P, _P, c_int64, _P, c_double, c_double, c_double, _P, _P]),

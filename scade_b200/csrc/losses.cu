@@ -60,14 +60,32 @@ space_carving_ray_kernel(const float* __restrict__ pred, const float* __restrict
     float ray_sum = 0.f;
     for (int p = lane; p < P; p += 32) {
       float pr = pred[r * P + p];
-      float best = 0.f, bsgn = 0.f;
+      // min over k of m |pred - h_k| (thresholded): m >= 0 is the ray's constant and the threshold map is monotone, so the
+      // arg-min is the NEAREST hypothesis -- the loop tracks |pred - h| alone (4 instructions per hypothesis: the kernel is
+      // issue-bound at K * P = 2560 distances per ray, not HBM-bound) and mask / threshold / sign are applied once to the
+      // winner.  Strict '<' keeps the first k on ties like torch.min(dim) (H:124); where the winner's distance is zeroed
+      // (m == 0 or below the threshold) its gradient is zero whichever k is named, so the tie order there is unobservable.
+      float best_ad = 0.f, best_h = 0.f;
       int bk = 0;
-      for (int k = 0; k < K; ++k) {
-        float h = hyp_full ? hyp[((int64_t)k * N + r) * P + p] : s_h[k * SC_RAYS + lr];
-        float sg;
-        float d = sc_dist(pr, h, m, thr, sg);
-        if (k == 0 || d < best) { best = d; bsgn = sg; bk = k; }   // H:124 (first arg-min)
+      if (hyp_full) {
+        for (int k = 0; k < K; ++k) {
+          const float h = hyp[((int64_t)k * N + r) * P + p];
+          const float ad = fabsf(pr - h);
+          if (k == 0 || ad < best_ad) { best_ad = ad; best_h = h; bk = k; }
+        }
+      } else {
+        const float* hk = s_h + lr;
+        best_h = hk[0];
+        best_ad = fabsf(pr - best_h);
+#pragma unroll 4
+        for (int k = 1; k < K; ++k) {
+          const float h = hk[k * SC_RAYS];
+          const float ad = fabsf(pr - h);
+          if (ad < best_ad) { best_ad = ad; best_h = h; bk = k; }
+        }
       }
+      float bsgn;
+      const float best = sc_dist(pr, best_h, m, thr, bsgn);
       ray_sum += best;
       float g = bsgn * gval;
       if (d_pred) d_pred[r * P + p] = g;

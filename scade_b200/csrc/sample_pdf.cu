@@ -68,6 +68,27 @@ __device__ __forceinline__ int search_right(const float* s_cdf, int B, float u) 
   return lo;
 }
 
+// G independent searches per lane, branch-free and in lock step: #{a[0..len) <= key} (kStrict: #{a < key}) for a sorted
+// array in shared memory.  Every level issues its G shared-memory loads back to back, so a lane pays one load latency per
+// level instead of one per level and key (the per-key while loop was the sampler's critical path: 8 dependent loads per key).
+template <int G, bool kStrict>
+__device__ __forceinline__ void count_below(const float* a, int len, const float (&key)[G], int (&pos)[G]) {
+#pragma unroll
+  for (int g = 0; g < G; ++g) pos[g] = 0;
+  int step = 1;
+  while ((step << 1) <= len) step <<= 1;
+  for (; step > 0; step >>= 1) {
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      const int t = pos[g] + step;
+      if (t <= len) {
+        const float v = a[t - 1];
+        if (kStrict ? (v < key[g]) : (v <= key[g])) pos[g] = t;
+      }
+    }
+  }
+}
+
 __device__ __forceinline__ float fetch_u(const float* u, int u_is_joint, int64_t r, int n, int j) {
   if (u == nullptr) return torch_linspace(0.f, 1.f, n, j);       // det, H:347
   return u_is_joint ? u[j] : u[r * n + j];
@@ -100,30 +121,55 @@ __device__ __forceinline__ void resample_ray(const RayPdfSource& src, int64_t r_
   float* s_bins = s_cdf + B;
   float* s_sort = s_bins + B;
   build_cdf(src, r_src, s_cdf, s_bins, lane);
-  float ssum = 0.f;
-  for (int j = lane; j < n; j += 32) {
-    float uj = fetch_u(u, u_is_joint, r, n, j);
-    int idx = search_right(s_cdf, B, uj);
-    int below = max(0, idx - 1);                        // H:368
-    int above = min(B - 1, idx);                        // H:369
-    float c0 = s_cdf[below], c1 = s_cdf[above];
-    float b0 = s_bins[below], b1 = s_bins[above];
-    float den = c1 - c0;                                // H:378
-    if (den < 1e-5f) den = 1.0f;                        // H:379
-    float t = (uj - c0) / den;                          // H:380
-    float smp = b0 + t * (b1 - b0);                     // H:381
-    samples_out[r * n + j] = smp;
-    if (u_out) u_out[r * n + j] = uj;
-    if (z_merged) s_sort[(B + 1) + j] = smp;
-    ssum += smp;
+  constexpr int G = 4;
+  float ssum = 0.f, sqsum_pass = 0.f;
+  const bool one_group = n <= 32 * G;                   // (n = 128: every lane holds all of its samples in registers)
+  float kept[G];
+  for (int j0 = 0; j0 < n; j0 += 32 * G) {
+    float uj[G];
+    int idx[G];
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      const int j = j0 + 32 * g + lane;
+      uj[g] = j < n ? fetch_u(u, u_is_joint, r, n, j) : 0.f;
+    }
+    count_below<G, false>(s_cdf, B, uj, idx);           // searchsorted(cdf, u, right=True), H:366
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      const int j = j0 + 32 * g + lane;
+      kept[g] = 0.f;
+      if (j >= n) continue;
+      int below = max(0, idx[g] - 1);                   // H:368
+      int above = min(B - 1, idx[g]);                   // H:369
+      float c0 = s_cdf[below], c1 = s_cdf[above];
+      float b0 = s_bins[below], b1 = s_bins[above];
+      float den = c1 - c0;                              // H:378
+      if (den < 1e-5f) den = 1.0f;                      // H:379
+      float t = (uj[g] - c0) / den;                     // H:380
+      float smp = b0 + t * (b1 - b0);                   // H:381
+      samples_out[r * n + j] = smp;
+      if (u_out) u_out[r * n + j] = uj[g];
+      if (z_merged) s_sort[(B + 1) + j] = smp;
+      kept[g] = smp;
+      ssum += smp;
+    }
   }
   if (z_std != nullptr) {                               // RS:744  torch.std(z_samples, unbiased=False)
     float mean = warp_sum(ssum) / (float)n;
     float v = 0.f;
-    for (int j = lane; j < n; j += 32) {
-      float d = samples_out[r * n + j] - mean;          // own writes: visible to the writing thread
-      v += d * d;
+    if (one_group) {
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+        const int j = 32 * g + lane;
+        if (j < n) { float d = kept[g] - mean; v += d * d; }
+      }
+    } else {
+      for (int j = lane; j < n; j += 32) {
+        float d = samples_out[r * n + j] - mean;        // own writes: visible to the writing thread
+        v += d * d;
+      }
     }
+    (void)sqsum_pass;
     v = warp_sum(v) / (float)n;
     if (lane == 0) z_std[r] = sqrtf(v);
   }
@@ -142,23 +188,23 @@ __device__ __forceinline__ void resample_ray(const RayPdfSource& src, int64_t r_
     for (int j = lane; j < n - 1; j += 32) sorted &= zb[j] <= zb[j + 1];
     if (__all_sync(FULL, sorted)) {
       float* s_out = s_sort + sort_pow2;
-      for (int i = lane; i < S; i += 32) {
-        const float a = za[i];
-        int lo = 0, hi = n;                             // #{b < a}: equal values keep the coarse sample first
-        while (lo < hi) {
-          int mid = (lo + hi) >> 1;
-          if (zb[mid] < a) lo = mid + 1; else hi = mid;
-        }
-        s_out[i + lo] = a;
+      for (int i0 = 0; i0 < S; i0 += 32 * G) {          // #{b < a}: equal values keep the coarse sample first
+        float key[G];
+        int rank[G];
+#pragma unroll
+        for (int g = 0; g < G; ++g) { const int i = i0 + 32 * g + lane; key[g] = i < S ? za[i] : 0.f; }
+        count_below<G, true>(zb, n, key, rank);
+#pragma unroll
+        for (int g = 0; g < G; ++g) { const int i = i0 + 32 * g + lane; if (i < S) s_out[i + rank[g]] = key[g]; }
       }
-      for (int j = lane; j < n; j += 32) {
-        const float b = zb[j];
-        int lo = 0, hi = S;                             // #{a <= b}
-        while (lo < hi) {
-          int mid = (lo + hi) >> 1;
-          if (za[mid] <= b) lo = mid + 1; else hi = mid;
-        }
-        s_out[j + lo] = b;
+      for (int j0 = 0; j0 < n; j0 += 32 * G) {          // #{a <= b}
+        float key[G];
+        int rank[G];
+#pragma unroll
+        for (int g = 0; g < G; ++g) { const int j = j0 + 32 * g + lane; key[g] = j < n ? zb[j] : 0.f; }
+        count_below<G, false>(za, S, key, rank);
+#pragma unroll
+        for (int g = 0; g < G; ++g) { const int j = j0 + 32 * g + lane; if (j < n) s_out[j + rank[g]] = key[g]; }
       }
       __syncwarp();
       for (int i = lane; i < tot; i += 32) z_merged[r * tot + i] = s_out[i];

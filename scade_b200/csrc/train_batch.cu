@@ -8,6 +8,10 @@
 //   row (same arithmetic as pixel_ray / write_batch_row in rays.cu, bit-identical to get_rays), the whole warp strides over the
 //   K hypotheses and the cached uniforms of that pixel.  The pixel choice itself (np.random.choice, H:281) stays on the host so
 //   that the reference's RNG stream is preserved; its indices are the only per-step host->device traffic (8 B per ray).
+#include <cuda_fp16.h>
+
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace scade {
@@ -27,7 +31,8 @@ struct GatherArgs {
   const float* image;          // [H,W,3]
   const float* depth; int Cd;  // [H,W,Cd] or null
   const uint8_t* valid;        // [H,W] bool or null
-  const float* hyp; int K;     // [K,H,W] or null
+  const void* hyp; int K;      // [K,H,W] fp32 (or fp16 when hyp_f16: the resident hypothesis store) or null
+  int hyp_f16;
   const float* cached_u; int Nu;   // [H,W,Nu] or null
   int mask_corners;
   float* ray_batch;            // [N,11] or null
@@ -81,20 +86,32 @@ __global__ void __launch_bounds__(256) gather_train_batch_kernel(const __grid_co
   }
   if (a.hyp) {
     const int64_t plane = (int64_t)a.H * a.W;
-    for (int k = lane; k < a.K; k += 32) a.target_h[(int64_t)k * a.N + n] = a.hyp[k * plane + pix];   // RS:791
+    if (a.hyp_f16) {
+      const __half* h16 = reinterpret_cast<const __half*>(a.hyp);
+      for (int k = lane; k < a.K; k += 32) a.target_h[(int64_t)k * a.N + n] = __half2float(h16[k * plane + pix]);
+    } else {
+      const float* h32 = reinterpret_cast<const float*>(a.hyp);
+      for (int k = lane; k < a.K; k += 32) a.target_h[(int64_t)k * a.N + n] = h32[k * plane + pix];   // RS:791
+    }
   }
   if (a.cached_u)
     for (int u = lane; u < a.Nu; u += 32) a.u_out[n * a.Nu + u] = a.cached_u[pix * a.Nu + u];         // RS:805-806
+}
+
+// np.clip(d, near, far) (data/load_scene.py:348) + fp32 -> fp16, for the resident hypothesis store
+__global__ void pack_hypotheses_f16_kernel(const float* __restrict__ in, int64_t n, float lo, float hi, __half* __restrict__ out) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = __float2half_rn(fminf(fmaxf(in[i], lo), hi));
 }
 
 }  // namespace scade
 
 using namespace scade;
 
-extern "C" int scade_gather_train_batch(int H, int W, const float* intrinsic_host, const float* c2w_host,
+static int gather_train_batch_impl(int H, int W, const float* intrinsic_host, const float* c2w_host,
                                         const int64_t* select_inds, int64_t N, float near, float far, const float* image,
                                         const float* depth, int depth_channels, const uint8_t* valid_depth,
-                                        const float* hypotheses, int K, const float* cached_u, int n_u, int mask_corners,
+                                        const void* hypotheses, int hyp_f16, int K, const float* cached_u, int n_u, int mask_corners,
                                         float* ray_batch, float* rays_o_d, float* target_s, float* target_d,
                                         uint8_t* target_vd, float* target_h, float* mask, float* u_out, void* stream) {
   SCADE_CHECK_ARG(H > 0 && W > 0 && N >= 0 && intrinsic_host && c2w_host, "gather_train_batch: bad image / camera");
@@ -111,11 +128,42 @@ extern "C" int scade_gather_train_batch(int H, int W, const float* intrinsic_hos
     a.cam.t[r] = c2w_host[r * 4 + 3];
   }
   a.H = H; a.W = W; a.select = select_inds; a.N = N; a.near = near; a.far = far;
-  a.image = image; a.depth = depth; a.Cd = depth_channels; a.valid = valid_depth; a.hyp = hypotheses; a.K = K;
+  a.image = image; a.depth = depth; a.Cd = depth_channels; a.valid = valid_depth; a.hyp = hypotheses; a.hyp_f16 = hyp_f16; a.K = K;
   a.cached_u = cached_u; a.Nu = n_u; a.mask_corners = mask_corners;
   a.ray_batch = ray_batch; a.rays_od = rays_o_d; a.target_s = target_s; a.target_d = target_d; a.target_vd = target_vd;
   a.target_h = target_h; a.mask = mask; a.u_out = u_out;
   gather_train_batch_kernel<<<(unsigned)ceil_div<int64_t>(N, 8), 256, 0, as_stream(stream)>>>(a);
+  SCADE_LAUNCH_CHECK();
+  return SCADE_OK;
+}
+
+extern "C" int scade_gather_train_batch(int H, int W, const float* intrinsic_host, const float* c2w_host,
+                                        const int64_t* select_inds, int64_t N, float near, float far, const float* image,
+                                        const float* depth, int depth_channels, const uint8_t* valid_depth,
+                                        const float* hypotheses, int K, const float* cached_u, int n_u, int mask_corners,
+                                        float* ray_batch, float* rays_o_d, float* target_s, float* target_d,
+                                        uint8_t* target_vd, float* target_h, float* mask, float* u_out, void* stream) {
+  return gather_train_batch_impl(H, W, intrinsic_host, c2w_host, select_inds, N, near, far, image, depth, depth_channels, valid_depth,
+                                 hypotheses, 0, K, cached_u, n_u, mask_corners, ray_batch, rays_o_d, target_s, target_d, target_vd,
+                                 target_h, mask, u_out, stream);
+}
+
+extern "C" int scade_gather_train_batch_h16(int H, int W, const float* intrinsic_host, const float* c2w_host,
+                                            const int64_t* select_inds, int64_t N, float near, float far, const float* image,
+                                            const float* depth, int depth_channels, const uint8_t* valid_depth,
+                                            const uint16_t* hypotheses_f16, int K, const float* cached_u, int n_u, int mask_corners,
+                                            float* ray_batch, float* rays_o_d, float* target_s, float* target_d,
+                                            uint8_t* target_vd, float* target_h, float* mask, float* u_out, void* stream) {
+  return gather_train_batch_impl(H, W, intrinsic_host, c2w_host, select_inds, N, near, far, image, depth, depth_channels, valid_depth,
+                                 hypotheses_f16, 1, K, cached_u, n_u, mask_corners, ray_batch, rays_o_d, target_s, target_d, target_vd,
+                                 target_h, mask, u_out, stream);
+}
+
+extern "C" int scade_pack_hypotheses_f16(const float* hyp, int64_t n, float near, float far, uint16_t* out, void* stream) {
+  SCADE_CHECK_ARG(hyp && out && n >= 0, "pack_hypotheses_f16: bad arguments");
+  if (n == 0) return SCADE_OK;
+  const int blocks = (int)std::min<int64_t>(ceil_div<int64_t>(n, 256), 8 * num_sms());
+  pack_hypotheses_f16_kernel<<<blocks, 256, 0, as_stream(stream)>>>(hyp, n, near, far, reinterpret_cast<__half*>(out));
   SCADE_LAUNCH_CHECK();
   return SCADE_OK;
 }

@@ -98,7 +98,7 @@ class NetHandle:
             if nbytes == 0:
                 raise _lib.ScadeError("this network shape is not supported by the tensor-core (tc_f16 / tc_f16x3) paths")
             if buf is None or buf.numel() != nbytes or buf.device != self.params[0].device:
-                buf = self._packed[precision] = torch.empty(nbytes, dtype=torch.uint8, device=self.params[0].device)
+                buf = self._packed[precision] = torch.zeros(nbytes, dtype=torch.uint8, device=self.params[0].device)   # (alignment padding stays 0)
             net = self.struct(PREC_FP32)
             check(_L().scade_mlp_pack(byref(net), precision, ptr(buf), stream_ptr()), "scade_mlp_pack")
             self._packed_key[precision] = key

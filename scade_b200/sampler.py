@@ -49,7 +49,8 @@ def gather_train_batch(H, W, intrinsic, pose, select_inds, image, depth=None, va
         depth = depth.unsqueeze(-1)
     Cd = 0 if depth is None else depth.shape[-1]
     valid8 = None if valid_depth is None else valid_depth.to(device=dev, dtype=torch.bool).contiguous().view(torch.uint8)
-    hyp = f32(hypotheses)
+    hyp16 = hypotheses is not None and hypotheses.dtype == torch.float16       # a slice of checkpoint.HypothesisStore
+    hyp = hypotheses.to(dev).contiguous() if hyp16 else f32(hypotheses)
     K = 0
     if hyp is not None:
         hyp = hyp.reshape(hyp.shape[0], H, W)
@@ -68,7 +69,8 @@ def gather_train_batch(H, W, intrinsic, pose, select_inds, image, depth=None, va
     }
     intr = _lib.host_floats([float(v) for v in torch.as_tensor(intrinsic).detach().cpu().reshape(-1)[:4]])
     c2w = _lib.host_floats([float(v) for v in torch.as_tensor(pose).detach().cpu().reshape(-1, 4)[:3].reshape(-1)])
-    check(_lib.load().scade_gather_train_batch(
+    fn = _lib.load().scade_gather_train_batch_h16 if hyp16 else _lib.load().scade_gather_train_batch
+    check(fn(
         int(H), int(W), intr, c2w, ptr(sel), N, float(near), float(far), ptr(image), ptr(depth), int(Cd), ptr(valid8), ptr(hyp),
         int(K), ptr(cu), int(Nu), int(bool(mask_corners)), ptr(out["ray_batch"]), ptr(out["batch_rays"]), ptr(out["target_s"]),
         ptr(out["target_d"]), ptr(out["target_vd"]), ptr(out["target_h"]), ptr(out["mask"]), ptr(out["cached_u"]), stream_ptr()),
