@@ -120,7 +120,9 @@ struct StageDesc {
   StageBlock blk[2];
 };
 struct PackPlan {
-  int n_stages;
+  int n_stages;                       // stage descriptors in st[]
+  int n_fwd;                          // the first n_fwd are the forward stream, block n_fwd of the launch writes the fp32 tail
+  unsigned long long bwd_off;         // byte offset of the stages behind the tail (dgrad stream)
   StageDesc st[MAX_STAGE_DESCS];
   const float* w_alpha; const float* b_alpha; const float* w_rgb; const float* b_rgb;
   const float* epi_bias[MAX_LAYERS];  // bias vector of layer l if its epilogue adds it, else nullptr
@@ -865,11 +867,41 @@ __device__ __forceinline__ void split_f16(float b, __half* hi, __half* lo) {
   *lo = __float2half_rn(b - __half2float(*hi));
 }
 
-__global__ void pack_kernel(const __grid_constant__ PackPlan plan, uint8_t* __restrict__ out) {
-  if ((int)blockIdx.x == plan.n_stages) {
+// Source of element (n, k) of a stage: at most one fp32 value (a weight, or a bias half riding on the 1.0 columns).
+// mode 0: zero; 1: weight -> hi (or lo for a W_lo stage); 2: bias -> hi half; 3: bias -> lo half (both zero in a W_lo stage).
+__device__ __forceinline__ const float* pack_source(const StageDesc& sd, int n, int k, int* mode) {
+  *mode = 0;
+  const float* p = nullptr;
+  for (int j = 0; j < sd.n_blocks; ++j) {
+    const StageBlock& b = sd.blk[j];
+    const int bn = n - b.dst_row0;
+    if (bn < 0 || bn >= b.nrows) continue;
+    if (b.bias_mode == 2) {
+      // bias stage: K-step 0 only; positions 12/13 meet the encoding chunk's 1.0 columns (60/61 = 48 + 12/13)
+      if (k == 12 || k == 13) { p = sd.bias + sd.row0 + bn; *mode = (k == 12) ? 2 : 3; }
+      continue;
+    }
+    const int sc = k - b.dst_col0;
+    if (sc >= 0 && sc < b.ncols) {
+      p = sd.trans ? sd.W + (int64_t)(b.col0 + sc) * sd.ld + sd.row0 + bn : sd.W + (int64_t)(sd.row0 + bn) * sd.ld + b.col0 + sc;
+      *mode = 1;
+    }
+    if (b.bias_mode == 1 && (k == ONES_COL || k == ONES_COL + 1)) {      // both bias halves ride in the W_hi stage
+      p = sd.bias + sd.row0 + bn;
+      *mode = (k == ONES_COL) ? 2 : 3;
+    }
+  }
+  return p;
+}
+
+// One launch packs a network's whole stream: blocks [0, n_fwd) the forward stages, block n_fwd the fp32 tail, the rest the
+// dgrad stages behind it (at bwd_off).  A block is one 16 KB stage; a thread's 32 elements are fetched 8 at a time with
+// independent loads (the re-pack sits on the train step's critical path after every optimizer step: ~25 us -> a few us).
+__global__ void __launch_bounds__(256) pack_kernel(const __grid_constant__ PackPlan plan, uint8_t* __restrict__ out) {
+  if ((int)blockIdx.x == plan.n_fwd) {
     // fp32 tail: rgb_linear (two layouts), alpha_linear, head biases, epilogue biases
     if (plan.w_alpha == nullptr) return;
-    PackedTail* tail = reinterpret_cast<PackedTail*>(out + (size_t)plan.n_stages * STAGE_BYTES);
+    PackedTail* tail = reinterpret_cast<PackedTail*>(out + (size_t)plan.n_fwd * STAGE_BYTES);
     for (int k = threadIdx.x; k < W / 2; k += blockDim.x) {
       tail->w_rgb[k] = make_float4(plan.w_rgb[k], plan.w_rgb[W / 2 + k], plan.w_rgb[W + k], 0.f);
       tail->w_rgb_p[0][k] = plan.w_rgb[k];
@@ -885,40 +917,35 @@ __global__ void pack_kernel(const __grid_constant__ PackPlan plan, uint8_t* __re
     }
     return;
   }
-  const StageDesc& sd = plan.st[blockIdx.x];
-  __half* dst = reinterpret_cast<__half*>(out + (size_t)blockIdx.x * STAGE_BYTES);
-  for (int idx = threadIdx.x; idx < STAGE_N * KCHUNK; idx += blockDim.x) {
-    const int n = idx / KCHUNK, k = idx % KCHUNK;
-    __half hv = __float2half_rn(0.f);
-    for (int j = 0; j < sd.n_blocks; ++j) {
-      const StageBlock& b = sd.blk[j];
-      const int bn = n - b.dst_row0;
-      if (bn < 0 || bn >= b.nrows) continue;
-      if (b.bias_mode == 2) {
-        // bias stage: K-step 0 only; positions 12/13 meet the encoding chunk's 1.0 columns (60/61 = 48 + 12/13)
-        if (k == 12 || k == 13) {
-          __half hi, lo;
-          split_f16(sd.bias[sd.row0 + bn], &hi, &lo);
-          hv = (k == 12) ? hi : lo;
-        }
-        continue;
-      }
-      const int sc = k - b.dst_col0;
-      if (sc >= 0 && sc < b.ncols) {
-        const float w = sd.trans ? sd.W[(int64_t)(b.col0 + sc) * sd.ld + sd.row0 + bn]
-                                 : sd.W[(int64_t)(sd.row0 + bn) * sd.ld + b.col0 + sc];
-        __half hi, lo;
-        split_f16(w, &hi, &lo);
-        hv = sd.lo ? lo : hi;
-      }
-      if (b.bias_mode == 1 && (k == ONES_COL || k == ONES_COL + 1)) {
-        __half hi, lo;
-        split_f16(sd.bias[sd.row0 + bn], &hi, &lo);
-        hv = sd.lo ? __float2half_rn(0.f) : ((k == ONES_COL) ? hi : lo);      // both bias halves ride in the W_hi stage
-      }
+  const bool bwd = (int)blockIdx.x > plan.n_fwd;
+  const StageDesc& sd = plan.st[bwd ? blockIdx.x - 1 : blockIdx.x];
+  __half* dst = reinterpret_cast<__half*>(bwd ? out + plan.bwd_off + (size_t)(blockIdx.x - plan.n_fwd - 1) * STAGE_BYTES
+                                              : out + (size_t)blockIdx.x * STAGE_BYTES);
+  constexpr int PER_THREAD = STAGE_N * KCHUNK / 256, BATCH = 8;
+#pragma unroll 1
+  for (int it0 = 0; it0 < PER_THREAD; it0 += BATCH) {
+    float v[BATCH];
+    int mode[BATCH], nn[BATCH], kk[BATCH];
+#pragma unroll
+    for (int i = 0; i < BATCH; ++i) {
+      const int idx = threadIdx.x + (it0 + i) * 256;
+      // consecutive threads walk the source's contiguous axis: k for (out, in) weights, n for the transposed dgrad stages
+      nn[i] = sd.trans ? idx % STAGE_N : idx / KCHUNK;
+      kk[i] = sd.trans ? idx / STAGE_N : idx % KCHUNK;
+      const float* p = pack_source(sd, nn[i], kk[i], &mode[i]);
+      v[i] = p != nullptr ? __ldg(p) : 0.f;
     }
-    uint32_t off = sw128_offset(n, k >> 3) + (k & 7) * 2;
-    dst[off >> 1] = hv;
+#pragma unroll
+    for (int i = 0; i < BATCH; ++i) {
+      __half hi, lo;
+      split_f16(v[i], &hi, &lo);
+      __half hv = __float2half_rn(0.f);
+      if (mode[i] == 1) hv = sd.lo ? lo : hi;
+      else if (mode[i] == 2) hv = sd.lo ? hv : hi;
+      else if (mode[i] == 3) hv = sd.lo ? hv : lo;
+      const uint32_t off = sw128_offset(nn[i], kk[i] >> 3) + (kk[i] & 7) * 2;
+      dst[off >> 1] = hv;
+    }
   }
 }
 
@@ -985,6 +1012,7 @@ static void build_plans(const scade_net& net, NetPlan* np, PackPlan* pp, bool x3
   add_layer(net.params[pv + 2], W, false, 0, 0, 0, 0, true, W, 0, 2, net.params[pv + 3]);                        // feature_linear
   add_layer(net.params[pv], W + nd.in_views, true, W, nd.in_views, nd.in_ch, 0, true, W / 2, 1, 3, net.params[pv + 1]);   // views
   P.stages_per_pass = Q.n_stages;
+  Q.n_fwd = Q.n_stages;
   Q.w_alpha = net.params[pv + 4]; Q.b_alpha = net.params[pv + 5];
   Q.w_rgb = net.params[pv + 6]; Q.b_rgb = net.params[pv + 7];
   if (np) *np = P;
@@ -1143,17 +1171,20 @@ size_t mlp_tc_packed_bytes(const scade_net_desc& d, bool x3) {
 
 int mlp_tc_pack(const scade_net& net, void* packed_out, cudaStream_t st, bool x3) {
   tc::PackPlan pp;
-  if (x3) {
-    tc::build_plans(net, nullptr, &pp, true);
-    tc::pack_kernel<<<pp.n_stages + 1, 256, 0, st>>>(pp, reinterpret_cast<uint8_t*>(packed_out));
-    SCADE_LAUNCH_CHECK();
-    return SCADE_OK;
+  tc::build_plans(net, nullptr, &pp, x3);
+  if (!x3) {
+    // the dgrad stream rides in the same launch, behind the forward stream and its tail
+    tc::PackPlan pb;
+    tc::build_bwd_plans(net, nullptr, &pb);
+    if (pp.n_stages + pb.n_stages > tc::MAX_STAGE_DESCS) {
+      set_error("mlp_pack: %d stages exceed the pack plan", pp.n_stages + pb.n_stages);
+      return SCADE_ERR_UNSUPPORTED;
+    }
+    for (int i = 0; i < pb.n_stages; ++i) pp.st[pp.n_stages + i] = pb.st[i];
+    pp.n_stages += pb.n_stages;
+    pp.bwd_off = tc::fwd_stream_bytes(net.desc);
   }
-  tc::build_plans(net, nullptr, &pp);
   tc::pack_kernel<<<pp.n_stages + 1, 256, 0, st>>>(pp, reinterpret_cast<uint8_t*>(packed_out));
-  SCADE_LAUNCH_CHECK();
-  tc::build_bwd_plans(net, nullptr, &pp);
-  tc::pack_kernel<<<pp.n_stages, 256, 0, st>>>(pp, reinterpret_cast<uint8_t*>(packed_out) + tc::fwd_stream_bytes(net.desc));
   SCADE_LAUNCH_CHECK();
   return SCADE_OK;
 }

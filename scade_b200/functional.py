@@ -559,7 +559,9 @@ def img2mse(x, y, denominator=0):
 # fused render_rays forward (no autograd): one C call, one stream
 # ----------------------------------------------------------------------------------------------
 def render_rays_forward(ray_batch, coarse, fine, n_samples, n_importance, bb_center, bb_scale, precision=PREC_FP32,
-                        lindisp=False, is_joint=False, t_rand=None, u_coarse=None, u_fine=None, retraw=False):
+                        lindisp=False, is_joint=False, t_rand=None, u_coarse=None, u_fine=None, retraw=False, out=None):
+    """scade_render_rays_forward.  `out`: optional {name: preallocated contiguous fp32 CUDA tensor} for any of the returned
+    tensors (GraphedRenderRays lays the maps it reads back in ONE buffer so that they leave in one device->host copy)."""
     precision = PRECISIONS[precision]
     ray_batch = f32(ray_batch)
     N = ray_batch.shape[0]
@@ -573,16 +575,33 @@ def render_rays_forward(ray_batch, coarse, fine, n_samples, n_importance, bb_cen
               "acc0": (N,), "depth0": (N,), "z_vals0": (N, n_samples), "weights0": (N, n_samples), "z_std": (N,)}
     if retraw:
         shapes["raw"] = (N, S, 4)
-    ret = {k: torch.empty(s, dtype=torch.float32, device=dev) for k, s in shapes.items()}
-    out = _lib.RenderOut()
+    ret = {}
+    need = []
+    for k, shp in shapes.items():
+        t = None if out is None else out.get(k)
+        if t is not None and (tuple(t.shape) != tuple(shp) or t.dtype != torch.float32 or not t.is_cuda or not t.is_contiguous()):
+            raise _lib.ScadeError(f"render_rays_forward: out[{k!r}] must be a contiguous fp32 CUDA tensor of shape {tuple(shp)}")
+        ret[k] = t
+        if t is None:
+            need.append(k)
+    if need:
+        # ONE allocation for all remaining outputs (the reference's dict has 15 entries: 15 allocator calls per chunk otherwise),
+        # every view 16-byte aligned
+        numel = {k: int(torch.Size(shapes[k]).numel()) for k in need}
+        flat = torch.empty(sum((n + 3) // 4 * 4 for n in numel.values()), dtype=torch.float32, device=dev)
+        off = 0
+        for k in need:
+            ret[k] = flat[off:off + numel[k]].view(shapes[k])
+            off += (numel[k] + 3) // 4 * 4
+    out_c = _lib.RenderOut()
     for k in _lib.RENDER_OUT_FIELDS:
-        setattr(out, k, ret[k].data_ptr() if k in ret else None)
+        setattr(out_c, k, ret[k].data_ptr() if k in ret else None)
     nc, nf = coarse.struct(precision), fine.struct(precision)
     ws = _bytes(_L().scade_render_rays_workspace_bytes(byref(cfg), byref(coarse.desc), byref(fine.desc), N), dev)
     t_rand = None if t_rand is None else f32(t_rand, dev)
     u_coarse = None if u_coarse is None else f32(u_coarse, dev)
     u_fine = None if u_fine is None else f32(u_fine, dev)
     check(_L().scade_render_rays_forward(byref(cfg), ptr(ray_batch), N, byref(nc), byref(nf), ptr(t_rand), ptr(u_coarse),
-                                         ptr(u_fine), byref(out), ptr(ws), ws.numel(), stream_ptr()),
+                                         ptr(u_fine), byref(out_c), ptr(ws), ws.numel(), stream_ptr()),
           "scade_render_rays_forward")
     return ret

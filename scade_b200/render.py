@@ -119,7 +119,7 @@ def _rand(shape, pytest, device):
 def render_rays(ray_batch, use_viewdirs, network_fn, network_query_fn, N_samples, precomputed_z_samples=None,
                 embedded_cam=None, retraw=False, lindisp=False, perturb=0., N_importance=0, network_fine=None,
                 raw_noise_std=0., verbose=False, pytest=False, is_joint=False, cached_u=None, near=None, far=None,
-                ndc=None, t_rand=None, u_coarse=None):
+                ndc=None, t_rand=None, u_coarse=None, _out=None):
     """RS:581-751.  Returns the reference's dict (RS:733-744); every value is a tensor.
 
     Extra keyword arguments ``t_rand`` / ``u_coarse`` inject the uniforms the reference draws at RS:570 and
@@ -160,7 +160,7 @@ def render_rays(ray_batch, use_viewdirs, network_fn, network_query_fn, N_samples
         return F_.render_rays_forward(ray_batch, nets[0].handle(), nets[1].handle(), N_samples, N_importance,
                                       network_query_fn.bb_center, network_query_fn.bb_scale,
                                       precision=network_query_fn.precision, lindisp=lindisp, is_joint=False,
-                                      t_rand=t_rand, u_coarse=u_coarse, u_fine=u_fine, retraw=retraw)
+                                      t_rand=t_rand, u_coarse=u_coarse, u_fine=u_fine, retraw=retraw, out=_out)
 
     rays_o, rays_d, viewdirs = ray_batch[:, 0:3], ray_batch[:, 3:6].contiguous(), ray_batch[:, 8:11]
 
@@ -223,16 +223,27 @@ class GraphedRenderRays:
         torch.cuda.current_stream(self.device).wait_stream(side)
         torch.cuda.synchronize(self.device)
         if self.host_outputs and self.out_host is None:
-            self.out_host = {k: torch.empty(ret[k].shape, dtype=ret[k].dtype).pin_memory() for k in self.host_outputs}
+            # the maps that travel back live in ONE device buffer and ONE pinned host buffer: a single device->host copy per step
+            sizes = [int(ret[k].numel()) for k in self.host_outputs]
+            self._dev_flat = torch.empty(sum(sizes), dtype=torch.float32, device=self.device)
+            self._host_flat = torch.empty(sum(sizes), dtype=torch.float32).pin_memory()
+            self._dev_views, self.out_host, off = {}, {}, 0
+            for k, n in zip(self.host_outputs, sizes):
+                self._dev_views[k] = self._dev_flat[off:off + n].view(ret[k].shape)
+                self.out_host[k] = self._host_flat[off:off + n].view(ret[k].shape)
+                off += n
         self.graph = torch.cuda.CUDAGraph()
         # thread_local: CUDA calls of other threads (e.g. an NCCL watchdog polling its events) must not invalidate the capture
         with torch.cuda.graph(self.graph, capture_error_mode="thread_local"), torch.no_grad():
             if self.host_outputs:
                 self.rays.copy_(self.rays_host, non_blocking=True)
-            self.out = render_rays(self.rays, self.use_viewdirs, **self.kwargs)
-            if self.host_outputs:
-                for k in self.host_outputs:
-                    self.out_host[k].copy_(self.out[k], non_blocking=True)
+                self.out = render_rays(self.rays, self.use_viewdirs, _out=self._dev_views, **self.kwargs)
+                for k, v in self._dev_views.items():          # (a path that allocated its own outputs: stage them)
+                    if self.out[k].data_ptr() != v.data_ptr():
+                        v.copy_(self.out[k])
+                self._host_flat.copy_(self._dev_flat, non_blocking=True)
+            else:
+                self.out = render_rays(self.rays, self.use_viewdirs, **self.kwargs)
 
     def __call__(self, ray_batch=None):
         if ray_batch is not None:
