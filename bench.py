@@ -329,7 +329,7 @@ def run_gpu(args):
         tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
         if os.path.exists(tpath):
             with open(tpath) as f:
-                traffic = json.load(f).get("mlp_fine_dram_bytes_per_launch")
+                traffic = json.load(f).get("mlp_fine_x3_dram_bytes_per_launch" if prec == "tc_f16x3" else "mlp_fine_dram_bytes_per_launch")
         is_tc = prec in ("tc_f16", "tc_f16x3")
         dtype = {"tc_f16": "f16 operands / f32 accumulate (tcgen05)", "fp32": "f32",
                  "tc_f16x3": "f16 hi/lo operand pairs, 3 tcgen05 passes / f32 accumulate (fp32-level tolerance)"}[prec]

@@ -225,6 +225,16 @@ int scade_space_carving_loss(const float* pred, const float* hyp, int hyp_full, 
                              float* loss_out, float* d_pred, float* d_hyp, void* workspace,
                              size_t workspace_bytes, void* stream);
 
+/* The default branch with the loss glue of RS:954 fused in: hyp_raw [K,N,1] are the RAW hypotheses, the kernel forms
+ * h = hyp_raw * (*scale_dev) + (*shift_dev) itself (scale / shift: one DEVICE float each, the step's DEPTH_SCALES[img_i] /
+ * DEPTH_SHIFTS[img_i]) and returns d loss / d scale, d loss / d shift in d_scale_shift[0..1] (nullable) instead of a [K,N]
+ * hypothesis gradient -- the train step loses the elementwise mul / add and the two reductions autograd ran for them.
+ * `denominator` overrides N in the mean over rays when > 0 (ray-sharded training divides by the GLOBAL count). */
+int scade_space_carving_loss_affine(const float* pred, const float* hyp_raw, const float* scale_dev,
+                                    const float* shift_dev, const float* mask, int K, int64_t N, int P,
+                                    float threshold, float grad_scale, int64_t denominator, float* loss_out,
+                                    float* d_pred, float* d_scale_shift, void* stream);
+
 /* The joint branch (H:115-119: mean over rays BEFORE the min over k) for a ray-sharded step (SURVEY 8(e) "Exception"), in two
  * halves around one all-reduce of K*P floats:
  *   accumulate: qsum_out[k,p] = sum over this rank's N rays of dist[k,n,p]  (zeroed first);

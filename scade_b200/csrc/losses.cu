@@ -32,7 +32,8 @@ __device__ __forceinline__ float sc_dist(float pred, float h, float m, float thr
 __global__ void __launch_bounds__(SC_WARPS * 32)
 space_carving_ray_kernel(const float* __restrict__ pred, const float* __restrict__ hyp, int hyp_full,
                          const float* __restrict__ mask, int K, int64_t N, int P, float thr, float gscale, float inv_n,
-                         float* __restrict__ loss_out, float* __restrict__ d_pred, float* __restrict__ d_hyp) {
+                         float* __restrict__ loss_out, float* __restrict__ d_pred, float* __restrict__ d_hyp,
+                         const float* __restrict__ scale_dev, const float* __restrict__ shift_dev, float* __restrict__ d_ss) {
   extern __shared__ float smem[];   // s_h[K][32 rays] | s_dh[K][32 rays] | per warp: K*32 lane-private gradient accumulators
   __shared__ float s_part[SC_WARPS];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -40,11 +41,17 @@ space_carving_ray_kernel(const float* __restrict__ pred, const float* __restrict
   float* s_h = smem;
   float* s_dh = s_h + K * SC_RAYS;
   float* s_g = s_dh + K * SC_RAYS + (size_t)wid * K * 32;
-  const bool want_dh = d_hyp != nullptr;
+  // affine form (RS:954 fused in): hyp holds the RAW hypotheses, h = hyp * scale + shift is formed here (mul then add, like
+  // torch's two ops) and d loss / d scale, d loss / d shift leave as two atomics per block (d_ss[0], d_ss[1])
+  const bool affine = scale_dev != nullptr;
+  const float a_scale = affine ? scale_dev[0] : 1.0f, a_shift = affine ? shift_dev[0] : 0.0f;
+  const bool want_dh = d_hyp != nullptr || d_ss != nullptr;
   if (!hyp_full) {
     for (int k = wid; k < K; k += SC_WARPS) {
       const int64_t r = r0 + lane;
-      s_h[k * SC_RAYS + lane] = r < N ? hyp[(int64_t)k * N + r] : 0.f;
+      float h = r < N ? hyp[(int64_t)k * N + r] : 0.f;
+      if (affine) h = __fadd_rn(__fmul_rn(h, a_scale), a_shift);
+      s_h[k * SC_RAYS + lane] = h;
     }
   }
   __syncthreads();
@@ -110,9 +117,19 @@ space_carving_ray_kernel(const float* __restrict__ pred, const float* __restrict
   if (lane == 0) s_part[wid] = warp_total;
   __syncthreads();
   if (want_dh && !hyp_full) {
+    float ps = 0.f, pt = 0.f;                            // d scale = sum d_h * h_raw, d shift = sum d_h  (RS:954)
     for (int k = wid; k < K; k += SC_WARPS) {
       const int64_t r = r0 + lane;
-      if (r < N) d_hyp[(int64_t)k * N + r] = s_dh[k * SC_RAYS + lane];
+      if (r < N) {
+        const float g = s_dh[k * SC_RAYS + lane];        // rows of rays beyond N were never written: guarded by r < N
+        if (d_hyp) d_hyp[(int64_t)k * N + r] = g;
+        if (d_ss) { ps = fmaf(g, hyp[(int64_t)k * N + r], ps); pt += g; }
+      }
+    }
+    if (d_ss) {
+      ps = warp_sum(ps);
+      pt = warp_sum(pt);
+      if (lane == 0) { atomicAdd(d_ss, ps); atomicAdd(d_ss + 1, pt); }
     }
   }
   if (threadIdx.x == 0) {
@@ -266,7 +283,8 @@ extern "C" int scade_space_carving_loss(const float* pred, const float* hyp, int
     if (smem > 48 * 1024)
       SCADE_CUDA(cudaFuncSetAttribute(space_carving_ray_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     space_carving_ray_kernel<<<(unsigned)ceil_div<int64_t>(N, SC_RAYS), SC_WARPS * 32, smem, st>>>(
-        pred, hyp, hyp_full, mask, K, N, P, threshold, grad_scale, 1.0f / (float)N, loss_out, d_pred, d_hyp);
+        pred, hyp, hyp_full, mask, K, N, P, threshold, grad_scale, 1.0f / (float)N, loss_out, d_pred, d_hyp, nullptr, nullptr,
+        nullptr);
     SCADE_LAUNCH_CHECK();
     return SCADE_OK;
   }
@@ -279,6 +297,26 @@ extern "C" int scade_space_carving_loss(const float* pred, const float* hyp, int
   int* kstar = reinterpret_cast<int*>(reinterpret_cast<char*>(workspace) + align_up((size_t)K * P * sizeof(float)));
   SCADE_TRY(sc_joint_accumulate(pred, hyp, hyp_full, mask, K, N, P, threshold, qsum, st));
   return sc_joint_finish(pred, hyp, hyp_full, mask, qsum, kstar, K, N, N, P, threshold, grad_scale, loss_out, d_pred, d_hyp, st);
+}
+
+extern "C" int scade_space_carving_loss_affine(const float* pred, const float* hyp_raw, const float* scale_dev,
+                                               const float* shift_dev, const float* mask, int K, int64_t N, int P,
+                                               float threshold, float grad_scale, int64_t denominator, float* loss_out,
+                                               float* d_pred, float* d_scale_shift, void* stream) {
+  SCADE_CHECK_ARG(pred && hyp_raw && scale_dev && shift_dev && loss_out && K > 0 && N > 0 && P > 0,
+                  "space_carving_loss_affine: bad arguments");
+  cudaStream_t st = as_stream(stream);
+  SCADE_CUDA(cudaMemsetAsync(loss_out, 0, sizeof(float), st));
+  if (d_scale_shift) SCADE_CUDA(cudaMemsetAsync(d_scale_shift, 0, 2 * sizeof(float), st));
+  size_t smem = ((size_t)2 * K * SC_RAYS + (size_t)SC_WARPS * K * 32) * sizeof(float);
+  SCADE_CHECK_ARG(smem <= 160 * 1024, "space_carving_loss_affine: K=%d too large", K);
+  if (smem > 48 * 1024)
+    SCADE_CUDA(cudaFuncSetAttribute(space_carving_ray_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const float inv_n = 1.0f / (float)(denominator > 0 ? denominator : N);
+  space_carving_ray_kernel<<<(unsigned)ceil_div<int64_t>(N, SC_RAYS), SC_WARPS * 32, smem, st>>>(
+      pred, hyp_raw, 0, mask, K, N, P, threshold, grad_scale, inv_n, loss_out, d_pred, nullptr, scale_dev, shift_dev, d_scale_shift);
+  SCADE_LAUNCH_CHECK();
+  return SCADE_OK;
 }
 
 extern "C" int scade_space_carving_joint_accumulate(const float* pred, const float* hyp, int hyp_full, const float* mask, int K,

@@ -143,7 +143,10 @@ def sharded_train_step(ray_batch, target_s, target_h, scale, shift, render_kwarg
                     raise ValueError("sharded_train_step: scale / shift require grad but are not leaf tensors (e.g. "
                                      "DEPTH_SCALES[img_i]); pass the leaves as extra_params=[DEPTH_SCALES, DEPTH_SHIFTS] or keep "
                                      "them in a FlatParams -- their gradients would otherwise stay rank-local")
-    th = target_h * scale + shift                                                       # RS:954
+    # RS:954 (target_h * scale + shift) is fused into the space-carving kernel when scale / shift are single CUDA elements
+    affine = (not is_joint and torch.is_tensor(scale) and torch.is_tensor(shift) and scale.numel() == 1 and shift.numel() == 1
+              and scale.is_cuda and shift.is_cuda and target_h.dim() == 3 and target_h.shape[-1] == 1)
+    th = None if affine else target_h * scale + shift                                   # RS:954
     bucket = _BucketOverlap(flat, fine if (overlap and fine is not coarse) else None, group) if use_flat else None
     ret = R_.render_rays(ray_batch, True, cached_u=u_fine, t_rand=t_rand, u_coarse=u_coarse, retraw=False, is_joint=is_joint,
                          **render_kwargs)
@@ -154,6 +157,10 @@ def sharded_train_step(ray_batch, target_s, target_h, scale, shift, render_kwarg
         # the GLOBAL loss on every rank (one [K,P] all-reduce inside); its share of the rank-summed partials is 1/world
         sc_full = F_.space_carving_loss_joint_sharded(ret["pred_hyp"], th, n_global, mask=mask, threshold=threshold, group=group)
         sc, sc_part = sc_full, sc_full.detach() / float(world)
+    elif affine:
+        sc = F_.space_carving_loss_affine(ret["pred_hyp"], target_h, scale, shift, mask=mask, threshold=threshold,
+                                          denominator=n_global)                          # local sum / GLOBAL ray count
+        sc_part = sc.detach()
     else:
         sc = NH.compute_space_carving_loss(ret["pred_hyp"], th, is_joint=False, mask=mask, threshold=threshold) \
             * (float(n_local) / float(n_global))

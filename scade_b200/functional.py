@@ -349,12 +349,15 @@ class _Raw2OutputsFn(torch.autograd.Function):
                                      ptr(disp), ptr(acc), ptr(w), ptr(depth), stream_ptr()), "scade_raw2outputs")
         ctx.save_for_backward(raw, z_vals, rays_d, noise if noise is not None else torch.empty(0, device=dev))
         ctx.has_noise = noise is not None
+        ctx.set_materialize_grads(False)      # unused outputs (disp / acc / depth in the train step) arrive as None, not as zero tensors
         return rgb, disp, acc, w, depth
 
     @staticmethod
     def backward(ctx, d_rgb, d_disp, d_acc, d_w, d_depth):
         raw, z_vals, rays_d, noise = ctx.saved_tensors
         N, S = z_vals.shape
+        if all(t is None for t in (d_rgb, d_disp, d_acc, d_w, d_depth)):
+            return None, None, None, None
         d_raw = torch.empty_like(raw)
         g = [None if t is None else f32(t) for t in (d_rgb, d_disp, d_acc, d_w, d_depth)]
         check(_L().scade_raw2outputs_backward(ptr(raw), ptr(z_vals), ptr(rays_d), rays_d.shape[1],
@@ -382,10 +385,13 @@ class _SamplePdfFn(torch.autograd.Function):
                                     ptr(u_out), stream_ptr()), "scade_sample_pdf")
         ctx.save_for_backward(bins, weights, u_out)
         ctx.mark_non_differentiable(u_out)
+        ctx.set_materialize_grads(False)
         return samples, u_out
 
     @staticmethod
     def backward(ctx, d_samples, _d_u):
+        if d_samples is None:
+            return None, None, None, None, None
         bins, weights, u = ctx.saved_tensors
         N, B = bins.shape
         d_w = torch.empty_like(weights)
@@ -422,10 +428,13 @@ class _ResampleFromZFn(torch.autograd.Function):
         outs = (samples, u_out, merged if want_merge else torch.empty(0, device=dev),
                 std if want_std else torch.empty(0, device=dev))
         ctx.mark_non_differentiable(*outs[1:])
+        ctx.set_materialize_grads(False)
         return outs
 
     @staticmethod
     def backward(ctx, d_samples, *_):
+        if d_samples is None:
+            return None, None, None, None, None, None, None
         z_vals, weights, u = ctx.saved_tensors
         N, S = z_vals.shape
         d_w = torch.empty_like(weights)
@@ -487,6 +496,44 @@ def space_carving_loss(pred, hyp, is_joint=False, mask=None, threshold=0.0):
     mask = None if mask is None else f32(mask)
     want = torch.is_grad_enabled() and (pred.requires_grad or hyp.requires_grad)
     return _SpaceCarvingFn.apply(pred, hyp, mask, bool(is_joint), float(threshold), want)
+
+
+class _SpaceCarvingAffineFn(torch.autograd.Function):
+    """compute_space_carving_loss(pred, target_h * scale + shift) (RS:954 + H:93-128, default branch) in one launch, with the
+    gradients w.r.t. pred, scale and shift produced in the same pass."""
+
+    @staticmethod
+    def forward(ctx, pred, hyp_raw, scale, shift, mask, threshold, denominator, want):
+        N, P = pred.shape
+        K = hyp_raw.shape[0]
+        dev = pred.device
+        loss = torch.empty((1,), dtype=torch.float32, device=dev)
+        d_pred = torch.empty_like(pred) if want else None
+        d_ss = torch.empty((2,), dtype=torch.float32, device=dev) if want else None
+        check(_L().scade_space_carving_loss_affine(ptr(pred), ptr(hyp_raw), ptr(scale), ptr(shift), ptr(mask), K, N, P,
+                                                   float(threshold), 1.0, int(denominator), ptr(loss), ptr(d_pred), ptr(d_ss),
+                                                   stream_ptr()), "scade_space_carving_loss_affine")
+        if want:
+            ctx.save_for_backward(d_pred, d_ss)
+        ctx.shapes = (scale.shape, shift.shape)
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        d_pred, d_ss = ctx.saved_tensors
+        ss = d_ss * g
+        return d_pred * g, None, ss[0].reshape(ctx.shapes[0]), ss[1].reshape(ctx.shapes[1]), None, None, None, None
+
+
+def space_carving_loss_affine(pred, hyp_raw, scale, shift, mask=None, threshold=0.0, denominator=0):
+    """compute_space_carving_loss(pred, hyp_raw * scale + shift) (RS:954, RS:974; is_joint=False, hyp_raw [K,N,1], scale / shift
+    single-element CUDA tensors).  denominator > 0 replaces N in the mean over rays (ray-sharded training)."""
+    pred, hyp_raw = f32(pred), f32(hyp_raw)
+    if hyp_raw.dim() != 3 or hyp_raw.shape[-1] != 1 or scale.numel() != 1 or shift.numel() != 1:
+        raise _lib.ScadeError("space_carving_loss_affine: needs hyp_raw [K,N,1] and single-element scale / shift")
+    mask = None if mask is None else f32(mask)
+    want = torch.is_grad_enabled() and (pred.requires_grad or scale.requires_grad or shift.requires_grad)
+    return _SpaceCarvingAffineFn.apply(pred, hyp_raw, f32(scale), f32(shift), mask, float(threshold), int(denominator), want)
 
 
 class _SpaceCarvingJointShardedFn(torch.autograd.Function):

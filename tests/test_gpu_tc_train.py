@@ -359,3 +359,36 @@ def test_space_carving_joint_sharded_matches_full_batch(dev, hyp_full):
     l2.backward()
     np.testing.assert_allclose(float(l2.detach()), float(full.detach()), rtol=1e-6)    # the [K,P] sums are float atomics: order varies
     torch.testing.assert_close(p2.grad, p_t.grad, rtol=1e-6, atol=0)
+
+
+def test_space_carving_affine_matches_composed(dev):
+    """RS:954 fused into the loss kernel (scade_space_carving_loss_affine): same loss bits and d_pred bits as
+    compute_space_carving_loss(pred, target_h * scale + shift), d_scale / d_shift equal autograd's reductions to fp32 round-off;
+    `denominator` rescales like the ray-sharded step needs; both against the oracle."""
+    from scade_b200 import functional as F_
+    rng = np.random.default_rng(8)
+    N, P, K = 777, 128, 20
+    pred = rng.uniform(0.3, 4.8, (N, P)).astype(np.float32)
+    hyp = rng.uniform(0.1, 5.0, (K, N, 1)).astype(np.float32)
+    mask = (rng.random(N) > 0.1).astype(np.float32)
+    T = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    for thr in (0.0, 0.03):
+        p1, s1, h1 = T(pred).requires_grad_(True), torch.tensor([1.07], device=dev, requires_grad=True), torch.tensor([-0.04], device=dev, requires_grad=True)
+        l1 = F_.space_carving_loss(p1, T(hyp) * s1 + h1, mask=T(mask), threshold=thr)
+        l1.backward()
+        p2, s2, h2 = T(pred).requires_grad_(True), torch.tensor([1.07], device=dev, requires_grad=True), torch.tensor([-0.04], device=dev, requires_grad=True)
+        l2 = F_.space_carving_loss_affine(p2, T(hyp), s2, h2, mask=T(mask), threshold=thr)
+        l2.backward()
+        np.testing.assert_allclose(float(l1.detach()), float(l2.detach()), rtol=1e-6)      # block partials meet in float atomics
+        assert torch.equal(p1.grad, p2.grad)
+        np.testing.assert_allclose(float(s2.grad), float(s1.grad), rtol=2e-5)
+        np.testing.assert_allclose(float(h2.grad), float(h1.grad), rtol=2e-5, atol=1e-9)
+        ref = O.space_carving_loss(pred, hyp * np.float32(1.07) + np.float32(-0.04), False, mask, thr)
+        np.testing.assert_allclose(float(l2.detach()), float(ref), rtol=2e-6)
+        d_pred_ref, d_h_ref = O.space_carving_loss_bwd(pred, hyp * np.float32(1.07) + np.float32(-0.04), False, mask, thr)
+        np.testing.assert_allclose(float(s2.grad), float((d_h_ref * hyp).sum()), rtol=1e-4)
+        # a ray shard normalised by the global count
+        p3 = T(pred[:300]).requires_grad_(True)
+        l3 = F_.space_carving_loss_affine(p3, T(hyp[:, :300]), s2.detach(), h2.detach(), mask=T(mask[:300]), threshold=thr, denominator=N)
+        l3f = F_.space_carving_loss(T(pred[:300]), T(hyp[:, :300]) * 1.07 - 0.04, mask=T(mask[:300]), threshold=thr)
+        np.testing.assert_allclose(float(l3.detach()), float(l3f) * 300 / N, rtol=1e-6)
