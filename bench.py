@@ -390,7 +390,7 @@ def measure_train(args, dev, rank, world, steps):
     from scade_b200.dist import shard_range, sharded_train_step
     from tests.golden.generate_goldens import net_pair
     lib = _lib.load()
-    N, Nc, Nf, K = 4096, 64, 128, 20
+    N, Nc, Nf, K = int(args.train_rays), 64, 128, 20
     pc, pf = net_pair(NET_D, NET_W)
     nets = []
     for p in (pc, pf):
@@ -425,14 +425,14 @@ def measure_train(args, dev, rank, world, steps):
     if args.optimizer == "fused" and args.train_graph:
         # the whole step (zero_grad, forward, losses, backward, all-reduce, both Adam launches) as one CUDA graph
         from scade_b200.dist import GraphedTrainStep
-        graphed = GraphedTrainStep(kw, scale, shift, flat, [opt, opt_ss], n_global=N, warmup=3)
+        graphed = GraphedTrainStep(kw, scale, shift, flat, [opt, opt_ss], n_global=N, warmup=3, overlap=bool(args.train_overlap))
 
     def step():
         if graphed is not None:
             return graphed(rb, target_s, target_h)
         opt.zero_grad(set_to_none=False)
         opt_ss.zero_grad(set_to_none=False)
-        losses = sharded_train_step(rb, target_s, target_h, scale, shift, kw, n_global=N, flat=flat)
+        losses = sharded_train_step(rb, target_s, target_h, scale, shift, kw, n_global=N, flat=flat, overlap=bool(args.train_overlap))
         opt.step()
         opt_ss.step()
         return losses
@@ -459,7 +459,7 @@ def measure_train(args, dev, rank, world, steps):
         burst, sustained, _, src = load_peaks()
         sec = float(ms) * 1e-3 / steps
         rec = {
-            "metric": "train rays/sec (4096 rays, 64c+128f, K=20, fwd+loss+bwd+allreduce+Adam)", "value": N / sec, "unit": "rays/s",
+            "metric": f"train rays/sec ({N} rays, 64c+128f, K=20, fwd+loss+bwd+allreduce+Adam)", "value": N / sec, "unit": "rays/s",
             "n_gpus": world, "steps": steps, "warmup": max(args.warmup, 3), "ms_per_step": sec * 1e3, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None,
             "dtype": "f16 operands / f32 accumulate (tcgen05 fwd+dgrad+wgrad)" if args.precision == "tc_f16" else "f32", "data": "synthetic",
@@ -632,6 +632,8 @@ def main():
     ap.add_argument("--optimizer", default="fused", choices=["fused", "torch"],
                     help="train workload: fused = flat parameters + scade_adam_step (default); torch = torch.optim.Adam on 48 tensors")
     ap.add_argument("--train-graph", type=int, default=1, help="train workload: replay the step as one CUDA graph (0 = eager)")
+    ap.add_argument("--train-rays", type=int, default=4096, help="train workload: global rays per step (BASELINE config 3: 4096)")
+    ap.add_argument("--train-overlap", type=int, default=1, help="train workload: all-reduce the fine net's gradient bucket under the coarse backward")
     ap.add_argument("--workload", default="render", choices=["render", "render_c2", "train", "image", "video"],
                     help="render = BASELINE metric (default); render_c2 = config 2 (1024 rays x (64c+128f), 1 GPU); train = config 3 (4096 rays, 64c+128f, K=20, fwd+loss+bwd+allreduce+Adam); "
                          "image / video = configs 4 / 5 (full 640x480 frames, pixels sharded across the GPUs)")

@@ -227,13 +227,14 @@ int scade_space_carving_loss(const float* pred, const float* hyp, int hyp_full, 
 
 /* The default branch with the loss glue of RS:954 fused in: hyp_raw [K,N,1] are the RAW hypotheses, the kernel forms
  * h = hyp_raw * (*scale_dev) + (*shift_dev) itself (scale / shift: one DEVICE float each, the step's DEPTH_SCALES[img_i] /
- * DEPTH_SHIFTS[img_i]) and returns d loss / d scale, d loss / d shift in d_scale_shift[0..1] (nullable) instead of a [K,N]
- * hypothesis gradient -- the train step loses the elementwise mul / add and the two reductions autograd ran for them.
+ * DEPTH_SHIFTS[img_i]) and returns grad_scale * d loss / d scale and d loss / d shift in *d_scale, *d_shift (both nullable)
+ * instead of a [K,N] hypothesis gradient -- the train step loses the elementwise mul / add and the two reductions autograd
+ * ran for them.  accumulate != 0: the two values are ADDED to what *d_scale / *d_shift hold (the parameters' .grad slots).
  * `denominator` overrides N in the mean over rays when > 0 (ray-sharded training divides by the GLOBAL count). */
 int scade_space_carving_loss_affine(const float* pred, const float* hyp_raw, const float* scale_dev,
                                     const float* shift_dev, const float* mask, int K, int64_t N, int P,
                                     float threshold, float grad_scale, int64_t denominator, float* loss_out,
-                                    float* d_pred, float* d_scale_shift, void* stream);
+                                    float* d_pred, float* d_scale, float* d_shift, int accumulate, void* stream);
 
 /* The joint branch (H:115-119: mean over rays BEFORE the min over k) for a ray-sharded step (SURVEY 8(e) "Exception"), in two
  * halves around one all-reduce of K*P floats:

@@ -80,7 +80,8 @@ _SIGNATURES = {
     "scade_space_carving_workspace_bytes": (c_size_t, [c_int, c_int64, c_int]),
     "scade_space_carving_loss": (c_int, [_P, _P, c_int, _P, c_int, c_int64, c_int, c_int, c_float, c_float, _P, _P, _P,
                                          _P, c_size_t, _P]),
-    "scade_space_carving_loss_affine": (c_int, [_P, _P, _P, _P, _P, c_int, c_int64, c_int, c_float, c_float, c_int64, _P, _P, _P, _P]),
+    "scade_space_carving_loss_affine": (c_int, [_P, _P, _P, _P, _P, c_int, c_int64, c_int, c_float, c_float, c_int64, _P, _P, _P, _P,
+                                                c_int, _P]),
     "scade_space_carving_joint_accumulate": (c_int, [_P, _P, c_int, _P, c_int, c_int64, c_int, c_float, _P, _P]),
     "scade_space_carving_joint_finish": (c_int, [_P, _P, c_int, _P, _P, c_int, c_int64, c_int64, c_int, c_float, c_float, _P, _P, _P,
                                                  _P, _P]),

@@ -15,7 +15,8 @@
 namespace scade {
 
 constexpr int SC_WARPS = 8;
-constexpr int SC_RAYS = 32;         // rays per block: hyp[k, r0 .. r0+31] is one 128-byte line per hypothesis
+// rays per block: 32 (hyp[k, r0 .. r0+31] is one 128-byte line per hypothesis) for large batches; 8 (one ray per warp) when
+// the batch is too small to fill the machine with 32-ray blocks (a 512-ray shard of an 8-GPU step would be 16 blocks)
 
 __device__ __forceinline__ float sc_dist(float pred, float h, float m, float thr, float& sgn) {
   float diff = pred - h;
@@ -29,11 +30,13 @@ __device__ __forceinline__ float sc_dist(float pred, float h, float m, float thr
 // staged in shared memory by loads that run along N (hyp is [K, N, 1]: ray r of hypothesis k sits at k*N + r, so a per-ray
 // walk over k is K scattered 4-byte loads -- 4.6% of the HBM roofline in round 1), and the hypothesis gradients leave the same way.
 // Per ray: lanes walk the P samples, min over K in registers, gradient in the same pass, no [K,N,P] tensor.
+template <int SC_RAYS>
 __global__ void __launch_bounds__(SC_WARPS * 32)
 space_carving_ray_kernel(const float* __restrict__ pred, const float* __restrict__ hyp, int hyp_full,
                          const float* __restrict__ mask, int K, int64_t N, int P, float thr, float gscale, float inv_n,
                          float* __restrict__ loss_out, float* __restrict__ d_pred, float* __restrict__ d_hyp,
-                         const float* __restrict__ scale_dev, const float* __restrict__ shift_dev, float* __restrict__ d_ss) {
+                         const float* __restrict__ scale_dev, const float* __restrict__ shift_dev, float* __restrict__ d_scale,
+                         float* __restrict__ d_shift) {
   extern __shared__ float smem[];   // s_h[K][32 rays] | s_dh[K][32 rays] | per warp: K*32 lane-private gradient accumulators
   __shared__ float s_part[SC_WARPS];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -45,13 +48,15 @@ space_carving_ray_kernel(const float* __restrict__ pred, const float* __restrict
   // torch's two ops) and d loss / d scale, d loss / d shift leave as two atomics per block (d_ss[0], d_ss[1])
   const bool affine = scale_dev != nullptr;
   const float a_scale = affine ? scale_dev[0] : 1.0f, a_shift = affine ? shift_dev[0] : 0.0f;
-  const bool want_dh = d_hyp != nullptr || d_ss != nullptr;
+  const bool want_dh = d_hyp != nullptr || d_scale != nullptr;
   if (!hyp_full) {
     for (int k = wid; k < K; k += SC_WARPS) {
       const int64_t r = r0 + lane;
-      float h = r < N ? hyp[(int64_t)k * N + r] : 0.f;
-      if (affine) h = __fadd_rn(__fmul_rn(h, a_scale), a_shift);
-      s_h[k * SC_RAYS + lane] = h;
+      if (lane < SC_RAYS) {
+        float h = r < N ? hyp[(int64_t)k * N + r] : 0.f;
+        if (affine) h = __fadd_rn(__fmul_rn(h, a_scale), a_shift);
+        s_h[k * SC_RAYS + lane] = h;
+      }
     }
   }
   __syncthreads();
@@ -120,16 +125,16 @@ space_carving_ray_kernel(const float* __restrict__ pred, const float* __restrict
     float ps = 0.f, pt = 0.f;                            // d scale = sum d_h * h_raw, d shift = sum d_h  (RS:954)
     for (int k = wid; k < K; k += SC_WARPS) {
       const int64_t r = r0 + lane;
-      if (r < N) {
+      if (lane < SC_RAYS && r < N) {
         const float g = s_dh[k * SC_RAYS + lane];        // rows of rays beyond N were never written: guarded by r < N
         if (d_hyp) d_hyp[(int64_t)k * N + r] = g;
-        if (d_ss) { ps = fmaf(g, hyp[(int64_t)k * N + r], ps); pt += g; }
+        if (d_scale) { ps = fmaf(g, hyp[(int64_t)k * N + r], ps); pt += g; }
       }
     }
-    if (d_ss) {
+    if (d_scale) {
       ps = warp_sum(ps);
       pt = warp_sum(pt);
-      if (lane == 0) { atomicAdd(d_ss, ps); atomicAdd(d_ss + 1, pt); }
+      if (lane == 0) { atomicAdd(d_scale, ps); atomicAdd(d_shift, pt); }
     }
   }
   if (threadIdx.x == 0) {
@@ -245,6 +250,30 @@ extern "C" size_t scade_space_carving_workspace_bytes(int K, int64_t N, int P) {
   return align_up((size_t)K * P * sizeof(float)) + align_up((size_t)P * sizeof(int));
 }
 
+template <int SC_RAYS>
+static int launch_space_carving_t(const float* pred, const float* hyp, int hyp_full, const float* mask, int K, int64_t N, int P,
+                                  float thr, float gscale, float inv_n, float* loss_out, float* d_pred, float* d_hyp,
+                                  const float* scale_dev, const float* shift_dev, float* d_scale, float* d_shift, cudaStream_t st) {
+  size_t smem = ((size_t)2 * K * SC_RAYS + (size_t)SC_WARPS * K * 32) * sizeof(float);
+  SCADE_CHECK_ARG(smem <= 160 * 1024, "space_carving_loss: K=%d too large", K);
+  if (smem > 48 * 1024)
+    SCADE_CUDA(cudaFuncSetAttribute(space_carving_ray_kernel<SC_RAYS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  space_carving_ray_kernel<SC_RAYS><<<(unsigned)ceil_div<int64_t>(N, SC_RAYS), SC_WARPS * 32, smem, st>>>(
+      pred, hyp, hyp_full, mask, K, N, P, thr, gscale, inv_n, loss_out, d_pred, d_hyp, scale_dev, shift_dev, d_scale, d_shift);
+  SCADE_LAUNCH_CHECK();
+  return SCADE_OK;
+}
+
+static int launch_space_carving(const float* pred, const float* hyp, int hyp_full, const float* mask, int K, int64_t N, int P,
+                                float thr, float gscale, float inv_n, float* loss_out, float* d_pred, float* d_hyp,
+                                const float* scale_dev, const float* shift_dev, float* d_scale, float* d_shift, cudaStream_t st) {
+  if (N >= 8192)
+    return launch_space_carving_t<32>(pred, hyp, hyp_full, mask, K, N, P, thr, gscale, inv_n, loss_out, d_pred, d_hyp, scale_dev,
+                                      shift_dev, d_scale, d_shift, st);
+  return launch_space_carving_t<8>(pred, hyp, hyp_full, mask, K, N, P, thr, gscale, inv_n, loss_out, d_pred, d_hyp, scale_dev,
+                                   shift_dev, d_scale, d_shift, st);
+}
+
 static int sc_joint_accumulate(const float* pred, const float* hyp, int hyp_full, const float* mask, int K, int64_t N, int P,
                                float threshold, float* qsum, cudaStream_t st) {
   SCADE_CUDA(cudaMemsetAsync(qsum, 0, (size_t)K * P * sizeof(float), st));
@@ -277,17 +306,9 @@ extern "C" int scade_space_carving_loss(const float* pred, const float* hyp, int
   SCADE_CHECK_ARG(pred && hyp && loss_out && K > 0 && N > 0 && P > 0, "space_carving_loss: bad arguments");
   cudaStream_t st = as_stream(stream);
   SCADE_CUDA(cudaMemsetAsync(loss_out, 0, sizeof(float), st));
-  if (!is_joint) {
-    size_t smem = ((size_t)2 * K * SC_RAYS + (size_t)SC_WARPS * K * 32) * sizeof(float);
-    SCADE_CHECK_ARG(smem <= 160 * 1024, "space_carving_loss: K=%d too large", K);
-    if (smem > 48 * 1024)
-      SCADE_CUDA(cudaFuncSetAttribute(space_carving_ray_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    space_carving_ray_kernel<<<(unsigned)ceil_div<int64_t>(N, SC_RAYS), SC_WARPS * 32, smem, st>>>(
-        pred, hyp, hyp_full, mask, K, N, P, threshold, grad_scale, 1.0f / (float)N, loss_out, d_pred, d_hyp, nullptr, nullptr,
-        nullptr);
-    SCADE_LAUNCH_CHECK();
-    return SCADE_OK;
-  }
+  if (!is_joint)
+    return launch_space_carving(pred, hyp, hyp_full, mask, K, N, P, threshold, grad_scale, 1.0f / (float)N, loss_out, d_pred, d_hyp,
+                                nullptr, nullptr, nullptr, nullptr, st);
   size_t need = scade_space_carving_workspace_bytes(K, N, P);
   if (workspace == nullptr || workspace_bytes < need) {
     set_error("space_carving_loss(is_joint): workspace %zu < %zu bytes", workspace_bytes, need);
@@ -302,21 +323,18 @@ extern "C" int scade_space_carving_loss(const float* pred, const float* hyp, int
 extern "C" int scade_space_carving_loss_affine(const float* pred, const float* hyp_raw, const float* scale_dev,
                                                const float* shift_dev, const float* mask, int K, int64_t N, int P,
                                                float threshold, float grad_scale, int64_t denominator, float* loss_out,
-                                               float* d_pred, float* d_scale_shift, void* stream) {
-  SCADE_CHECK_ARG(pred && hyp_raw && scale_dev && shift_dev && loss_out && K > 0 && N > 0 && P > 0,
+                                               float* d_pred, float* d_scale, float* d_shift, int accumulate, void* stream) {
+  SCADE_CHECK_ARG(pred && hyp_raw && scale_dev && shift_dev && loss_out && K > 0 && N > 0 && P > 0 && ((d_scale == nullptr) == (d_shift == nullptr)),
                   "space_carving_loss_affine: bad arguments");
   cudaStream_t st = as_stream(stream);
   SCADE_CUDA(cudaMemsetAsync(loss_out, 0, sizeof(float), st));
-  if (d_scale_shift) SCADE_CUDA(cudaMemsetAsync(d_scale_shift, 0, 2 * sizeof(float), st));
-  size_t smem = ((size_t)2 * K * SC_RAYS + (size_t)SC_WARPS * K * 32) * sizeof(float);
-  SCADE_CHECK_ARG(smem <= 160 * 1024, "space_carving_loss_affine: K=%d too large", K);
-  if (smem > 48 * 1024)
-    SCADE_CUDA(cudaFuncSetAttribute(space_carving_ray_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (d_scale && !accumulate) {
+    SCADE_CUDA(cudaMemsetAsync(d_scale, 0, sizeof(float), st));
+    SCADE_CUDA(cudaMemsetAsync(d_shift, 0, sizeof(float), st));
+  }
   const float inv_n = 1.0f / (float)(denominator > 0 ? denominator : N);
-  space_carving_ray_kernel<<<(unsigned)ceil_div<int64_t>(N, SC_RAYS), SC_WARPS * 32, smem, st>>>(
-      pred, hyp_raw, 0, mask, K, N, P, threshold, grad_scale, inv_n, loss_out, d_pred, nullptr, scale_dev, shift_dev, d_scale_shift);
-  SCADE_LAUNCH_CHECK();
-  return SCADE_OK;
+  return launch_space_carving(pred, hyp_raw, 0, mask, K, N, P, threshold, grad_scale, inv_n, loss_out, d_pred, nullptr, scale_dev,
+                              shift_dev, d_scale, d_shift, st);
 }
 
 extern "C" int scade_space_carving_joint_accumulate(const float* pred, const float* hyp, int hyp_full, const float* mask, int K,

@@ -1353,6 +1353,8 @@ int mlp_tc_backward(const scade_net& net, const float* d_out, int64_t P, float* 
   // 4. alpha_linear / rgb_linear
   {
     const int pv = 2 * d.D;
+    // a block walks its tiles one after the other at load latency (~12-19 us per 128-point tile): as many blocks as tiles,
+    // up to 4 per SM (fewer, larger blocks were 3x slower at 512 rays)
     const int blocks = (int)std::min<int64_t>(L.T, 4 * num_sms());
     tc::head_wgrad_tc_kernel<<<blocks, 256, 0, st>>>(ws, L, reinterpret_cast<const float4*>(d_out), P, grads[pv + 4], grads[pv + 5],
                                                      grads[pv + 6], grads[pv + 7]);

@@ -147,9 +147,44 @@ def sharded_train_step(ray_batch, target_s, target_h, scale, shift, render_kwarg
     affine = (not is_joint and torch.is_tensor(scale) and torch.is_tensor(shift) and scale.numel() == 1 and shift.numel() == 1
               and scale.is_cuda and shift.is_cuda and target_h.dim() == 3 and target_h.shape[-1] == 1)
     th = None if affine else target_h * scale + shift                                   # RS:954
+    if (t_rand is None and u_coarse is None and u_fine is None and float(render_kwargs.get("perturb", 0.)) > 0. and not is_joint):
+        # the step's three uniform draws (RS:570, H:350 twice) as ONE generator launch carved into views (same distribution
+        # as the reference's three torch.rand calls, a different position in the Philox stream)
+        Ns, Ni = int(render_kwargs["N_samples"]), int(render_kwargs["N_importance"])
+        r = torch.rand(n_local * (Ns + 2 * Ni), device=ray_batch.device)
+        t_rand = r[:n_local * Ns].view(n_local, Ns)
+        u_coarse = r[n_local * Ns:n_local * (Ns + Ni)].view(n_local, Ni)
+        u_fine = r[n_local * (Ns + Ni):].view(n_local, Ni)
     bucket = _BucketOverlap(flat, fine if (overlap and fine is not coarse) else None, group) if use_flat else None
     ret = R_.render_rays(ray_batch, True, cached_u=u_fine, t_rand=t_rand, u_coarse=u_coarse, retraw=False, is_joint=is_joint,
                          **render_kwargs)
+    if use_flat and affine:
+        # Loss heads without autograd nodes (3 launches): each kernel writes its local-sum / GLOBAL-count loss straight into a
+        # slot of the flat gradient buffer's tail (so the partials ride in the exchange without a stack / copy) and returns the
+        # gradient of the total loss w.r.t. its input; d scale / d shift are accumulated into the parameters' .grad slots by
+        # the space-carving kernel itself when they are leaves with flat gradients, else handed to autograd.
+        tail = flat.tail()
+        d_rgb = F_.img2mse_head(ret["rgb_map"], target_s, n_global * 3, 1.0, tail[0:1])                   # RS:968
+        d_rgb0 = F_.img2mse_head(ret["rgb0"], target_s, n_global * 3, 1.0, tail[2:3])                     # RS:981
+        direct_ss = all(t.is_leaf and t.grad is not None and t.grad.is_cuda and t.grad.is_contiguous() for t in (scale, shift))
+        if direct_ss:
+            d_sc, d_sh = scale.grad.reshape(-1), shift.grad.reshape(-1)
+        else:
+            d_ss = torch.empty(2, dtype=torch.float32, device=ray_batch.device)
+            d_sc, d_sh = d_ss[0:1], d_ss[1:2]
+        d_pred = F_.space_carving_affine_head(ret["pred_hyp"], target_h, scale, shift, mask, threshold, n_global,
+                                              space_carving_weight, tail[1:2], d_sc, d_sh, accumulate=direct_ss)   # RS:954,974
+        outs, grads = [ret["rgb_map"], ret["rgb0"], ret["pred_hyp"]], [d_rgb, d_rgb0, d_pred]
+        if not direct_ss:
+            for t, g in ((scale, d_sc), (shift, d_sh)):
+                if t.requires_grad:
+                    outs.append(t)
+                    grads.append(g.reshape(t.shape))
+        torch.autograd.backward(outs, grads)                                            # RS:985
+        bucket.finish()
+        losses = tail[:3].clone()
+        return {"img_loss": losses[0], "space_carving": losses[1], "img_loss0": losses[2],
+                "loss": torch.add(losses[0] + losses[2], losses[1], alpha=float(space_carving_weight))}
     # local sums divided by the global count: sum over ranks == the single-GPU mean (H:11, H:125-126)
     img_loss = F_img2mse(ret["rgb_map"], target_s, n_global * 3)
     img_loss0 = F_img2mse(ret["rgb0"], target_s, n_global * 3)
@@ -223,8 +258,11 @@ class GraphedTrainStep:
         self.graph, self.static, self.losses = None, None, None
 
     def _body(self, rb, ts, th):
-        for o in self.opts:
-            o.zero_grad(set_to_none=False)
+        if self.flat is not None and self.flat.intact():
+            self.flat.zero_grad()                             # one memset for every gradient + the loss-partial tail
+        else:
+            for o in self.opts:
+                o.zero_grad(set_to_none=False)
         if self.per_image:                                  # curr_scale = DEPTH_SCALES[img_i] (RS:947-948), index on the device
             scale = self.scale.index_select(0, self.img_index).reshape(1)
             shift = self.shift.index_select(0, self.img_index).reshape(1)

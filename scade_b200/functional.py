@@ -345,7 +345,7 @@ class _Raw2OutputsFn(torch.autograd.Function):
         acc = torch.empty_like(disp)
         depth = torch.empty_like(disp)
         w = torch.empty((N, S), dtype=torch.float32, device=dev)
-        check(_L().scade_raw2outputs(ptr(raw), ptr(z_vals), ptr(rays_d), rays_d.shape[1], ptr(noise), N, S, ptr(rgb),
+        check(_L().scade_raw2outputs(ptr(raw), ptr(z_vals), _row_ptr(rays_d), rays_d.stride(0), ptr(noise), N, S, ptr(rgb),
                                      ptr(disp), ptr(acc), ptr(w), ptr(depth), stream_ptr()), "scade_raw2outputs")
         ctx.save_for_backward(raw, z_vals, rays_d, noise if noise is not None else torch.empty(0, device=dev))
         ctx.has_noise = noise is not None
@@ -360,16 +360,29 @@ class _Raw2OutputsFn(torch.autograd.Function):
             return None, None, None, None
         d_raw = torch.empty_like(raw)
         g = [None if t is None else f32(t) for t in (d_rgb, d_disp, d_acc, d_w, d_depth)]
-        check(_L().scade_raw2outputs_backward(ptr(raw), ptr(z_vals), ptr(rays_d), rays_d.shape[1],
+        check(_L().scade_raw2outputs_backward(ptr(raw), ptr(z_vals), _row_ptr(rays_d), rays_d.stride(0),
                                               ptr(noise) if ctx.has_noise else None, N, S, ptr(g[0]), ptr(g[1]),
                                               ptr(g[2]), ptr(g[3]), ptr(g[4]), ptr(d_raw), stream_ptr()),
               "scade_raw2outputs_backward")
         return d_raw, None, None, None
 
 
+def _row_ptr(t):
+    """Device pointer of a 2-D fp32 CUDA tensor whose rows are contiguous but may be strided (a column slice such as
+    ray_batch[:, 3:6]): the kernels take the row stride separately."""
+    if not t.is_cuda or t.dtype != torch.float32 or t.dim() != 2 or t.stride(1) != 1:
+        raise _lib.ScadeError("expected a 2-D fp32 CUDA tensor with unit column stride")
+    return c_void_p(t.data_ptr())
+
+
 def raw2outputs(raw, z_vals, rays_d, noise=None):
-    """compute_weights + raw2outputs (RS:511-562) -> (rgb_map, disp_map, acc_map, weights, depth_map)."""
-    return _Raw2OutputsFn.apply(f32(raw), f32(z_vals), f32(rays_d), None if noise is None else f32(noise))
+    """compute_weights + raw2outputs (RS:511-562) -> (rgb_map, disp_map, acc_map, weights, depth_map).  rays_d [N,3] may be a
+    column slice of the ray batch (no copy is made)."""
+    if not torch.is_tensor(rays_d):
+        rays_d = torch.as_tensor(rays_d)
+    if rays_d.dtype != torch.float32 or rays_d.dim() != 2 or rays_d.stride(1) != 1:
+        rays_d = f32(rays_d).reshape(-1, rays_d.shape[-1])
+    return _Raw2OutputsFn.apply(f32(raw), f32(z_vals), rays_d, None if noise is None else f32(noise))
 
 
 # ----------------------------------------------------------------------------------------------
@@ -511,8 +524,9 @@ class _SpaceCarvingAffineFn(torch.autograd.Function):
         d_pred = torch.empty_like(pred) if want else None
         d_ss = torch.empty((2,), dtype=torch.float32, device=dev) if want else None
         check(_L().scade_space_carving_loss_affine(ptr(pred), ptr(hyp_raw), ptr(scale), ptr(shift), ptr(mask), K, N, P,
-                                                   float(threshold), 1.0, int(denominator), ptr(loss), ptr(d_pred), ptr(d_ss),
-                                                   stream_ptr()), "scade_space_carving_loss_affine")
+                                                   float(threshold), 1.0, int(denominator), ptr(loss), ptr(d_pred),
+                                                   ptr(d_ss), ptr(d_ss[1:]) if want else None, 0, stream_ptr()),
+              "scade_space_carving_loss_affine")
         if want:
             ctx.save_for_backward(d_pred, d_ss)
         ctx.shapes = (scale.shape, shift.shape)
@@ -594,6 +608,32 @@ class _MseFn(torch.autograd.Function):
     def backward(ctx, g):
         (d_x,) = ctx.saved_tensors
         return d_x * g, None, None, None
+
+
+def img2mse_head(x, y, denominator, grad_scale, loss_out):
+    """img2mse (H:11) as a loss HEAD without autograd nodes: writes the loss into `loss_out` (1 float, e.g. a slot of the flat
+    gradient buffer's tail) and returns grad_scale * d loss / d x for torch.autograd.backward(x, grad)."""
+    x = f32(x)
+    d_x = torch.empty_like(x)
+    check(_L().scade_img2mse(ptr(x), ptr(f32(y).expand_as(x).contiguous()), x.numel(), int(denominator), float(grad_scale),
+                             ptr(loss_out), ptr(d_x), stream_ptr()), "scade_img2mse")
+    return d_x
+
+
+def space_carving_affine_head(pred, hyp_raw, scale, shift, mask, threshold, denominator, grad_scale, loss_out, d_scale, d_shift,
+                              accumulate):
+    """scade_space_carving_loss_affine as a loss head without autograd nodes: the (unweighted) loss goes to `loss_out`,
+    grad_scale * d loss / d pred is returned, grad_scale * d loss / d scale|shift are written (or accumulated) into the
+    1-element tensors d_scale / d_shift."""
+    pred, hyp_raw = f32(pred), f32(hyp_raw)
+    N, P = pred.shape
+    d_pred = torch.empty_like(pred)
+    check(_L().scade_space_carving_loss_affine(ptr(pred), ptr(hyp_raw), ptr(f32(scale)), ptr(f32(shift)),
+                                               ptr(None if mask is None else f32(mask)), hyp_raw.shape[0], N, P, float(threshold),
+                                               float(grad_scale), int(denominator), ptr(loss_out), ptr(d_pred), ptr(d_scale),
+                                               ptr(d_shift), int(bool(accumulate)), stream_ptr()),
+          "scade_space_carving_loss_affine")
+    return d_pred
 
 
 def img2mse(x, y, denominator=0):

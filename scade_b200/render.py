@@ -162,7 +162,7 @@ def render_rays(ray_batch, use_viewdirs, network_fn, network_query_fn, N_samples
                                       precision=network_query_fn.precision, lindisp=lindisp, is_joint=False,
                                       t_rand=t_rand, u_coarse=u_coarse, u_fine=u_fine, retraw=retraw, out=_out)
 
-    rays_o, rays_d, viewdirs = ray_batch[:, 0:3], ray_batch[:, 3:6].contiguous(), ray_batch[:, 8:11]
+    rays_o, rays_d, viewdirs = ray_batch[:, 0:3], ray_batch[:, 3:6], ray_batch[:, 8:11]     # (views: the kernels take a row stride)
 
     def query(z, net):
         if fused:

@@ -392,3 +392,25 @@ def test_space_carving_affine_matches_composed(dev):
         l3 = F_.space_carving_loss_affine(p3, T(hyp[:, :300]), s2.detach(), h2.detach(), mask=T(mask[:300]), threshold=thr, denominator=N)
         l3f = F_.space_carving_loss(T(pred[:300]), T(hyp[:, :300]) * 1.07 - 0.04, mask=T(mask[:300]), threshold=thr)
         np.testing.assert_allclose(float(l3.detach()), float(l3f) * 300 / N, rtol=1e-6)
+
+
+@pytest.mark.parametrize("N", [300, 9001])
+def test_space_carving_both_block_shapes_vs_oracle(dev, N):
+    """The default branch picks 8 rays per block for small batches and 32 (hypotheses staged along N) from 8192 rays on:
+    both against the oracle, forward and backward, with a mask and ragged last blocks."""
+    from scade_b200 import functional as F_
+    rng = np.random.default_rng(N)
+    P, K = 48, 6
+    pred = rng.uniform(0.3, 4.8, (N, P)).astype(np.float32)
+    hyp = rng.uniform(0.1, 5.0, (K, N, 1)).astype(np.float32)
+    hyp[1] = hyp[0]                                                                  # duplicates: ties pick the first k
+    mask = (rng.random(N) > 0.15).astype(np.float32)
+    T = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    p_t, h_t = T(pred).requires_grad_(True), T(hyp).requires_grad_(True)
+    loss = F_.space_carving_loss(p_t, h_t, mask=T(mask), threshold=0.02)
+    loss.backward()
+    np.testing.assert_allclose(float(loss.detach()), float(O.space_carving_loss(pred, hyp, False, mask, 0.02)), rtol=3e-6)
+    d_pred, d_hyp = O.space_carving_loss_bwd(pred, hyp, False, mask, 0.02)
+    np.testing.assert_allclose(p_t.grad.cpu().numpy(), d_pred, rtol=1e-5, atol=1e-12)
+    np.testing.assert_allclose(h_t.grad.cpu().numpy(), d_hyp, rtol=1e-4, atol=1e-10)
+    assert float(h_t.grad[1].abs().max()) == 0.0                                     # the duplicate never wins
