@@ -33,6 +33,8 @@
 #include <cuda.h>
 #include <cuda_fp16.h>
 
+#include <stdlib.h>
+
 #include <algorithm>
 #include <type_traits>
 
