@@ -289,6 +289,21 @@ def run_gpu(args):
     sync_all()
     e2e_eager_sec = time.perf_counter() - t0
 
+    # ---- the same end-to-end step with depth-2 pipelining (scade_b200.render.PipelinedRenderRays): step s+1's rays cross PCIe
+    #      and step s-1's maps travel back while step s computes; every step still copies its own inputs and results ----
+    pipe = R_.PipelinedRenderRays(N_RAYS, depth=2, host_outputs=tuple(out_host), **kwargs)
+    for _ in range(4):
+        pipe.submit(rb_host)
+    pipe.drain()
+    sync_all()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        pipe.submit(rb_host)
+    pipe.drain()
+    sync_all()
+    e2e_pipe_sec = time.perf_counter() - t0
+    del pipe
+
     # ---- dominant kernel alone: fine-pass MLP launch (4096 x 256 points) ----
     z_f = step_resident()["z_vals"]
     fused_comp = F_.composite_fusable(netf.handle(), prec, N_COARSE + N_FINE)
@@ -348,6 +363,9 @@ def run_gpu(args):
                     "api": "scade_b200.render.GraphedRenderRays (render_rays for a fixed chunk size replayed as one CUDA graph that "
                            "includes the H2D copy of the pinned host ray batch and the D2H copies of the rgb/disp/acc/depth maps; "
                            "stream sync every step)",
+                    "pipelined_value": N_RAYS * world * args.steps / e2e_pipe_sec,
+                    "pipelined_api": "scade_b200.render.PipelinedRenderRays(depth=2): two graph slots on two streams, the copies of one step "
+                                     "overlap the kernels of the other; same bytes per step (rank-0 clock)",
                     "eager_value": N_RAYS * world * args.steps / e2e_eager_sec,
                     "eager_api": "scade_b200.render.render_rays called eagerly every step (same copies; rank-0 clock)"},
             "gpu_launches": int(launches),

@@ -259,6 +259,58 @@ class GraphedRenderRays:
         return self.out
 
 
+class PipelinedRenderRays:
+    """`depth` GraphedRenderRays slots, each on its own CUDA stream, used round-robin: while slot A's kernels run, slot B's ray
+    batch crosses PCIe and slot A's previous maps travel back -- the copies of a serving loop overlap the compute instead of
+    bracketing it.  Each slot owns its pinned host buffers, device buffers and graph.
+
+        pipe = PipelinedRenderRays(n_rays, depth=2, host_outputs=("rgb_map", "depth_map"), **render_kwargs_test)
+        t0 = pipe.submit(rays_host_0)                # host tensor [n_rays, 11]; returns a ticket
+        t1 = pipe.submit(rays_host_1)
+        maps0 = pipe.result(t0)                      # waits for that submission only; pinned host tensors, valid until the
+                                                     # slot is submitted again (depth submissions later)
+    """
+
+    def __init__(self, n_rays, depth=2, host_outputs=("rgb_map", "disp_map", "acc_map", "depth_map"), device=None, **kwargs):
+        self.device = device or torch.device("cuda", torch.cuda.current_device())
+        self.depth = int(depth)
+        self.streams = [torch.cuda.Stream(device=self.device) for _ in range(self.depth)]
+        self.slots = []
+        for st in self.streams:
+            st.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(st):
+                self.slots.append(GraphedRenderRays(n_rays, device=self.device, host_outputs=host_outputs, **kwargs))
+        torch.cuda.synchronize(self.device)
+        self.events = [None] * self.depth
+        self.count = 0
+
+    def submit(self, ray_batch_host):
+        i = self.count % self.depth
+        if self.events[i] is not None:
+            self.events[i].synchronize()             # the slot's previous run has read its rays_host and written its out_host
+        slot = self.slots[i]
+        slot.rays_host.copy_(ray_batch_host)
+        with torch.cuda.stream(self.streams[i]):
+            slot.graph.replay()
+            ev = torch.cuda.Event()
+            ev.record(self.streams[i])
+        self.events[i] = ev
+        self.count += 1
+        return self.count - 1
+
+    def result(self, ticket):
+        if ticket < self.count - self.depth or ticket >= self.count:
+            raise ValueError("PipelinedRenderRays.result: that submission's slot has been reused (or the ticket is unknown)")
+        i = ticket % self.depth
+        self.events[i].synchronize()
+        return self.slots[i].out_host
+
+    def drain(self):
+        for ev in self.events:
+            if ev is not None:
+                ev.synchronize()
+
+
 def batchify_rays(rays_flat, chunk=1024 * 32, use_viewdirs=False, **kwargs):
     """RS:66-78"""
     all_ret = {}

@@ -176,3 +176,39 @@ def test_cpp_host_renders_through_the_c_abi(dev):
     r = subprocess.run([exe, "96", "128"], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "OK" in r.stdout and "kernel launches/frame" in r.stdout, r.stdout
+
+
+def test_pipelined_render_rays_matches_single_calls(dev):
+    """PipelinedRenderRays (two graph slots on two streams, copies overlapping compute): every submission returns exactly what
+    render_rays returns for that batch, in order, also when slots are reused."""
+    import numpy as np
+    import torch
+    from scade_b200 import nerf_helpers as NH, render as R_, synthetic as syn
+    from tests.golden.generate_goldens import net_pair
+    pc, pf = net_pair(8, 256)
+    bb_center, bb_scale = syn.bounding_box()
+
+    def mk(p):
+        net = NH.NeRF(D=8, W=256, input_ch=57, input_ch_views=3, output_ch=5, skips=[4], use_viewdirs=True, precision="tc_f16")
+        net.load_state_dict({k: torch.from_numpy(v) for k, v in p.items()})
+        return net.to(dev).requires_grad_(False)
+    qf = R_.NetworkQuery(NH.get_embedder(9, 0)[0], NH.get_embedder(0, 0)[0], bb_center, bb_scale, precision="tc_f16")
+    kw = dict(network_fn=mk(pc), network_query_fn=qf, N_samples=64, embedded_cam=torch.tensor((), device=dev), perturb=0.0,
+              N_importance=128, network_fine=mk(pf), raw_noise_std=0.0)
+    n = 300
+    batches = [torch.from_numpy(syn.make_ray_batch(n, seed=200 + i)).pin_memory() for i in range(5)]
+    pipe = R_.PipelinedRenderRays(n, depth=2, host_outputs=("rgb_map", "depth_map"), **kw)
+    tickets, got = [], []
+    for i, b in enumerate(batches):
+        tickets.append(pipe.submit(b))
+        if i >= 1:                                        # consume with one submission in flight
+            out = pipe.result(tickets[i - 1])
+            got.append({k: v.clone() for k, v in out.items()})
+    got.append({k: v.clone() for k, v in pipe.result(tickets[-1]).items()})
+    with torch.no_grad():
+        for b, g in zip(batches, got):
+            ref = R_.render_rays(b.to(dev), True, **kw)
+            np.testing.assert_array_equal(g["rgb_map"].numpy(), ref["rgb_map"].cpu().numpy())
+            np.testing.assert_array_equal(g["depth_map"].numpy(), ref["depth_map"].cpu().numpy())
+    with pytest.raises(ValueError):
+        pipe.result(tickets[0])                           # that slot has been reused since
