@@ -156,8 +156,8 @@ def sharded_train_step(ray_batch, target_s, target_h, scale, shift, render_kwarg
         u_coarse = r[n_local * Ns:n_local * (Ns + Ni)].view(n_local, Ni)
         u_fine = r[n_local * (Ns + Ni):].view(n_local, Ni)
     bucket = _BucketOverlap(flat, fine if (overlap and fine is not coarse) else None, group) if use_flat else None
-    ret = R_.render_rays(ray_batch, True, cached_u=u_fine, t_rand=t_rand, u_coarse=u_coarse, retraw=False, is_joint=is_joint,
-                         **render_kwargs)
+    kw = {k: v for k, v in render_kwargs.items() if k not in ("retraw", "is_joint", "cached_u", "t_rand", "u_coarse", "use_viewdirs")}
+    ret = R_.render_rays(ray_batch, True, cached_u=u_fine, t_rand=t_rand, u_coarse=u_coarse, retraw=False, is_joint=is_joint, **kw)
     if use_flat and affine:
         # Loss heads without autograd nodes (3 launches): each kernel writes its local-sum / GLOBAL-count loss straight into a
         # slot of the flat gradient buffer's tail (so the partials ride in the exchange without a stack / copy) and returns the
