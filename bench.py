@@ -656,6 +656,8 @@ def main():
                     help="render = BASELINE metric (default); render_c2 = config 2 (1024 rays x (64c+128f), 1 GPU); train = config 3 (4096 rays, 64c+128f, K=20, fwd+loss+bwd+allreduce+Adam); "
                          "image / video = configs 4 / 5 (full 640x480 frames, pixels sharded across the GPUs)")
     args = ap.parse_args()
+    # rank 0 prints ONE JSON line on stdout: NCCL's own banner ("NCCL version ...", whenever NCCL_DEBUG is set on the box) goes to stderr
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     if args.workload == "render_c2":
         set_shape(1024, 64, 128, "BASELINE config 2")
         args.no_train = True
