@@ -156,6 +156,21 @@ def sharded_train_step(ray_batch, target_s, target_h, scale, shift, render_kwarg
         u_coarse = r[n_local * Ns:n_local * (Ns + Ni)].view(n_local, Ni)
         u_fine = r[n_local * (Ns + Ni):].view(n_local, Ni)
     bucket = _BucketOverlap(flat, fine if (overlap and fine is not coarse) else None, group) if use_flat else None
+    try:
+        return _sharded_train_step_body(ray_batch, target_s, target_h, scale, shift, render_kwargs, n_global, n_local, world,
+                                        space_carving_weight, threshold, mask, t_rand, u_coarse, u_fine, group, flat, is_joint,
+                                        use_flat, affine, th, bucket, coarse, fine, None if use_flat else leaves)
+    finally:
+        if bucket is not None and bucket.handle is not None:
+            bucket.handle.grad_ready_hook = None          # never leave the early-bucket hook armed after a failed step
+
+
+def _sharded_train_step_body(ray_batch, target_s, target_h, scale, shift, render_kwargs, n_global, n_local, world,
+                             space_carving_weight, threshold, mask, t_rand, u_coarse, u_fine, group, flat, is_joint, use_flat,
+                             affine, th, bucket, coarse, fine, leaves):
+    from . import functional as F_
+    from . import nerf_helpers as NH
+    from . import render as R_
     kw = {k: v for k, v in render_kwargs.items() if k not in ("retraw", "is_joint", "cached_u", "t_rand", "u_coarse", "use_viewdirs")}
     ret = R_.render_rays(ray_batch, True, cached_u=u_fine, t_rand=t_rand, u_coarse=u_coarse, retraw=False, is_joint=is_joint, **kw)
     if use_flat and affine:

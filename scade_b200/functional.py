@@ -125,15 +125,24 @@ def stash_layout(handle, P):
     return out
 
 
-_direct_grad_ids = set()      # id(param) of parameters whose owner opted in to in-place gradient accumulation
+_direct_grad_refs = {}         # id(param) -> weakref of parameters whose owner opted in to in-place gradient accumulation
 
 
 def enable_direct_grads(params, on=True):
     """Opt in (scade_b200.optim.FlatParams does) to having the backward kernels accumulate straight into ``p.grad`` instead of
     returning gradients through autograd.  Explicit because it bypasses autograd's own accumulation: tensor hooks on the
     parameters do not fire and torch.autograd.grad() would still write .grad."""
+    import weakref
     for p in params:
-        (_direct_grad_ids.add if on else _direct_grad_ids.discard)(id(p))
+        if on:
+            _direct_grad_refs[id(p)] = weakref.ref(p, lambda _r, k=id(p): _direct_grad_refs.pop(k, None))
+        else:
+            _direct_grad_refs.pop(id(p), None)
+
+
+def _direct_grad(p):
+    r = _direct_grad_refs.get(id(p))
+    return r is not None and r() is p              # (an id can be recycled after the registered tensor died)
 
 
 def _mlp_backward(handle, precision, d_out, P, ws, device):
@@ -143,7 +152,7 @@ def _mlp_backward(handle, precision, d_out, P, ws, device):
     set, is called once the backward kernels of this network are enqueued (scade_b200.dist launches that network's gradient
     bucket all-reduce from it, overlapping the rest of the backward)."""
     params = handle.params
-    direct = all(id(p) in _direct_grad_ids and p.requires_grad and p.grad is not None and p.grad.is_contiguous()
+    direct = all(_direct_grad(p) and p.requires_grad and p.grad is not None and p.grad.is_contiguous()
                  and p.grad.dtype == torch.float32 and p.grad.is_cuda for p in params)
     if direct:
         grads = [p.grad for p in params]
