@@ -122,7 +122,7 @@ __device__ __forceinline__ void resample_ray(const RayPdfSource& src, int64_t r_
   float* s_sort = s_bins + B;
   build_cdf(src, r_src, s_cdf, s_bins, lane);
   constexpr int G = 4;
-  float ssum = 0.f, sqsum_pass = 0.f;
+  float ssum = 0.f;
   const bool one_group = n <= 32 * G;                   // (n = 128: every lane holds all of its samples in registers)
   float kept[G];
   for (int j0 = 0; j0 < n; j0 += 32 * G) {
@@ -169,7 +169,6 @@ __device__ __forceinline__ void resample_ray(const RayPdfSource& src, int64_t r_
         v += d * d;
       }
     }
-    (void)sqsum_pass;
     v = warp_sum(v) / (float)n;
     if (lane == 0) z_std[r] = sqrtf(v);
   }
