@@ -159,10 +159,33 @@ def sharded_train_step(ray_batch, target_s, target_h, scale, shift, render_kwarg
     try:
         return _sharded_train_step_body(ray_batch, target_s, target_h, scale, shift, render_kwargs, n_global, n_local, world,
                                         space_carving_weight, threshold, mask, t_rand, u_coarse, u_fine, group, flat, is_joint,
-                                        use_flat, affine, th, bucket, coarse, fine, None if use_flat else leaves)
+                                        use_flat, affine, th, bucket, coarse, fine, list(extra_params or []) if use_flat else leaves)
     finally:
         if bucket is not None and bucket.handle is not None:
             bucket.handle.grad_ready_hook = None          # never leave the early-bucket hook armed after a failed step
+
+
+def _reduce_grads(tensors, group):
+    """In-place sum over the ranks of the .grad of a few small leaf tensors (scale / shift kept outside the flat storage)."""
+    if _world(group)[1] > 1:
+        for t in tensors:
+            if t.grad is not None:
+                dist.all_reduce(t.grad, op=dist.ReduceOp.SUM, group=group)
+
+
+def _outside_flat(flat, scale, shift, extra_params):
+    """Leaf tensors that receive gradients in the step but do not live in `flat` (their .grad needs its own all-reduce).
+    Raises for non-leaf scale / shift whose leaves were not named."""
+    inside = {id(p) for p in flat.params}
+    out = [t for t in (extra_params or []) if id(t) not in inside]
+    for t in (scale, shift):
+        if not (torch.is_tensor(t) and t.requires_grad):
+            continue
+        if t.is_leaf and id(t) not in inside and all(t is not o for o in out):
+            out.append(t)
+        # (a non-leaf scale / shift such as DEPTH_SCALES[img_i] sends its gradient to its table: inside `flat`, or named in
+        #  extra_params)
+    return out
 
 
 def _sharded_train_step_body(ray_batch, target_s, target_h, scale, shift, render_kwargs, n_global, n_local, world,
@@ -197,6 +220,7 @@ def _sharded_train_step_body(ray_batch, target_s, target_h, scale, shift, render
                     grads.append(g.reshape(t.shape))
         torch.autograd.backward(outs, grads)                                            # RS:985
         bucket.finish()
+        _reduce_grads(_outside_flat(flat, scale, shift, leaves), group)
         losses = tail[:3].clone()
         return {"img_loss": losses[0], "space_carving": losses[1], "img_loss0": losses[2],
                 "loss": torch.add(losses[0] + losses[2], losses[1], alpha=float(space_carving_weight))}
@@ -223,6 +247,7 @@ def _sharded_train_step_body(ray_batch, target_s, target_h, scale, shift, render
         tail = flat.tail()
         tail[:k].copy_(losses)
         bucket.finish()
+        _reduce_grads(_outside_flat(flat, scale, shift, leaves), group)
         losses = tail[:k].clone()
     else:
         params = [p for net in dict.fromkeys([coarse, fine]) for p in net.parameters() if p.requires_grad]

@@ -115,6 +115,17 @@ def _bucket_worker(rank, world, port, out_dir):
         calls = b.finish()
         assert fine.handle().grad_ready_hook is None
         results[order] = {"sent": sent, "got": flat.flat_grad.clone(), "calls": calls, "range": b.range, "intact": flat.intact()}
+    # scale / shift leaves kept OUTSIDE the flat storage get their own (tiny) all-reduce; those inside do not
+    from scade_b200.dist import _outside_flat, _reduce_grads
+    net = NeRF(D=2, W=8, input_ch=9, input_ch_views=3, output_ch=5, skips=[4], use_viewdirs=True)
+    s_in, s_out, h_out = (torch.ones(1, requires_grad=True) for _ in range(3))
+    flat = flatten_parameters(net, [s_in])
+    s_out.grad, h_out.grad = torch.full((1,), float(rank + 1)), torch.full((1,), 10.0 * (rank + 1))
+    assert _outside_flat(flat, s_in, h_out, None) == [h_out]
+    outside = _outside_flat(flat, s_out, h_out, None)
+    assert len(outside) == 2 and outside[0] is s_out and outside[1] is h_out
+    _reduce_grads(outside, None)
+    results["outside"] = (float(s_out.grad), float(h_out.grad))
     torch.save(results, os.path.join(out_dir, f"bucket{rank}.pt"))
     dist.barrier()
     dist.destroy_process_group()
@@ -129,3 +140,4 @@ def test_bucketed_gradient_exchange_world2(tmp_path):
         for r in res:
             assert r[order]["intact"] and r[order]["calls"] == want_calls, (order, r[order]["calls"])
             assert torch.allclose(r[order]["got"], want, rtol=1e-6, atol=1e-6), order
+    assert all(r["outside"] == (3.0, 30.0) for r in res)
