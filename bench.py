@@ -43,6 +43,19 @@ def set_shape(n_rays, n_coarse, n_fine, tag):
     METRIC = f"rays/sec ({N_RAYS} rays x {N_COARSE + N_FINE} samples, 8x256 MLP)"
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """The one JSON line of the run, on the process's real stdout (see main())."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def load_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -130,7 +143,7 @@ def run_reference(args):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(), "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": base["value"], "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -383,7 +396,7 @@ def run_gpu(args):
         if not args.no_cpu_baseline:
             base = cpu_arm(N_RAYS, 2, 1)
             line["cpu_baseline"] = {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         # the other ranks must not busy-wait in an NCCL barrier (one spinning host thread each) while rank 0 times the CPU
         # baseline on the same cores: they block on the rendezvous store's socket instead
@@ -510,7 +523,7 @@ def run_train(args):
         dist.init_process_group("nccl", device_id=dev)
     rec = measure_train(args, dev, rank, world, args.steps)
     if rank == 0:
-        print(json.dumps(rec), flush=True)
+        emit(rec)
     finish(world)
 
 
@@ -630,7 +643,7 @@ def run_image(args):
         if psnr is not None:
             line["psnr_vs_oracle_db"] = psnr
             line["psnr_note"] = "rgb of frames 0 / 40 / 80 vs the fp32 CPU oracle on 1024 random pixels per frame"
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -656,8 +669,13 @@ def main():
                     help="render = BASELINE metric (default); render_c2 = config 2 (1024 rays x (64c+128f), 1 GPU); train = config 3 (4096 rays, 64c+128f, K=20, fwd+loss+bwd+allreduce+Adam); "
                          "image / video = configs 4 / 5 (full 640x480 frames, pixels sharded across the GPUs)")
     args = ap.parse_args()
-    # rank 0 prints ONE JSON line on stdout: NCCL's own banner ("NCCL version ...", whenever NCCL_DEBUG is set on the box) goes to stderr
-    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+    # stdout carries ONE JSON line (rank 0): everything else that writes to file descriptor 1 during the run -- NCCL's banner
+    # ("NCCL version ...", whenever NCCL_DEBUG is set on the box), library chatter -- is sent to stderr; the line itself goes to
+    # the saved descriptor
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     if args.workload == "render_c2":
         set_shape(1024, 64, 128, "BASELINE config 2")
         args.no_train = True
