@@ -89,6 +89,11 @@ struct LayerDesc {
                           // the 1.0 columns, K positions 48..63, have non-zero weights)
   int bias_stage;         // 1: one extra ring stage carries the bias as a K=16 MMA step against the encoding chunk's 1.0 columns
                           //    (last hidden layer: its shared-memory row is taken by the alpha_linear weights)
+  int a_tmem;             // 1: the activation K chunks of this layer are read from TENSOR MEMORY (columns [0, 128) of the tile's
+                          //    region: 256 fp16 per row, two per column) -- the views layer of the render forward, whose N = 128
+                          //    MMAs are bound by the shared-memory A fetch, not by the math
+  int d_col;              // accumulator column offset inside the tile's 256-column region (128 for that views layer)
+  int out_tmem;           // 1: the epilogue leaves this layer's fp16 output in tensor memory (the feature layer feeding it)
 };
 
 struct NetPlan {
@@ -277,6 +282,7 @@ __device__ __forceinline__ void pp_mma_issuer(const NetPlan& plan, uint32_t sbas
       const int a_step = plan.layers[l].a_step;                // A chunk of K chunk i (after the encoding chunk) = a_step * i
       const int emb_ks0 = plan.layers[l].emb_ks0;
       const uint32_t idesc = make_idesc(2 * TILE_M, plan.layers[l].n_out);
+      const int a_tmem = plan.layers[l].a_tmem, d_col = plan.layers[l].d_col;
       // one (stage, tile): wait for the slot in both CTAs, issue its MMAs for super-tile t, optionally release it
       auto consume_at = [&](int t, uint32_t& slot_ref, uint32_t& ph_ref, int i, bool release) {
         const uint32_t sl = slot_ref, p = ph_ref;
@@ -286,7 +292,7 @@ __device__ __forceinline__ void pp_mma_issuer(const NetPlan& plan, uint32_t sbas
         mbar_wait(bar_full + 8 * sl, p);                 // both CTAs' halves of the stage have landed
         tc_fence_after();
         if (elect_one()) {
-          const uint32_t d_addr = tmem_base + t * W;
+          const uint32_t d_addr = tmem_base + t * W + d_col;
           if (i == n_kst) {
             // bias stage: A = K-step 3 of the encoding chunk (the two 1.0 columns), B = K-step 0 (bias hi/lo at k = 12, 13)
             const uint64_t a_desc = desc_hi | (uint64_t)(((sbase + OFF_EMB + t * CHUNK_BYTES + 3 * 32) & 0x3FFFF) >> 4);
@@ -302,9 +308,17 @@ __device__ __forceinline__ void pp_mma_issuer(const NetPlan& plan, uint32_t sbas
             const uint64_t a_desc = desc_hi | (uint64_t)((a_addr & 0x3FFFF) >> 4);
             const uint64_t b_desc = desc_hi | (uint64_t)(((sbase + OFF_STAGE + sl * STAGE_BYTES + j * (STAGE_BYTES / 2)) & 0x3FFFF) >> 4);
             const int ks0 = emb ? emb_ks0 : 0;                 // the layer's first MMA (K chunk 0, step ks0) overwrites the accumulator
+            if (a_tmem && !emb) {
+              // A from tensor memory: activation chunk c = 64 K values = 32 columns of the tile's region, 8 columns per K step
+              const uint32_t a_col = tmem_base + t * W + (kc - has_emb) * a_step * (KCHUNK / 2);
 #pragma unroll
-            for (int ks = 0; ks < KCHUNK / 16; ++ks)
-              if (ks >= ks0) mma_f16_ss_pair(d_addr, a_desc + 2 * ks, b_desc + 2 * ks, idesc, (kc != 0 || ks != ks0) ? 1u : 0u);
+              for (int ks = 0; ks < KCHUNK / 16; ++ks)
+                mma_f16_ts_pair(d_addr, a_col + 8 * ks, b_desc + 2 * ks, idesc, (kc != 0 || ks != 0) ? 1u : 0u);
+            } else {
+#pragma unroll
+              for (int ks = 0; ks < KCHUNK / 16; ++ks)
+                if (ks >= ks0) mma_f16_ss_pair(d_addr, a_desc + 2 * ks, b_desc + 2 * ks, idesc, (kc != 0 || ks != ks0) ? 1u : 0u);
+            }
           }
           if (release) mma_commit_pair(bar_empty + 8 * sl, (uint16_t)3);
         }
@@ -423,6 +437,39 @@ __device__ __forceinline__ float hidden_epilogue(uint32_t t_col, uint8_t* dst, u
 
 __device__ __forceinline__ void named_bar_sync(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
 __device__ __forceinline__ void named_bar_arrive(int id, int threads) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
+
+// feature_linear's epilogue when the views layer reads its A operand from tensor memory: fp32 accumulators (+ bias, no
+// activation, H:234) -> fp16 pairs -> columns [0, 128) of the tile's own TMEM region (row = lane, column j = features 2j, 2j+1).
+// The two column-half threads of a row interleave 32-column chunks (thread `half` takes chunks half, 2 + half, 4 + half, 6 + half)
+// and write the 16 packed columns of chunk i at [16 i, 16 i + 16).  The packed image overwrites accumulator columns that the
+// OTHER thread of the pair reads (chunks 0..3), so the stores start only after a 64-thread barrier that both pass once their
+// loads of chunks 0..3 have completed; the first chunk's result waits in registers until then.
+__device__ __forceinline__ void feature_epilogue_tmem(uint32_t t_tile, int half, const float* sbias_tile, int pair_bar) {
+  uint32_t r[32], first[16];
+#pragma unroll
+  for (int s = 0; s < 4; ++s) {
+    const int i = 2 * s + half;                                 // 32-column chunk
+    tmem_ld32(t_tile + 32 * i, r);
+    tmem_ld_wait();
+    if (s == 1) named_bar_sync(pair_bar, 64);
+    const float4* p4 = reinterpret_cast<const float4*>(sbias_tile + 32 * i);
+    uint32_t pk[16];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const float4 b = p4[q];
+      pk[2 * q] = pack_plain_f16x2(__float_as_uint(__uint_as_float(r[4 * q]) + b.x), __float_as_uint(__uint_as_float(r[4 * q + 1]) + b.y));
+      pk[2 * q + 1] = pack_plain_f16x2(__float_as_uint(__uint_as_float(r[4 * q + 2]) + b.z), __float_as_uint(__uint_as_float(r[4 * q + 3]) + b.w));
+    }
+    if (s == 0) {
+#pragma unroll
+      for (int q = 0; q < 16; ++q) first[q] = pk[q];
+    } else {
+      if (s == 1) tmem_st16(t_tile + 16 * half, first);
+      tmem_st16(t_tile + 16 * i, pk);
+    }
+  }
+  tmem_st_wait();
+}
 
 // kStash: additionally write every layer's fp16 output chunk (TMA bulk store of the shared-memory image the next layer's
 // MMAs read anyway), the ReLU sign masks and the alpha pre-activation to the training stash.
@@ -634,7 +681,10 @@ __global__ void __launch_bounds__(PP_THREADS, 1) nerf_mlp_tc_pp_kernel(const __g
           if (kind == 1) {
             if (bias_epi) alpha = hidden_epilogue<true, true, true, kStash>(t_col, dst, rx4, srow, wa, sgn);
             else alpha = hidden_epilogue<false, true, true, kStash>(t_col, dst, rx4, srow, wa, sgn);
-          } else if (kind == 2) hidden_epilogue<true, false, false, false>(t_col, dst, rx4, srow, wa, sgn);
+          } else if (kind == 2) {
+            if (!kStash && plan.layers[l].out_tmem) feature_epilogue_tmem(t_lane, half, sbias, pair_bar);
+            else hidden_epilogue<true, false, false, false>(t_col, dst, rx4, srow, wa, sgn);
+          }
           else if (bias_epi) hidden_epilogue<true, true, false, kStash>(t_col, dst, rx4, srow, wa, sgn);
           else hidden_epilogue<false, true, false, kStash>(t_col, dst, rx4, srow, wa, sgn);
           TRACE(tr, 0x600 + l);                          // operand chunks written
@@ -695,8 +745,9 @@ __global__ void __launch_bounds__(PP_THREADS, 1) nerf_mlp_tc_pp_kernel(const __g
           // 1. this thread's 64 accumulator columns -> registers; the tile's TMEM and encoding chunk are then free, so the
           //    next step's layer 0 is released BEFORE the rgb arithmetic (which then runs under that layer's MMAs)
           uint32_t rr[2][32];
-          tmem_ld32(t_lane + half * 64, rr[0]);
-          tmem_ld32(t_lane + half * 64 + 32, rr[1]);
+          const uint32_t t_views = t_lane + plan.layers[l].d_col + half * 64;
+          tmem_ld32(t_views, rr[0]);
+          tmem_ld32(t_views + 32, rr[1]);
           tmem_ld_wait();
           tc_fence_before();
           if (has_next) {
@@ -953,7 +1004,7 @@ __global__ void __launch_bounds__(256) pack_kernel(const __grid_constant__ PackP
 
 // Build the layer table and the stage list for a network description.  Stage order = consumption order:
 // layer -> ring stage -> CTA (CTA 0's N half, CTA 1's N half).  A ring stage holds `kpack` K chunks of one CTA's N half.
-static void build_plans(const scade_net& net, NetPlan* np, PackPlan* pp, bool x3 = false) {
+static void build_plans(const scade_net& net, NetPlan* np, PackPlan* pp, bool x3 = false, bool views_tmem = false) {
   const scade_net_desc& d = net.desc;
   NetDims nd(d);
   NetPlan P{};
@@ -1013,6 +1064,11 @@ static void build_plans(const scade_net& net, NetPlan* np, PackPlan* pp, bool x3
   const int pv = 2 * d.D;
   add_layer(net.params[pv + 2], W, false, 0, 0, 0, 0, true, W, 0, 2, net.params[pv + 3]);                        // feature_linear
   add_layer(net.params[pv], W + nd.in_views, true, W, nd.in_views, nd.in_ch, 0, true, W / 2, 1, 3, net.params[pv + 1]);   // views
+  if (views_tmem) {                                          // feature layer -> TMEM, views layer reads it from there
+    P.layers[P.n_layers - 2].out_tmem = 1;
+    P.layers[P.n_layers - 1].a_tmem = 1;
+    P.layers[P.n_layers - 1].d_col = W / 2;
+  }
   P.stages_per_pass = Q.n_stages;
   Q.n_fwd = Q.n_stages;
   Q.w_alpha = net.params[pv + 4]; Q.b_alpha = net.params[pv + 5];
@@ -1221,7 +1277,10 @@ int mlp_tc_forward(const scade_net& net, const float* rays, int ray_stride, cons
   }
   SCADE_TRY(tc::set_kernel_attributes());
   tc::NetPlan plan;
-  tc::build_plans(net, &plan, nullptr, x3);
+  // render forward (no stash, fast mode): the views layer takes its A operand from tensor memory (SCADE_TC_VIEWS_TMEM=0: from
+  // shared memory, for A/B)
+  static const bool views_tmem_on = [] { const char* e = getenv("SCADE_TC_VIEWS_TMEM"); return e == nullptr || atoi(e) != 0; }();
+  tc::build_plans(net, &plan, nullptr, x3, !x3 && !save && views_tmem_on);
   NetDims nd(net.desc);
   tc::FwdArgs a{};
   a.packed = reinterpret_cast<const uint8_t*>(net.packed_f16);
