@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define SCADE_B200_VERSION 101
+#define SCADE_B200_VERSION 102
 
 typedef enum {
   SCADE_OK = 0,
@@ -97,16 +97,17 @@ int scade_mlp_forward_rays(const scade_net* net, int precision, const float* ray
                            int save_for_backward, void* stream);
 
 /* scade_mlp_forward_rays followed by scade_raw2outputs (RS:659-660 / RS:718-720) as ONE kernel: the alpha compositing
- * (compute_weights' exclusive transmittance product + the weighted sums of raw2outputs, RS:511-562) runs in the epilogue of the
- * last tensor-core layer on the (rgb_raw, sigma) values it just produced, so `raw` never travels through memory
- * (raw_out may be NULL; pass a buffer for retraw).  Bit-identical to the two calls.  SCADE_PREC_TC_F16 only, and S must be 64, 128
- * or 256 (a ray is then a whole number of 32-sample warps inside one CTA's 256 points); otherwise SCADE_ERR_UNSUPPORTED
- * (scade_mlp_forward_rays_composite_supported tells beforehand).  weights [N,S] is required; the maps are nullable. */
+ * (compute_weights' exclusive transmittance product + the weighted sums of raw2outputs, RS:511-562) runs inside the network
+ * kernel on the (rgb_raw, sigma) values its last layer just produced -- a compositor warp per CTA takes them over through a
+ * 4 KB cache-resident slot of `workspace` -- so `raw` never travels through device memory (raw_out may be NULL; pass a buffer
+ * for retraw).  Bit-identical to the two calls.  SCADE_PREC_TC_F16 only, S a multiple of 32 (64 + 128 = 192 included);
+ * otherwise SCADE_ERR_UNSUPPORTED (scade_mlp_forward_rays_composite_supported tells beforehand).  weights [N,S] is required;
+ * the maps are nullable.  workspace: scade_mlp_workspace_bytes(desc, N*S, SCADE_PREC_TC_F16, 0) bytes, 16-byte aligned. */
 int scade_mlp_forward_rays_composite_supported(const scade_net_desc* desc, int precision, int S);
 int scade_mlp_forward_rays_composite(const scade_net* net, int precision, const float* rays, int ray_stride,
                                      const float* z_vals, int64_t N, int S, const float* bb_center_host, float bb_scale,
                                      float* raw_out, float* weights, float* rgb_map, float* disp_map, float* acc_map,
-                                     float* depth_map, void* stream);
+                                     float* depth_map, void* workspace, size_t workspace_bytes, void* stream);
 
 /* NeRF.forward (H:223-247) on an already embedded input x [P, input_ch + input_ch_views]. */
 int scade_mlp_forward_embedded(const scade_net* net, int precision, const float* x, int64_t P,

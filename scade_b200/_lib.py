@@ -58,7 +58,7 @@ _SIGNATURES = {
                                        _P, _P, c_size_t, c_int, _P]),
     "scade_mlp_forward_rays_composite_supported": (c_int, [POINTER(NetDesc), c_int, c_int]),
     "scade_mlp_forward_rays_composite": (c_int, [POINTER(Net), c_int, _P, c_int, _P, c_int64, c_int, POINTER(c_float), c_float,
-                                                 _P, _P, _P, _P, _P, _P, _P]),
+                                                 _P, _P, _P, _P, _P, _P, _P, c_size_t, _P]),
     "scade_mlp_forward_embedded": (c_int, [POINTER(Net), c_int, _P, c_int64, _P, _P, c_size_t, c_int, _P]),
     "scade_mlp_backward": (c_int, [POINTER(Net), c_int, _P, c_int64, POINTER(c_void_p), _P, c_size_t, _P]),
     "scade_mlp_tc_stash_layout": (c_int, [POINTER(NetDesc), c_int64, POINTER(c_int64), c_int]),

@@ -120,19 +120,20 @@ extern "C" int scade_mlp_forward_rays_composite_supported(const scade_net_desc* 
 extern "C" int scade_mlp_forward_rays_composite(const scade_net* net, int precision, const float* rays, int ray_stride,
                                                 const float* z_vals, int64_t N, int S, const float* bb_center_host,
                                                 float bb_scale, float* raw_out, float* weights, float* rgb_map,
-                                                float* disp_map, float* acc_map, float* depth_map, void* stream) {
+                                                float* disp_map, float* acc_map, float* depth_map, void* workspace,
+                                                size_t workspace_bytes, void* stream) {
   SCADE_TRY(check_net(net, precision));
   if (N == 0) return SCADE_OK;
   SCADE_CHECK_ARG(rays && z_vals && bb_center_host && weights && N > 0 && S > 0 && ray_stride >= 11,
                   "mlp_forward_rays_composite: bad arguments");
   SCADE_CHECK_ARG((reinterpret_cast<uintptr_t>(raw_out) & 15) == 0, "mlp_forward_rays_composite: raw_out must be 16-byte aligned");
   if (!scade_mlp_forward_rays_composite_supported(&net->desc, precision, S)) {
-    set_error("mlp_forward_rays_composite: needs SCADE_PREC_TC_F16 and S in {64, 128, 256} (precision %d, S=%d)", precision, S);
+    set_error("mlp_forward_rays_composite: needs SCADE_PREC_TC_F16 and S a multiple of 32 (precision %d, S=%d)", precision, S);
     return SCADE_ERR_UNSUPPORTED;
   }
   MlpCompositeOut co{weights, rgb_map, disp_map, acc_map, depth_map};
-  return mlp_tc_forward(*net, rays, ray_stride, z_vals, nullptr, N, S, bb_center_host, bb_scale, raw_out, nullptr, 0, 0,
-                        as_stream(stream), false, &co);
+  return mlp_tc_forward(*net, rays, ray_stride, z_vals, nullptr, N, S, bb_center_host, bb_scale, raw_out, workspace,
+                        workspace_bytes, 0, as_stream(stream), false, &co);
 }
 
 extern "C" int scade_mlp_forward_embedded(const scade_net* net, int precision, const float* x, int64_t P, float* out,
@@ -242,7 +243,8 @@ extern "C" int scade_render_rays_forward(const scade_render_cfg* cfg, const floa
   if (scade_mlp_forward_rays_composite_supported(&coarse->desc, cfg->precision, Nc)) {
     // network + compositing in one kernel (raw never reaches memory), then importance sampling + sort-merge (RS:702-713)
     SCADE_TRY(scade_mlp_forward_rays_composite(coarse, cfg->precision, ray_batch, rs, z0, N, Nc, cfg->bb_center, cfg->bb_scale,
-                                               nullptr, w0, out->rgb0, out->disp0, out->acc0, out->depth0, stream));
+                                               nullptr, w0, out->rgb0, out->disp0, out->acc0, out->depth0, ws + L.mlp, L.mlp_bytes,
+                                               stream));
     SCADE_TRY(scade_resample_from_z(z0, w0, N, Nc, Nf, perturbed ? u_coarse : nullptr, cfg->is_joint, f(L.zs), nullptr, zf, nullptr,
                                     stream));
   } else {
@@ -255,7 +257,8 @@ extern "C" int scade_render_rays_forward(const scade_render_cfg* cfg, const floa
   // fine pass                                                                     RS:714-720
   if (scade_mlp_forward_rays_composite_supported(&fine->desc, cfg->precision, S)) {
     SCADE_TRY(scade_mlp_forward_rays_composite(fine, cfg->precision, ray_batch, rs, zf, N, S, cfg->bb_center, cfg->bb_scale,
-                                               out->raw, wf, out->rgb_map, out->disp_map, out->acc_map, out->depth_map, stream));
+                                               out->raw, wf, out->rgb_map, out->disp_map, out->acc_map, out->depth_map, ws + L.mlp,
+                                               L.mlp_bytes, stream));
     // depth hypotheses from the fine distribution (RS:723-730, 744)
     SCADE_TRY(scade_resample_from_z(zf, wf, N, S, Nf, perturbed ? u_fine : nullptr, cfg->is_joint, hyp, out->u, nullptr, out->z_std,
                                     stream));

@@ -44,8 +44,10 @@ struct MlpCompositeOut {
   float* acc_map;     // [N]   nullable
   float* depth_map;   // [N]   nullable
 };
-// ray-aligned sample counts the fused epilogue handles (a ray = 2, 4 or 8 whole warps inside one CTA's 256 points)
-inline bool mlp_tc_composite_supported(int S) { return S == 64 || S == 128 || S == 256; }
+// sample counts the fused epilogue handles: a ray is a whole number of 32-row warps
+inline bool mlp_tc_composite_supported(int S) { return S >= 32 && S % 32 == 0 && S <= 8192; }
+// whole rays inside a CTA's 256 points per step; any other supported S runs the kernel's chain mode
+inline bool mlp_tc_composite_strided(int S) { return S == 32 || S == 64 || S == 128 || S == 256; }
 
 // entry points implemented in mlp_tc.cu (tcgen05 path)
 bool mlp_tc_supported(const scade_net_desc& d);

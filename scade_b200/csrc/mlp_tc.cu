@@ -36,6 +36,7 @@
 #include <stdlib.h>
 
 #include <algorithm>
+#include <numeric>
 #include <type_traits>
 
 #include "composite.cuh"
@@ -68,11 +69,9 @@ constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;         // barriers + alignment
 constexpr int OFF_BIAS = OFF_BAR + 256;
 constexpr int FWD_SMEM_BYTES = OFF_BIAS + TILES * W * 4;
 static_assert(FWD_SMEM_BYTES <= 227 * 1024, "forward kernel shared memory exceeds the 227 KB per-CTA limit");
-// kComp (compositing fused into the views epilogue): per-chunk transmittance products of the CTA's 8 row-warps, and the
-// tile 0 -> tile 1 hand-over of a 256-sample ray (carry + 5 x 32 per-lane partial sums) in the last 768 bytes
-constexpr int OFF_COMP = FWD_SMEM_BYTES;
-constexpr int COMP_SMEM_BYTES = FWD_SMEM_BYTES + 768;      // s_prod[8] | carry (8 floats) | [5][32] partial sums = 704 B
-static_assert(COMP_SMEM_BYTES <= 227 * 1024, "kComp shared memory exceeds the 227 KB per-CTA limit");
+// kComp (compositing fused into the network kernel): the views epilogue parks each point's (rgb_raw, sigma) in a 4 KB
+// per-CTA slot of an L2-resident ring in the call's workspace; the CTA's compositor warp picks it up from there
+constexpr int COMP_RING_BYTES_PER_CTA = TILES * TILE_M * 16;
 
 enum ASrc : int { SRC_EMB = 4 };         // 0..3 = activation chunk c
 
@@ -171,8 +170,16 @@ __device__ __forceinline__ void sincos_reduced(float arg, float* s, float* c) {
 }
 
 // ---- the kernel ------------------------------------------------------------------------------------
-// Alpha compositing (compute_weights + raw2outputs, run_scade_scannet.py:511-562) fused into the views epilogue (kComp):
-// requires rays mode and S in {64, 128, 256} (a ray is then a whole number of 32-row warps inside one CTA's 256 points).
+// Alpha compositing (compute_weights + raw2outputs, run_scade_scannet.py:511-562) fused into the network kernel (kComp).
+// Rays mode, S a multiple of 32.  The views epilogue (the critical loop of the kernel: it co-limits the step with the tensor
+// pipe) only parks the point's four raw values; warp 2 of the CTA -- otherwise idle -- is the COMPOSITOR: it walks the CTA's
+// points in order, 32 samples of one ray at a time, with the running transmittance and the per-lane partial sums of the ray
+// in registers, exactly like the stand-alone composite_ray_fwd (composite.cuh): same device functions, same operation order,
+// bit-identical results.  It has a whole step (~58k cycles) for 8 chunks of ~1k cycles.
+//   S in {32, 64, 128, 256}: steps are strided over the clusters; a CTA's 256 points per step hold whole rays.
+//   any other S ("chain" mode, e.g. the 64 + 128 = 192 samples of the reference's config file): each CTA walks a CONTIGUOUS
+//   range of chain_iters * 256 points that starts and ends on a ray boundary, so a ray that straddles tiles or steps stays
+//   with one compositor.
 struct CompArgs {
   float* weights;                 // [N,S]
   float* rgb_map;                 // [N,3]  nullable
@@ -180,7 +187,8 @@ struct CompArgs {
   float* acc_map;                 // [N]    nullable
   float* depth_map;               // [N]    nullable
   int write_raw;                  // also store raw [N,S,4] (retraw)
-  int pad;
+  int chain_iters;                // 0: steps strided over the clusters; > 0: chain mode, steps per CTA
+  float4* ring;                   // [CTAs][256] hand-over slots (workspace)
 };
 
 struct FwdArgs {
@@ -473,6 +481,85 @@ __device__ __forceinline__ void feature_epilogue_tmem(uint32_t t_tile, int half,
 
 // kStash: additionally write every layer's fp16 output chunk (TMA bulk store of the shared-memory image the next layer's
 // MMAs read anyway), the ReLU sign masks and the alpha pre-activation to the training stash.
+// The compositor warp of the kComp kernel (see CompArgs).  Runs with the control warps' 32 registers: its loop is latency-
+// tolerant (one 32-sample chunk at a time, nothing batched).
+__device__ __noinline__ void pp_compositor(const FwdArgs& a, uint32_t bar_raw, uint32_t cta_rank, int64_t unit0, int64_t n_steps,
+                                           int64_t n_units, int lane) {
+  const int S = a.S;
+  const int64_t cta = 2 * unit0 + cta_rank;
+  const float4* slot = a.comp.ring + cta * (int64_t)(TILES * TILE_M) + lane;
+  float carry = 1.0f, norm = 0.f, sr = 0.f, sg = 0.f, sb = 0.f, sdepth = 0.f, sacc = 0.f;
+  int it = 0;
+  for (int64_t step = unit0; step < n_steps; step += n_units, ++it) {
+    const int64_t base = (a.comp.chain_iters > 0 ? cta * (int64_t)a.comp.chain_iters + it : 2 * step + cta_rank) * (int64_t)(TILES * TILE_M);
+    for (int tile = 0; tile < TILES; ++tile) {
+      int64_t p = base + tile * TILE_M + lane;                          // a chunk is wholly live or wholly dead: 32 | S | P
+      const bool tile_live = p < a.P;
+      int64_t r = 0;
+      int i = 0;                                                        // sample index within the ray
+      float zi = 0.f, zn = 0.f;
+      if (tile_live) {                                                  // (z does not depend on the network: fetched before the wait)
+        r = a.P < (int64_t)0x7fffffff ? (int64_t)((uint32_t)p / (uint32_t)S) : p / S;
+        i = (int)(p - r * S);
+        zi = a.z[p];
+        zn = (i + 1 < S) ? a.z[p + 1] : zi;
+      }
+      mbar_wait(bar_raw + 8 * tile, (uint32_t)it & 1u);
+      if (tile_live) {
+        const float4* src = slot + tile * TILE_M;
+        float4 rw = __ldcg(src);
+        for (int q = 0; q < 4; ++q) {
+          // the next chunk's operands are requested before this chunk's arithmetic
+          const bool more = q < 3 && p + 32 < a.P;
+          const int i_n = (i + 32 - lane == S) ? lane : i + 32;
+          float4 rw_n = rw;
+          float zi_n = 0.f, zn_n = 0.f;
+          if (more) {
+            rw_n = __ldcg(src + (q + 1) * 32);
+            zi_n = a.z[p + 32];
+            zn_n = (i_n + 1 < S) ? a.z[p + 33] : zi_n;
+          }
+          if (i == lane) {                                              // first chunk of a ray (RS:516)
+            const float* rd = a.rays + r * a.ray_stride + 3;
+            const float dx = rd[0], dy = rd[1], dz = rd[2];
+            norm = sqrtf(dx * dx + dy * dy + dz * dz);
+            carry = 1.0f; sr = 0.f; sg = 0.f; sb = 0.f; sdepth = 0.f; sacc = 0.f;
+          }
+          const SampleTerms t = sample_terms(rw.w, 0.f, zi, zn, i == S - 1, norm);
+          const float incl = warp_scan_prod(t.tfac, lane);
+          float excl = __shfl_up_sync(FULL, incl, 1);
+          if (lane == 0) excl = 1.0f;
+          const float w = t.alpha * (carry * excl);
+          carry *= __shfl_sync(FULL, incl, 31);
+          a.comp.weights[p] = w;
+          sr = fmaf(w, sigmoidf_(rw.x), sr);                            // RS:543, RS:556
+          sg = fmaf(w, sigmoidf_(rw.y), sg);
+          sb = fmaf(w, sigmoidf_(rw.z), sb);
+          sdepth = fmaf(w, zi, sdepth);                                 // RS:558
+          sacc += w;                                                    // RS:560
+          if (i_n == lane) {                                            // that was the last chunk of the ray
+            const float tr = warp_sum(sr), tg = warp_sum(sg), tb = warp_sum(sb), td = warp_sum(sdepth), ta = warp_sum(sacc);
+            if (lane == 0) {
+              if (a.comp.rgb_map) { a.comp.rgb_map[r * 3] = tr; a.comp.rgb_map[r * 3 + 1] = tg; a.comp.rgb_map[r * 3 + 2] = tb; }
+              if (a.comp.depth_map) a.comp.depth_map[r] = td;
+              if (a.comp.acc_map) a.comp.acc_map[r] = ta;
+              if (a.comp.disp_map) {
+                const float qd = td / ta;                               // RS:559; torch.max propagates the nan of 0/0
+                a.comp.disp_map[r] = (qd != qd) ? qd : 1.0f / fmaxf(1e-10f, qd);
+              }
+            }
+            ++r;
+          }
+          if (!more) break;
+          rw = rw_n; zi = zi_n; zn = zn_n; i = i_n; p += 32;
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_raw + 16 + 8 * tile);              // the slot may be overwritten
+    }
+  }
+}
+
 template <bool kStash, bool kComp = false>
 __global__ void __launch_bounds__(PP_THREADS, 1) nerf_mlp_tc_pp_kernel(const __grid_constant__ FwdArgs a,
                                                                        const __grid_constant__ NetPlan plan,
@@ -488,7 +575,8 @@ __global__ void __launch_bounds__(PP_THREADS, 1) nerf_mlp_tc_pp_kernel(const __g
   const int64_t n_steps = (a.n_pairs + 1) / 2;
 
   const uint32_t bar_full = sbase + OFF_BAR, bar_empty = bar_full + 8 * NUM_STAGES;
-  const uint32_t bar_acc = bar_empty + 16 * NUM_STAGES, bar_aready = bar_acc + 16;     // (8 * NUM_STAGES bytes after bar_empty are unused)
+  const uint32_t bar_acc = bar_empty + 16 * NUM_STAGES, bar_aready = bar_acc + 16;
+  const uint32_t bar_raw = bar_empty + 8 * NUM_STAGES;   // kComp: [tile] raw values parked, [2 + tile] slot read (4 x 8 B, else unused)
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + OFF_BAR + 8 * (3 * NUM_STAGES + 4));
 
   if (threadIdx.x == 0) {
@@ -499,6 +587,10 @@ __global__ void __launch_bounds__(PP_THREADS, 1) nerf_mlp_tc_pp_kernel(const __g
     for (int t = 0; t < 2; ++t) {
       mbar_init(bar_acc + 8 * t, 1);
       mbar_init(bar_aready + 8 * t, PP_EPI_WARPS);      // 8 local + 8 remote epilogue warps per super-tile
+      if (kComp) {
+        mbar_init(bar_raw + 8 * t, 4);                  // the tile's four column-half-0 warps
+        mbar_init(bar_raw + 16 + 8 * t, 1);             // the compositor
+      }
     }
     fence_barrier_init();
   }
@@ -515,6 +607,8 @@ __global__ void __launch_bounds__(PP_THREADS, 1) nerf_mlp_tc_pp_kernel(const __g
       if (lane == 0) pp_weight_producer(plan, &tmap, sbase, bar_full, bar_empty, cta_rank, unit0, n_steps, n_units);
     } else if (warp == 1) {
       if (cta_rank == 0) pp_mma_issuer(plan, sbase, tmem_base, bar_full, bar_empty, bar_acc, bar_aready, unit0, n_steps, n_units, a.dbg);
+    } else if (kComp && warp == 2) {
+      pp_compositor(a, bar_raw, cta_rank, unit0, n_steps, n_units, lane);
     }
   } else {
     // ================= prologue / epilogue warps: thread == one row x 128 columns =================
@@ -547,12 +641,17 @@ __global__ void __launch_bounds__(PP_THREADS, 1) nerf_mlp_tc_pp_kernel(const __g
       }
     };
     // global point index of this thread's row in step `step`
-    auto point_of = [&](int64_t step) { return (2 * step + cta_rank) * (int64_t)(TILES * TILE_M) + tile * TILE_M + row; };
+    // (`it` = how many steps this cluster has done before `step`)
+    auto point_of = [&](int64_t step, int it) {
+      if (kComp && a.comp.chain_iters > 0)               // chain mode: this CTA's own contiguous range, one step after the other
+        return ((2 * unit0 + cta_rank) * (int64_t)a.comp.chain_iters + it) * (int64_t)(TILES * TILE_M) + tile * TILE_M + row;
+      return (2 * step + cta_rank) * (int64_t)(TILES * TILE_M) + tile * TILE_M + row;
+    };
 
     // ---- positional encoding of this thread's 32 encoding-chunk columns [32*half, 32*half + 32) for step `step`, as 16 packed
     //      fp16 pairs.  Computed one layer early (while the views layer's MMAs run) and stored once those MMAs have retired.
-    auto encode = [&](int64_t step, uint32_t (&pk)[16], float (&vd)[3]) {
-      const int64_t p_raw = point_of(step);
+    auto encode = [&](int64_t step, int it, uint32_t (&pk)[16], float (&vd)[3]) {
+      const int64_t p_raw = point_of(step, it);
       const int64_t p = p_raw < a.P ? p_raw : a.P - 1;
       float v[32];
 #pragma unroll
@@ -628,14 +727,15 @@ __global__ void __launch_bounds__(PP_THREADS, 1) nerf_mlp_tc_pp_kernel(const __g
       TRACE(tr, 0x400);                                  // epilogue warp: first prologue begins
       uint32_t pk[16];
       float vd[3];
-      encode(unit0, pk, vd);
+      encode(unit0, 0, pk, vd);
       store_emb(pk, vd);
       signal_a_ready();
       TRACE(tr, 0x401);                                  // prologue done, operand signalled
     }
 
-    for (int64_t step = unit0; step < n_steps; step += n_units) {
-      const int64_t p_raw = point_of(step);
+    int it = 0;
+    for (int64_t step = unit0; step < n_steps; step += n_units, ++it) {
+      const int64_t p_raw = point_of(step, it);
       const bool live = p_raw < a.P;
       const int64_t tile_g = 2 * (2 * step + cta_rank) + tile;            // 128-point tile index in the stash
 
@@ -710,7 +810,7 @@ __global__ void __launch_bounds__(PP_THREADS, 1) nerf_mlp_tc_pp_kernel(const __g
           const bool has_next = next < n_steps;
           uint32_t pk[16];
           float vd[3];
-          if (has_next) encode(next, pk, vd);
+          if (has_next) encode(next, it + 1, pk, vd);
           // rgb_linear's weights (3 x 128 fp32) are staged by one warp of the tile in activation chunk 3, which is dead once
           // this layer's MMAs have retired
           const bool stager = (half == 1 && quarter == 0);
@@ -718,17 +818,6 @@ __global__ void __launch_bounds__(PP_THREADS, 1) nerf_mlp_tc_pp_kernel(const __g
           if (stager) {
 #pragma unroll
             for (int i = 0; i < 3; ++i) wst[i] = __ldg(reinterpret_cast<const float4*>(&tail->w_rgb_p[0][0]) + i * 32 + lane);
-          }
-          // kComp: this sample's z, its successor's and the ray's direction norm, fetched under the MMAs (RS:514-516)
-          float c_z = 0.f, c_zn = 0.f, c_norm = 0.f;
-          if (kComp && half == 0) {
-            const int64_t pc = live ? p_raw : 0;
-            const int si = (int)(pc & (int64_t)(a.S - 1));
-            c_z = a.z[pc];
-            c_zn = (si + 1 < a.S) ? a.z[pc + 1] : c_z;
-            const float* rd = a.rays + (pc / a.S) * a.ray_stride + 3;
-            const float dx = rd[0], dy = rd[1], dz = rd[2];
-            c_norm = sqrtf(dx * dx + dy * dy + dz * dz);
           }
           mbar_wait(my_acc, acc_phase);
           acc_phase ^= 1;
@@ -814,76 +903,11 @@ __global__ void __launch_bounds__(PP_THREADS, 1) nerf_mlp_tc_pp_kernel(const __g
             if (live && (!kComp || a.comp.write_raw)) a.out[p_raw] = rawv;
             if (kStash) reinterpret_cast<float*>(sa.ws + sa.L.alpha)[tile_g * TILE_M + row] = al;
             if (kComp) {
-              // ---- compute_weights + raw2outputs (RS:511-562) on the rows of this tile: warp == 32 consecutive samples of one ray.
-              // Same device functions, same operation order as composite_ray_fwd (composite.cuh): bit-identical results.
-              const int S = a.S, cpr = S >> 5;                   // chunks (warps) per ray: 2, 4 or 8
-              const int cc = tile * 4 + quarter;                 // this warp's chunk among the CTA's 256 points
-              const int cl = cc & (cpr - 1);                     // ... and within its ray
-              const int nch = cpr < 4 ? cpr : 4;                 // chunks of a ray inside one tile
-              const int clt = cl & 3;                            // chunk within the ray's part of this tile
-              float* s_prod = reinterpret_cast<float*>(smem + OFF_COMP);             // [8]
-              float* s_hand = s_prod + 8;                                            // [0] carry, [8 + 32 k + lane] per-lane partial sums (k < 5): 704 B in all
-              float* s_terms = reinterpret_cast<float*>(a_tile + CHUNK_BYTES);      // [4 warps][5][32] in the tile's dead chunk 1
-              const int comp_bar = 11 + tile, x_bar = 13;
-              const int si = (int)(p_raw & (int64_t)(S - 1));
-              const SampleTerms t = sample_terms(rawv.w, 0.f, c_z, c_zn, si == S - 1, c_norm);
-              const float tf = live ? t.tfac : 1.0f;
-              const float incl = warp_scan_prod(tf, lane);
-              float excl = __shfl_up_sync(FULL, incl, 1);
-              if (lane == 0) excl = 1.0f;
-              const float pwarp = __shfl_sync(FULL, incl, 31);
-              if (lane == 0) s_prod[cc] = pwarp;
-              named_bar_sync(comp_bar, 128);
-              float carry = 1.0f;
-              if (cpr == 8 && tile == 1) {                       // 256-sample ray: tile 0 holds its first four chunks
-                named_bar_sync(x_bar, 160);
-                carry = s_hand[0];
-              }
-              for (int k = 0; k < clt; ++k) carry *= s_prod[cc - clt + k];
-              const float w = live ? t.alpha * (carry * excl) : 0.f;
-              if (live) a.comp.weights[p_raw] = w;
-              float* st = s_terms + quarter * 160;
-              st[lane] = w;
-              st[32 + lane] = sigmoidf_(rawv.x);                 // RS:543
-              st[64 + lane] = sigmoidf_(rawv.y);
-              st[96 + lane] = sigmoidf_(rawv.z);
-              st[128 + lane] = c_z;
-              named_bar_sync(comp_bar, 128);
-              if (clt == nch - 1) {                              // the warp holding the ray's last chunk in this tile sums the ray
-                float sr = 0.f, sg = 0.f, sb = 0.f, sdepth = 0.f, sacc = 0.f;
-                if (cpr == 8 && tile == 1) {
-                  sr = s_hand[8 + lane]; sg = s_hand[40 + lane]; sb = s_hand[72 + lane];
-                  sdepth = s_hand[104 + lane]; sacc = s_hand[136 + lane];
-                }
-                for (int k = 0; k < nch; ++k) {
-                  const float* q = s_terms + (quarter - (nch - 1) + k) * 160;
-                  const float wk = q[lane];
-                  sr = fmaf(wk, q[32 + lane], sr);               // RS:556
-                  sg = fmaf(wk, q[64 + lane], sg);
-                  sb = fmaf(wk, q[96 + lane], sb);
-                  sdepth = fmaf(wk, q[128 + lane], sdepth);      // RS:558
-                  sacc += wk;                                    // RS:560
-                }
-                if (cpr == 8 && tile == 0) {
-                  if (lane == 0) s_hand[0] = carry * pwarp;      // ((p0 p1) p2) p3
-                  s_hand[8 + lane] = sr; s_hand[40 + lane] = sg; s_hand[72 + lane] = sb;
-                  s_hand[104 + lane] = sdepth; s_hand[136 + lane] = sacc;
-                  __threadfence_block();
-                  named_bar_arrive(x_bar, 160);
-                } else {
-                  sr = warp_sum(sr); sg = warp_sum(sg); sb = warp_sum(sb); sdepth = warp_sum(sdepth); sacc = warp_sum(sacc);
-                  if (lane == 0 && live) {
-                    const int64_t r = p_raw / S;
-                    if (a.comp.rgb_map) { a.comp.rgb_map[r * 3] = sr; a.comp.rgb_map[r * 3 + 1] = sg; a.comp.rgb_map[r * 3 + 2] = sb; }
-                    if (a.comp.depth_map) a.comp.depth_map[r] = sdepth;
-                    if (a.comp.acc_map) a.comp.acc_map[r] = sacc;
-                    if (a.comp.disp_map) {
-                      const float q = sdepth / sacc;             // RS:559; torch.max propagates the nan of 0/0
-                      a.comp.disp_map[r] = (q != q) ? q : 1.0f / fmaxf(1e-10f, q);
-                    }
-                  }
-                }
-              }
+              // hand the point to the compositor warp: slot free (it has read the previous step's values) -> store -> signal
+              if (it > 0) mbar_wait(bar_raw + 16 + 8 * tile, (uint32_t)(it - 1) & 1u);
+              a.comp.ring[(2 * unit0 + cta_rank) * (int64_t)(TILES * TILE_M) + tile * TILE_M + row] = rawv;
+              __syncwarp();
+              if (lane == 0) mbar_arrive(bar_raw + 8 * tile);
             }
           }
           if (kStash) {
@@ -1192,7 +1216,7 @@ static int set_kernel_attributes() {
   if (dev >= 0 && dev < 64 && done[dev]) return SCADE_OK;
   SCADE_CUDA(cudaFuncSetAttribute(nerf_mlp_tc_pp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM_BYTES));
   SCADE_CUDA(cudaFuncSetAttribute(nerf_mlp_tc_pp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM_BYTES));
-  SCADE_CUDA(cudaFuncSetAttribute(nerf_mlp_tc_pp_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, COMP_SMEM_BYTES));
+  SCADE_CUDA(cudaFuncSetAttribute(nerf_mlp_tc_pp_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM_BYTES));
   SCADE_CUDA(cudaFuncSetAttribute(nerf_mlp_tc_x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM_BYTES));
   SCADE_CUDA(cudaFuncSetAttribute(nerf_mlp_tc_dgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
   SCADE_CUDA(cudaFuncSetAttribute(nerf_mlp_tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM_BYTES));
@@ -1248,7 +1272,8 @@ int mlp_tc_pack(const scade_net& net, void* packed_out, cudaStream_t st, bool x3
 }
 
 size_t mlp_tc_workspace_bytes(const scade_net_desc& d, int64_t P, int save) {
-  return save ? (size_t)tc::train_layout(d, P).total : 256;
+  // without a stash: the hand-over ring of the fused compositing (one 4 KB slot per CTA; sized for any device)
+  return save ? (size_t)tc::train_layout(d, P).total : (size_t)256 * tc::COMP_RING_BYTES_PER_CTA;
 }
 
 int mlp_tc_stash_layout(const scade_net_desc& d, int64_t P, int64_t* out, int n) {
@@ -1268,7 +1293,7 @@ int mlp_tc_forward(const scade_net& net, const float* rays, int ray_stride, cons
                    int64_t N, int S, const float* bb_center, float bb_scale, float* raw_out, void* workspace,
                    size_t ws_bytes, int save, cudaStream_t st, bool x3, const MlpCompositeOut* comp) {
   if (comp != nullptr && (x3 || save || rays == nullptr || !mlp_tc_composite_supported(S) || comp->weights == nullptr)) {
-    set_error("mlp_forward: fused compositing needs SCADE_PREC_TC_F16 without save_for_backward, rays mode and S in {64,128,256} (S=%d)", S);
+    set_error("mlp_forward: fused compositing needs SCADE_PREC_TC_F16 without save_for_backward, rays mode and S a multiple of 32 (S=%d)", S);
     return SCADE_ERR_UNSUPPORTED;
   }
   if (x3 && save) {
@@ -1296,6 +1321,13 @@ int mlp_tc_forward(const scade_net& net, const float* rays, int ray_stride, cons
     a.comp.weights = comp->weights; a.comp.rgb_map = comp->rgb_map; a.comp.disp_map = comp->disp_map;
     a.comp.acc_map = comp->acc_map; a.comp.depth_map = comp->depth_map;
     a.comp.write_raw = raw_out != nullptr;
+    const size_t ring_bytes = (size_t)num_sms() * tc::COMP_RING_BYTES_PER_CTA;
+    if (workspace == nullptr || ws_bytes < ring_bytes || (reinterpret_cast<uintptr_t>(workspace) & 15)) {
+      set_error("mlp_forward (fused compositing): needs a 16-byte aligned workspace of %zu bytes (scade_mlp_workspace_bytes), got %zu",
+                ring_bytes, ws_bytes);
+      return SCADE_ERR_WORKSPACE;
+    }
+    a.comp.ring = reinterpret_cast<float4*>(workspace);
   }
 #if SCADE_TC_TRACE
   { const char* e = getenv("SCADE_TC_DBG"); a.dbg = e ? atoi(e) : 0; }
@@ -1324,11 +1356,21 @@ int mlp_tc_forward(const scade_net& net, const float* rays, int ray_stride, cons
     SCADE_LAUNCH_CHECK();
     return SCADE_OK;
   }
-  const int64_t n_steps = (a.n_pairs + 1) / 2;
-  const int clusters = (int)std::min<int64_t>(n_steps, num_sms() / 2);
+  int64_t n_steps = (a.n_pairs + 1) / 2;
+  int clusters = (int)std::min<int64_t>(n_steps, num_sms() / 2);
+  if (comp != nullptr && !mlp_tc_composite_strided(S)) {
+    // chain mode (CompArgs): every CTA walks chain_iters consecutive 256-point steps; ranges start and end on ray boundaries
+    const int64_t cta_steps = a.n_pairs;                              // 256-point steps in all
+    const int64_t period = S / std::gcd(S, tc::TILES * tc::TILE_M);  // steps after which a range is on a ray boundary again
+    const int64_t iters = ceil_div<int64_t>(ceil_div<int64_t>(cta_steps, 2 * (num_sms() / 2)), period) * period;
+    clusters = (int)ceil_div<int64_t>(cta_steps, 2 * iters);
+    a.comp.chain_iters = (int)iters;
+    a.n_pairs = 2 * iters * clusters;                                 // every cluster runs exactly `iters` steps
+    n_steps = iters * clusters;
+  }
   void* args[] = {&a, &plan, &tmap, &sa};
   if (comp != nullptr)
-    SCADE_TRY(tc::launch_pair((const void*)tc::nerf_mlp_tc_pp_kernel<false, true>, clusters, tc::PP_THREADS, tc::COMP_SMEM_BYTES, st, args));
+    SCADE_TRY(tc::launch_pair((const void*)tc::nerf_mlp_tc_pp_kernel<false, true>, clusters, tc::PP_THREADS, tc::FWD_SMEM_BYTES, st, args));
   else
     SCADE_TRY(tc::launch_pair(save ? (const void*)tc::nerf_mlp_tc_pp_kernel<true> : (const void*)tc::nerf_mlp_tc_pp_kernel<false>,
                               clusters, tc::PP_THREADS, tc::FWD_SMEM_BYTES, st, args));

@@ -248,8 +248,8 @@ def composite_fusable(handle, precision, S):
 
 
 def mlp_forward_rays_composite(handle, rays, z_vals, bb_center, bb_scale, precision=PREC_TC_F16, retraw=False):
-    """run_network + raw2outputs (RS:659-660 / RS:718-720) as one kernel (no autograd): the alpha compositing runs in the
-    epilogue of the last tensor-core layer.  Returns (rgb_map, disp_map, acc_map, weights, depth_map, raw or None)."""
+    """run_network + raw2outputs (RS:659-660 / RS:718-720) as one kernel (no autograd): the alpha compositing runs on a
+    compositor warp of the tensor-core kernel, fed by the epilogue of its last layer.  Returns (rgb_map, disp_map, acc_map, weights, depth_map, raw or None)."""
     precision = PRECISIONS[precision]
     rays, z_vals = f32(rays), f32(z_vals)
     N, S = z_vals.shape
@@ -259,9 +259,10 @@ def mlp_forward_rays_composite(handle, rays, z_vals, bb_center, bb_scale, precis
     w = torch.empty((N, S), dtype=torch.float32, device=dev)
     raw = torch.empty((N, S, 4), dtype=torch.float32, device=dev) if retraw else None
     net = handle.struct(precision)
+    ws = torch.empty(handle.workspace_bytes(N * S, precision, 0), dtype=torch.uint8, device=dev)
     check(_L().scade_mlp_forward_rays_composite(byref(net), precision, ptr(rays), rays.shape[1], ptr(z_vals), N, S,
                                                 _lib.host_floats([float(c) for c in bb_center]), float(bb_scale), ptr(raw), ptr(w),
-                                                ptr(rgb), ptr(disp), ptr(acc), ptr(depth), stream_ptr()),
+                                                ptr(rgb), ptr(disp), ptr(acc), ptr(depth), ptr(ws), ws.numel(), stream_ptr()),
           "scade_mlp_forward_rays_composite")
     return rgb, disp, acc, w, depth, raw
 

@@ -228,18 +228,21 @@ def test_mlp_x3_vs_oracle(dev, P):
         assert dr.max() <= 1e-3
 
 
-@pytest.mark.parametrize("S,N", [(64, 37), (128, 19), (256, 5), (256, 300), (128, 1)])
+@pytest.mark.parametrize("S,N", [(64, 37), (128, 19), (256, 5), (256, 300), (128, 1), (32, 77),
+                                 (192, 1), (192, 5), (192, 4096), (192, 1237), (96, 50), (320, 9), (512, 3), (224, 611)])
 def test_fused_compositing_is_bit_identical(dev, S, N):
     """north_star: the cumprod alpha-composite fused into the epilogue of the last GEMM.  scade_mlp_forward_rays_composite
     (one kernel: raw never reaches memory) against scade_mlp_forward_rays + scade_raw2outputs (RS:659-660, RS:511-562):
-    every output bit-identical, for 2, 4 and 8 warps per ray, ragged last tiles and retraw on / off."""
+    every output bit-identical, for 1, 2, 4 and 8 warps per ray (whole rays per 256-point step), for the sample counts that
+    straddle tiles and steps (192 = the reference config's 64 + 128, 96, 224, 320, 512: the kernel's chain mode), ragged last
+    tiles and ranges, and retraw on / off."""
     from scade_b200 import functional as F_, nerf_helpers as NH
     params = syn.make_nerf_params(seed=11, D=8, W=256, bias_scale=0.05, alpha_bias=0.5, weight_gain=1.3)
     net = NH.NeRF(D=8, W=256, input_ch=57, input_ch_views=3, output_ch=5, skips=[4], use_viewdirs=True, precision="tc_f16")
     net.load_state_dict({k: torch.from_numpy(v) for k, v in params.items()})
     net = net.to(dev).requires_grad_(False)
     h = net.handle()
-    assert F_.composite_fusable(h, "tc_f16", S) and not F_.composite_fusable(h, "tc_f16", 192) and not F_.composite_fusable(h, "fp32", S)
+    assert F_.composite_fusable(h, "tc_f16", S) and not F_.composite_fusable(h, "tc_f16", 200) and not F_.composite_fusable(h, "fp32", S)
     bb_center, bb_scale = syn.bounding_box()
     rb = T(syn.make_ray_batch(N, seed=60 + S), dev)
     rng = np.random.default_rng(S + N)

@@ -26,7 +26,7 @@ def test_library_loads_and_exports_every_symbol():
     lib = _lib.load()
     for name in header_symbols():
         assert hasattr(lib, name), name
-    assert lib.scade_version() == 101
+    assert lib.scade_version() == 102
 
 
 def test_argument_validation_without_gpu():

@@ -1,5 +1,6 @@
 """Small eval + train invocations of every kernel family for `compute-sanitizer --tool memcheck` (run on a B200):
-fast tensor-core forward with and without the fused compositing (64 / 128 / 256 samples per ray), the tight mode, the
+fast tensor-core forward with the fused compositing (64 / 128 / 256 samples per ray, and 192 / 96: chain mode) and without
+(64 samples: not a multiple of 32), the tight mode, the
 stand-alone per-ray kernels, one tensor-core train step through the flat-storage loss heads, and the f4 / loss entry points."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -27,7 +28,8 @@ def kwargs(prec, Nc, Nf, perturb=0.0, grad=False):
 
 rb = torch.from_numpy(syn.make_ray_batch(77, seed=3)).to(dev)
 with torch.no_grad():
-    for prec, Nc, Nf in (("tc_f16", 24, 40), ("tc_f16", 64, 64), ("tc_f16", 128, 128), ("tc_f16x3", 64, 64), ("fp32", 16, 16)):
+    for prec, Nc, Nf in (("tc_f16", 24, 40), ("tc_f16", 64, 64), ("tc_f16", 128, 128), ("tc_f16", 64, 128), ("tc_f16", 32, 64),
+                         ("tc_f16x3", 64, 64), ("fp32", 16, 16)):
         out = R_.render_rays(rb, True, **kwargs(prec, Nc, Nf))
         torch.cuda.synchronize()
         print(f"eval {prec} {Nc}c+{Nf}f ok", float(out["rgb_map"].sum()))
