@@ -71,7 +71,7 @@ constexpr int FWD_SMEM_BYTES = OFF_BIAS + TILES * W * 4;
 static_assert(FWD_SMEM_BYTES <= 227 * 1024, "forward kernel shared memory exceeds the 227 KB per-CTA limit");
 // kComp (compositing fused into the network kernel): the views epilogue parks each point's (rgb_raw, sigma) in a 4 KB
 // per-CTA slot of an L2-resident ring in the call's workspace; the CTA's compositor warp picks it up from there
-constexpr int COMP_RING_BYTES_PER_CTA = TILES * TILE_M * 16;
+constexpr int COMP_RING_BYTES_PER_CTA = TILES * TILE_M * (16 + 4);   // [256] float4, then [256] float (last step only)
 
 enum ASrc : int { SRC_EMB = 4 };         // 0..3 = activation chunk c
 
@@ -188,7 +188,7 @@ struct CompArgs {
   float* depth_map;               // [N]    nullable
   int write_raw;                  // also store raw [N,S,4] (retraw)
   int chain_iters;                // 0: steps strided over the clusters; > 0: chain mode, steps per CTA
-  float4* ring;                   // [CTAs][256] hand-over slots (workspace)
+  uint8_t* ring;                  // [CTAs][COMP_RING_BYTES_PER_CTA] hand-over slots (workspace)
 };
 
 struct FwdArgs {
@@ -201,7 +201,8 @@ struct FwdArgs {
   float4* out;
   int64_t n_pairs;
   int dbg;              // trace build only -- timing ablations (results are WRONG when set): 1 = ignore weight arrival,
-                        // 2 = ignore operand readiness, 32 = no epilogue work
+                        // 2 = ignore operand readiness, 32 = no epilogue work, 64 = compositor: hand-shake only,
+                        // 128 = no compositor and no parking at all
   CompArgs comp;        // kComp only
 };
 
@@ -482,16 +483,21 @@ __device__ __forceinline__ void feature_epilogue_tmem(uint32_t t_tile, int half,
 // kStash: additionally write every layer's fp16 output chunk (TMA bulk store of the shared-memory image the next layer's
 // MMAs read anyway), the ReLU sign masks and the alpha pre-activation to the training stash.
 // The compositor warp of the kComp kernel (see CompArgs).  Runs with the control warps' 32 registers: its loop is latency-
-// tolerant (one 32-sample chunk at a time, nothing batched).
+// tolerant (one 32-sample chunk at a time, the next chunk's loads in flight).  In the CTA's LAST step nothing is left to hide
+// its ~3k cycles per chunk behind, so there the epilogue threads evaluate the per-sample terms themselves (in parallel, ~300
+// cycles once per launch) and park (sigmoid(rgb), alpha | 1 - alpha + 1e-10); the compositor is left with the scan and the sums.
 __device__ __noinline__ void pp_compositor(const FwdArgs& a, uint32_t bar_raw, uint32_t cta_rank, int64_t unit0, int64_t n_steps,
                                            int64_t n_units, int lane) {
   const int S = a.S;
   const int64_t cta = 2 * unit0 + cta_rank;
-  const float4* slot = a.comp.ring + cta * (int64_t)(TILES * TILE_M) + lane;
+  const float4* slot = reinterpret_cast<const float4*>(a.comp.ring + cta * COMP_RING_BYTES_PER_CTA) + lane;
+  const float* slot_tf = reinterpret_cast<const float*>(a.comp.ring + cta * COMP_RING_BYTES_PER_CTA + TILES * TILE_M * 16) + lane;
   float carry = 1.0f, norm = 0.f, sr = 0.f, sg = 0.f, sb = 0.f, sdepth = 0.f, sacc = 0.f;
   int it = 0;
+  [[maybe_unused]] Tracer tr;
   for (int64_t step = unit0; step < n_steps; step += n_units, ++it) {
     const int64_t base = (a.comp.chain_iters > 0 ? cta * (int64_t)a.comp.chain_iters + it : 2 * step + cta_rank) * (int64_t)(TILES * TILE_M);
+    const bool light = step + n_units >= n_steps;                       // last step: the terms arrive evaluated
     for (int tile = 0; tile < TILES; ++tile) {
       int64_t p = base + tile * TILE_M + lane;                          // a chunk is wholly live or wholly dead: 32 | S | P
       const bool tile_live = p < a.P;
@@ -504,37 +510,56 @@ __device__ __noinline__ void pp_compositor(const FwdArgs& a, uint32_t bar_raw, u
         zi = a.z[p];
         zn = (i + 1 < S) ? a.z[p + 1] : zi;
       }
+      TRACE(tr, 0x800 + tile);                                          // compositor: waits for the tile's values
       mbar_wait(bar_raw + 8 * tile, (uint32_t)it & 1u);
+      TRACE(tr, 0x900 + tile);                                          // ... parked
+#if SCADE_TC_TRACE
+      if (a.dbg & 64) {                                                 // timing ablation: hand-shake only
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_raw + 16 + 8 * tile);
+        continue;
+      }
+#endif
       if (tile_live) {
         const float4* src = slot + tile * TILE_M;
+        const float* src_tf = slot_tf + tile * TILE_M;
         float4 rw = __ldcg(src);
+        float tf = light ? __ldcg(src_tf) : 0.f;
         for (int q = 0; q < 4; ++q) {
           // the next chunk's operands are requested before this chunk's arithmetic
           const bool more = q < 3 && p + 32 < a.P;
           const int i_n = (i + 32 - lane == S) ? lane : i + 32;
           float4 rw_n = rw;
-          float zi_n = 0.f, zn_n = 0.f;
+          float zi_n = 0.f, zn_n = 0.f, tf_n = 0.f;
           if (more) {
             rw_n = __ldcg(src + (q + 1) * 32);
             zi_n = a.z[p + 32];
-            zn_n = (i_n + 1 < S) ? a.z[p + 33] : zi_n;
+            if (light) tf_n = __ldcg(src_tf + (q + 1) * 32);
+            else zn_n = (i_n + 1 < S) ? a.z[p + 33] : zi_n;
           }
-          if (i == lane) {                                              // first chunk of a ray (RS:516)
-            const float* rd = a.rays + r * a.ray_stride + 3;
-            const float dx = rd[0], dy = rd[1], dz = rd[2];
-            norm = sqrtf(dx * dx + dy * dy + dz * dz);
+          if (i == lane) {                                              // first chunk of a ray
             carry = 1.0f; sr = 0.f; sg = 0.f; sb = 0.f; sdepth = 0.f; sacc = 0.f;
+            if (!light) {                                               // RS:516
+              const float* rd = a.rays + r * a.ray_stride + 3;
+              const float dx = rd[0], dy = rd[1], dz = rd[2];
+              norm = sqrtf(dx * dx + dy * dy + dz * dz);
+            }
           }
-          const SampleTerms t = sample_terms(rw.w, 0.f, zi, zn, i == S - 1, norm);
-          const float incl = warp_scan_prod(t.tfac, lane);
+          float al = rw.w, cr = rw.x, cg = rw.y, cb = rw.z;
+          if (!light) {
+            const SampleTerms t = sample_terms(rw.w, 0.f, zi, zn, i == S - 1, norm);
+            al = t.alpha; tf = t.tfac;
+            cr = sigmoidf_(rw.x); cg = sigmoidf_(rw.y); cb = sigmoidf_(rw.z);   // RS:543
+          }
+          const float incl = warp_scan_prod(tf, lane);
           float excl = __shfl_up_sync(FULL, incl, 1);
           if (lane == 0) excl = 1.0f;
-          const float w = t.alpha * (carry * excl);
+          const float w = al * (carry * excl);
           carry *= __shfl_sync(FULL, incl, 31);
           a.comp.weights[p] = w;
-          sr = fmaf(w, sigmoidf_(rw.x), sr);                            // RS:543, RS:556
-          sg = fmaf(w, sigmoidf_(rw.y), sg);
-          sb = fmaf(w, sigmoidf_(rw.z), sb);
+          sr = fmaf(w, cr, sr);                                         // RS:556
+          sg = fmaf(w, cg, sg);
+          sb = fmaf(w, cb, sb);
           sdepth = fmaf(w, zi, sdepth);                                 // RS:558
           sacc += w;                                                    // RS:560
           if (i_n == lane) {                                            // that was the last chunk of the ray
@@ -551,11 +576,12 @@ __device__ __noinline__ void pp_compositor(const FwdArgs& a, uint32_t bar_raw, u
             ++r;
           }
           if (!more) break;
-          rw = rw_n; zi = zi_n; zn = zn_n; i = i_n; p += 32;
+          rw = rw_n; zi = zi_n; zn = zn_n; tf = tf_n; i = i_n; p += 32;
         }
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_raw + 16 + 8 * tile);              // the slot may be overwritten
+      TRACE(tr, 0xA00 + tile);                                          // ... composited
     }
   }
 }
@@ -608,6 +634,9 @@ __global__ void __launch_bounds__(PP_THREADS, 1) nerf_mlp_tc_pp_kernel(const __g
     } else if (warp == 1) {
       if (cta_rank == 0) pp_mma_issuer(plan, sbase, tmem_base, bar_full, bar_empty, bar_acc, bar_aready, unit0, n_steps, n_units, a.dbg);
     } else if (kComp && warp == 2) {
+#if SCADE_TC_TRACE
+      if (!(a.dbg & 128))
+#endif
       pp_compositor(a, bar_raw, cta_rank, unit0, n_steps, n_units, lane);
     }
   } else {
@@ -819,6 +848,21 @@ __global__ void __launch_bounds__(PP_THREADS, 1) nerf_mlp_tc_pp_kernel(const __g
 #pragma unroll
             for (int i = 0; i < 3; ++i) wst[i] = __ldg(reinterpret_cast<const float4*>(&tail->w_rgb_p[0][0]) + i * 32 + lane);
           }
+          // kComp, last step (see pp_compositor): this sample's z, its successor's and the ray's direction norm, fetched under
+          // the MMAs (RS:514-516)
+          float c_z = 0.f, c_zn = 0.f, c_norm = 0.f;
+          bool c_last = false;
+          if (kComp && half == 0 && !has_next) {
+            const int64_t pc = live ? p_raw : 0;
+            const int64_t rc = a.P < (int64_t)0x7fffffff ? (int64_t)((uint32_t)pc / (uint32_t)a.S) : pc / a.S;
+            const int si = (int)(pc - rc * a.S);
+            c_last = si == a.S - 1;
+            c_z = a.z[pc];
+            c_zn = c_last ? c_z : a.z[pc + 1];
+            const float* rd = a.rays + rc * a.ray_stride + 3;
+            const float dx = rd[0], dy = rd[1], dz = rd[2];
+            c_norm = sqrtf(dx * dx + dy * dy + dz * dz);
+          }
           mbar_wait(my_acc, acc_phase);
           acc_phase ^= 1;
           tc_fence_after();
@@ -902,11 +946,27 @@ __global__ void __launch_bounds__(PP_THREADS, 1) nerf_mlp_tc_pp_kernel(const __g
                                             (pb + o.z) + __ldg(&tail->b_rgb[2]), softplus_beta10(al));
             if (live && (!kComp || a.comp.write_raw)) a.out[p_raw] = rawv;
             if (kStash) reinterpret_cast<float*>(sa.ws + sa.L.alpha)[tile_g * TILE_M + row] = al;
+#if SCADE_TC_TRACE
+            if (kComp && !(a.dbg & 128)) {
+#else
             if (kComp) {
+#endif
               // hand the point to the compositor warp: slot free (it has read the previous step's values) -> store -> signal
               if (it > 0) mbar_wait(bar_raw + 16 + 8 * tile, (uint32_t)(it - 1) & 1u);
-              a.comp.ring[(2 * unit0 + cta_rank) * (int64_t)(TILES * TILE_M) + tile * TILE_M + row] = rawv;
+              uint8_t* slot = a.comp.ring + (2 * unit0 + cta_rank) * (int64_t)COMP_RING_BYTES_PER_CTA;
+              float4 park = rawv;
+              if (!has_next) {                              // last step: the per-sample terms, evaluated here (RS:512-520, 543)
+                const SampleTerms t = sample_terms(rawv.w, 0.f, c_z, c_zn, c_last, c_norm);
+                park = make_float4(sigmoidf_(rawv.x), sigmoidf_(rawv.y), sigmoidf_(rawv.z), t.alpha);
+                reinterpret_cast<float*>(slot + TILES * TILE_M * 16)[tile * TILE_M + row] = t.tfac;
+              }
+              reinterpret_cast<float4*>(slot)[tile * TILE_M + row] = park;
               __syncwarp();
+#if SCADE_TC_TRACE
+              if (a.dbg & 256) {                            // timing ablation: arrive without the release
+                if (lane == 0) asm volatile("mbarrier.arrive.relaxed.cta.shared::cta.b64 _, [%0];" ::"r"(bar_raw + 8 * tile) : "memory");
+              } else
+#endif
               if (lane == 0) mbar_arrive(bar_raw + 8 * tile);
             }
           }
@@ -1327,7 +1387,7 @@ int mlp_tc_forward(const scade_net& net, const float* rays, int ray_stride, cons
                 ring_bytes, ws_bytes);
       return SCADE_ERR_WORKSPACE;
     }
-    a.comp.ring = reinterpret_cast<float4*>(workspace);
+    a.comp.ring = reinterpret_cast<uint8_t*>(workspace);
   }
 #if SCADE_TC_TRACE
   { const char* e = getenv("SCADE_TC_DBG"); a.dbg = e ? atoi(e) : 0; }

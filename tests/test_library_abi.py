@@ -105,3 +105,21 @@ def test_packed_stream_size_follows_the_stage_plan():
     assert lib.scade_mlp_packed_bytes(ctypes.byref(_lib.NetDesc(8, 128, 9, 0, 4))) == 0       # width 128: fp32 path only
     assert lib.scade_mlp_packed_bytes(ctypes.byref(_lib.NetDesc(8, 256, 10, 0, 4))) == 0      # 63 encoding columns do not fit
     assert lib.scade_mlp_packed_bytes(ctypes.byref(_lib.NetDesc(8, 256, 9, 2, 4))) == 0       # encoded view directions
+
+
+def test_control_warps_stay_inside_their_registers():
+    """The TMA producer, the MMA issuer and the compositor warp run after `setmaxnreg.dec 32` (csrc/mlp_tc.cu regs_control):
+    no instruction of that region or of the local subroutines it calls may name a register above R31 (tools/sass_regions.py)."""
+    import shutil
+    import subprocess
+    import sys
+    _lib.load()
+    obj = os.path.join(ROOT, "scade_b200", "_lib", "mlp_tc.o")
+    if shutil.which("cuobjdump") is None or not os.path.exists(obj):
+        pytest.skip("needs cuobjdump and the object file of an in-tree build")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "sass_regions.py"), obj], capture_output=True, text=True, check=True).stdout
+    regions = [int(m) for m in re.findall(r"control region \[[^)]*\): max R(\d+)", out)]
+    assert len(regions) >= 3 and max(regions) <= 31, out
+    comp = out.split("nerf_mlp_tc_pp_kernelILb0ELb1")[1].split("_ZN5scade")[0]
+    calls = [int(m) for m in re.findall(r"call target [^:]*: \d+ instructions, max R(\d+)", comp)]
+    assert calls and max(calls) <= 31, out

@@ -22,7 +22,8 @@ CAP = 8192
 dev = torch.device("cuda:0")
 n_rays = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 stash = len(sys.argv) > 2 and sys.argv[2] == "stash"       # trace the training forward (kStash) instead
-S = 192 if stash else 256
+comp = len(sys.argv) > 2 and sys.argv[2] == "comp"         # trace the kernel with the compositor warp (kComp)
+S = int(sys.argv[3]) if len(sys.argv) > 3 else (192 if stash else 256)
 pf = syn.make_nerf_params(seed=11, bias_scale=0.05, alpha_bias=0.5, weight_gain=1.3)
 net = NH.NeRF(D=8, W=256, input_ch=57, input_ch_views=3, output_ch=5, skips=[4], use_viewdirs=True, precision="tc_f16")
 net.load_state_dict({k: torch.from_numpy(v) for k, v in pf.items()})
@@ -49,6 +50,8 @@ with torch.no_grad():
             _lib.check(lib.scade_mlp_forward_rays(ctypes.byref(cnet), _lib.PREC_TC_F16, _lib.ptr(rb), 11, _lib.ptr(z), n_rays, S,
                                                   _lib.host_floats(bb_center), float(bb_scale), _lib.ptr(raw), _lib.ptr(ws), ws.numel(), 1,
                                                   _lib.stream_ptr()), "fwd")
+        elif comp:
+            out = F_.mlp_forward_rays_composite(net.handle(), rb, z, bb_center, bb_scale, "tc_f16")
         else:
             raw = F_.mlp_forward_rays(net.handle(), rb, z, bb_center, bb_scale, "tc_f16")
         e.record()
@@ -120,3 +123,22 @@ for w, name in [(4, "tile0 half0"), (8, "tile0 half1"), (12, "tile1 half0"), (16
     for l in range(NL):
         print(f"   L{l}: {acc_wait[l] / n[l]:8.0f} {ep[l] / n[l]:8.0f} {sig[l] / n[l]:8.0f}")
     print(f"   sums: wait {np.sum(acc_wait / n):.0f}  epilogue {np.sum(ep / n):.0f}  signal {np.sum(sig / n):.0f}  prologue {np.mean(pro):.0f}")
+
+if comp:
+    # ---- compositor warp (warp 2): per tile, wait for the parked values -> composited
+    tag, clk = events(2)
+    t_wait = {}; t_ready = {}; work = [[], []]; waits = [[], []]
+    for g, c in zip(tag, clk):
+        kind, tl = g >> 8, g & 0xFF
+        if kind == 8: t_wait[tl] = c
+        elif kind == 9: t_ready[tl] = c; waits[tl].append(c - t_wait[tl])
+        elif kind == 10: work[tl].append(c - t_ready[tl]); last_done = c
+    for tl in (0, 1):
+        w_, k_ = np.array(waits[tl]), np.array(work[tl])
+        print(f"compositor tile {tl}: {len(k_)} steps; work clk mean {k_.mean():.0f} (first {k_[0]}, last {k_[-1]}); wait mean {w_.mean():.0f} min {w_.min()}")
+    # last epilogue stamp of CTA 0 against the compositor's end
+    ends = []
+    for w in range(4, 20):
+        tg, ck = events(w)
+        if len(ck): ends.append(ck[-1])
+    print(f"compositor ends {last_done - max(ends)} clk after the last epilogue stamp of the CTA")
