@@ -16,15 +16,16 @@
 //   * The two tiles ping-pong: while tile 1's MMAs of layer l run, tile 0's epilogue warps turn its layer-l accumulators into
 //     its layer-(l+1) operand, and vice versa.  Every wide layer is exactly 4 ring stages (no bias stages; the views layer
 //     packs two K chunks per stage), so the ring never blocks a tile on a slot the other tile still holds.
-//   * warp 0: TMA producer; warp 1: TMEM allocator + single-thread tcgen05.mma issuer (warps 2-3 idle; the control
-//     warpgroup hands its registers to the epilogue warpgroups with setmaxnreg); warps 4..19: prologue / epilogue
+//   * warp 0: TMA producer; warp 1: TMEM allocator + single-thread tcgen05.mma issuer; warp 2: the compositor of the kComp
+//     variant (alpha compositing of the values the views epilogue parks for it, see CompArgs), else idle; warp 3 idle; the
+//     control warpgroup hands its registers to the epilogue warpgroups with setmaxnreg; warps 4..19: prologue / epilogue
 //     (thread == one point row x 128 columns): positional encoding straight into the swizzled A tile, then per layer
 //     TMEM -> registers -> + fp32 bias (row broadcast from shared memory) -> ReLU -> fp16 -> swizzled A tile of the next layer.
 //   * Layers whose K includes the encoding chunk (layer 0, the skip layer, the views layer) get their bias from the tensor core:
 //     the packed weights carry fp16 hi/lo halves of the bias in the K positions of the chunk's two constant-1 columns.
 //   * alpha_linear (256->1) is fused into the last hidden layer's epilogue and rgb_linear (128->3) into the views epilogue, both
 //     as fp32 dot products on the un-rounded fp32 activations; softplus(beta=10) is applied before the single float4 store of
-//     (rgb_raw, sigma) per point -- the only HBM write of the kernel.
+//     (rgb_raw, sigma) per point -- the only HBM write of the kernel (kComp: weights and the per-ray maps instead).
 //   * skip connection (H:230) and view concat (H:235) are extra K chunks that re-use the encoding chunk; nothing is
 //     concatenated in memory.
 //   * kStash = true additionally leaves every layer's fp16 operand tile, ReLU sign masks and the alpha pre-activation in the
@@ -175,7 +176,7 @@ __device__ __forceinline__ void sincos_reduced(float arg, float* s, float* c) {
 // pipe) only parks the point's four raw values; warp 2 of the CTA -- otherwise idle -- is the COMPOSITOR: it walks the CTA's
 // points in order, 32 samples of one ray at a time, with the running transmittance and the per-lane partial sums of the ray
 // in registers, exactly like the stand-alone composite_ray_fwd (composite.cuh): same device functions, same operation order,
-// bit-identical results.  It has a whole step (~58k cycles) for 8 chunks of ~1k cycles.
+// bit-identical results.  It has a whole step (~58k cycles) for 8 chunks of ~3k cycles.
 //   S in {32, 64, 128, 256}: steps are strided over the clusters; a CTA's 256 points per step hold whole rays.
 //   any other S ("chain" mode, e.g. the 64 + 128 = 192 samples of the reference's config file): each CTA walks a CONTIGUOUS
 //   range of chain_iters * 256 points that starts and ends on a ray boundary, so a ray that straddles tiles or steps stays
@@ -1332,7 +1333,7 @@ int mlp_tc_pack(const scade_net& net, void* packed_out, cudaStream_t st, bool x3
 }
 
 size_t mlp_tc_workspace_bytes(const scade_net_desc& d, int64_t P, int save) {
-  // without a stash: the hand-over ring of the fused compositing (one 4 KB slot per CTA; sized for any device)
+  // without a stash: the hand-over ring of the fused compositing (one 5 KB slot per CTA; sized for any device)
   return save ? (size_t)tc::train_layout(d, P).total : (size_t)256 * tc::COMP_RING_BYTES_PER_CTA;
 }
 

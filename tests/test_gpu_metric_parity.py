@@ -231,7 +231,7 @@ def test_mlp_x3_vs_oracle(dev, P):
 @pytest.mark.parametrize("S,N", [(64, 37), (128, 19), (256, 5), (256, 300), (128, 1), (32, 77),
                                  (192, 1), (192, 5), (192, 4096), (192, 1237), (96, 50), (320, 9), (512, 3), (224, 611)])
 def test_fused_compositing_is_bit_identical(dev, S, N):
-    """north_star: the cumprod alpha-composite fused into the epilogue of the last GEMM.  scade_mlp_forward_rays_composite
+    """north_star: the cumprod alpha-composite fused into the kernel of the last GEMM.  scade_mlp_forward_rays_composite
     (one kernel: raw never reaches memory) against scade_mlp_forward_rays + scade_raw2outputs (RS:659-660, RS:511-562):
     every output bit-identical, for 1, 2, 4 and 8 warps per ray (whole rays per 256-point step), for the sample counts that
     straddle tiles and steps (192 = the reference config's 64 + 128, 96, 224, 320, 512: the kernel's chain mode), ragged last
