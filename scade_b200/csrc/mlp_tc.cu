@@ -189,6 +189,8 @@ struct CompArgs {
   float* depth_map;               // [N]    nullable
   int write_raw;                  // also store raw [N,S,4] (retraw)
   int chain_iters;                // 0: steps strided over the clusters; > 0: chain mode, steps per CTA
+  int tail_mode;                  // last step of a CTA: the epilogue threads evaluate the per-sample terms (pp_compositor)
+  int pad;
   uint8_t* ring;                  // [CTAs][COMP_RING_BYTES_PER_CTA] hand-over slots (workspace)
 };
 
@@ -498,7 +500,7 @@ __device__ __noinline__ void pp_compositor(const FwdArgs& a, uint32_t bar_raw, u
   [[maybe_unused]] Tracer tr;
   for (int64_t step = unit0; step < n_steps; step += n_units, ++it) {
     const int64_t base = (a.comp.chain_iters > 0 ? cta * (int64_t)a.comp.chain_iters + it : 2 * step + cta_rank) * (int64_t)(TILES * TILE_M);
-    const bool light = step + n_units >= n_steps;                       // last step: the terms arrive evaluated
+    const bool light = a.comp.tail_mode && step + n_units >= n_steps;   // last step: the terms arrive evaluated
     for (int tile = 0; tile < TILES; ++tile) {
       int64_t p = base + tile * TILE_M + lane;                          // a chunk is wholly live or wholly dead: 32 | S | P
       const bool tile_live = p < a.P;
@@ -853,7 +855,7 @@ __global__ void __launch_bounds__(PP_THREADS, 1) nerf_mlp_tc_pp_kernel(const __g
           // the MMAs (RS:514-516)
           float c_z = 0.f, c_zn = 0.f, c_norm = 0.f;
           bool c_last = false;
-          if (kComp && half == 0 && !has_next) {
+          if (kComp && half == 0 && !has_next && a.comp.tail_mode) {
             const int64_t pc = live ? p_raw : 0;
             const int64_t rc = a.P < (int64_t)0x7fffffff ? (int64_t)((uint32_t)pc / (uint32_t)a.S) : pc / a.S;
             const int si = (int)(pc - rc * a.S);
@@ -956,7 +958,7 @@ __global__ void __launch_bounds__(PP_THREADS, 1) nerf_mlp_tc_pp_kernel(const __g
               if (it > 0) mbar_wait(bar_raw + 16 + 8 * tile, (uint32_t)(it - 1) & 1u);
               uint8_t* slot = a.comp.ring + (2 * unit0 + cta_rank) * (int64_t)COMP_RING_BYTES_PER_CTA;
               float4 park = rawv;
-              if (!has_next) {                              // last step: the per-sample terms, evaluated here (RS:512-520, 543)
+              if (!has_next && a.comp.tail_mode) {          // last step: the per-sample terms, evaluated here (RS:512-520, 543)
                 const SampleTerms t = sample_terms(rawv.w, 0.f, c_z, c_zn, c_last, c_norm);
                 park = make_float4(sigmoidf_(rawv.x), sigmoidf_(rawv.y), sigmoidf_(rawv.z), t.alpha);
                 reinterpret_cast<float*>(slot + TILES * TILE_M * 16)[tile * TILE_M + row] = t.tfac;
@@ -1389,6 +1391,8 @@ int mlp_tc_forward(const scade_net& net, const float* rays, int ray_stride, cons
       return SCADE_ERR_WORKSPACE;
     }
     a.comp.ring = reinterpret_cast<uint8_t*>(workspace);
+    static const bool tail_on = [] { const char* e = getenv("SCADE_TC_COMP_TAIL"); return e == nullptr || atoi(e) != 0; }();   // 0: for A/B
+    a.comp.tail_mode = tail_on;
   }
 #if SCADE_TC_TRACE
   { const char* e = getenv("SCADE_TC_DBG"); a.dbg = e ? atoi(e) : 0; }

@@ -7,6 +7,7 @@ CPU or eager fallback: CPU tensors raise.
 from __future__ import annotations
 
 import ctypes
+import math
 from ctypes import byref, c_void_p
 
 import torch
@@ -247,24 +248,40 @@ def composite_fusable(handle, precision, S):
     return bool(_L().scade_mlp_forward_rays_composite_supported(byref(handle.desc), PRECISIONS[precision], int(S)))
 
 
-def mlp_forward_rays_composite(handle, rays, z_vals, bb_center, bb_scale, precision=PREC_TC_F16, retraw=False):
+def composite_buffers(handle, N, S, precision=PREC_TC_F16, retraw=False, device=None):
+    """Outputs + workspace of one mlp_forward_rays_composite call, as ONE allocation each (pass as `out=` to reuse them)."""
+    precision = PRECISIONS[precision]
+    n_raw = N * S * 4 if retraw else 0
+    flat = torch.empty(n_raw + N * S + 6 * N, dtype=torch.float32, device=device)      # raw first: it needs 16-byte alignment
+    o = n_raw
+    buf = {"raw": flat[:n_raw].view(N, S, 4) if retraw else None}
+    for key, shape in (("weights", (N, S)), ("rgb", (N, 3)), ("disp", (N,)), ("acc", (N,)), ("depth", (N,))):
+        n = math.prod(shape)
+        buf[key] = flat[o:o + n].view(shape)
+        o += n
+    buf["ws"] = torch.empty(handle.workspace_bytes(N * S, precision, 0), dtype=torch.uint8, device=device)
+    return buf
+
+
+def mlp_forward_rays_composite(handle, rays, z_vals, bb_center, bb_scale, precision=PREC_TC_F16, retraw=False, out=None):
     """run_network + raw2outputs (RS:659-660 / RS:718-720) as one kernel (no autograd): the alpha compositing runs on a
-    compositor warp of the tensor-core kernel, fed by the epilogue of its last layer.  Returns (rgb_map, disp_map, acc_map, weights, depth_map, raw or None)."""
+    compositor warp of the tensor-core kernel, fed by the epilogue of its last layer.  Returns (rgb_map, disp_map, acc_map,
+    weights, depth_map, raw or None); `out` = composite_buffers(...) of the same shape writes into existing buffers."""
     precision = PRECISIONS[precision]
     rays, z_vals = f32(rays), f32(z_vals)
     N, S = z_vals.shape
-    dev = z_vals.device
-    rgb = torch.empty((N, 3), dtype=torch.float32, device=dev)
-    disp, acc, depth = (torch.empty((N,), dtype=torch.float32, device=dev) for _ in range(3))
-    w = torch.empty((N, S), dtype=torch.float32, device=dev)
-    raw = torch.empty((N, S, 4), dtype=torch.float32, device=dev) if retraw else None
+    b = out if out is not None else composite_buffers(handle, N, S, precision, retraw, z_vals.device)
+    if b["weights"].shape != (N, S) or (retraw and b["raw"] is None):
+        raise ValueError("mlp_forward_rays_composite: `out` was made for another shape")
+    raw = b["raw"] if retraw else None
     net = handle.struct(precision)
-    ws = torch.empty(handle.workspace_bytes(N * S, precision, 0), dtype=torch.uint8, device=dev)
+    ws = b["ws"]
     check(_L().scade_mlp_forward_rays_composite(byref(net), precision, ptr(rays), rays.shape[1], ptr(z_vals), N, S,
-                                                _lib.host_floats([float(c) for c in bb_center]), float(bb_scale), ptr(raw), ptr(w),
-                                                ptr(rgb), ptr(disp), ptr(acc), ptr(depth), ptr(ws), ws.numel(), stream_ptr()),
+                                                _lib.host_floats([float(c) for c in bb_center]), float(bb_scale), ptr(raw),
+                                                ptr(b["weights"]), ptr(b["rgb"]), ptr(b["disp"]), ptr(b["acc"]), ptr(b["depth"]),
+                                                ptr(ws), ws.numel(), stream_ptr()),
           "scade_mlp_forward_rays_composite")
-    return rgb, disp, acc, w, depth, raw
+    return b["rgb"], b["disp"], b["acc"], b["weights"], b["depth"], raw
 
 
 def mlp_forward_embedded(handle, x, precision=PREC_FP32):
