@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define SCADE_B200_VERSION 102
+#define SCADE_B200_VERSION 103
 
 typedef enum {
   SCADE_OK = 0,
@@ -129,6 +129,12 @@ int scade_mlp_backward(const scade_net* net, int precision, const float* d_out, 
  * Every activation region is [T][chunks][128 rows][128 B]: the K-major SWIZZLE_128B image of a [128 points x 64
  * features] fp16 tile (16-byte piece j of row r sits at r*128 + ((j ^ (r & 7)) << 4)). */
 int scade_mlp_tc_stash_layout(const scade_net_desc* desc, int64_t P, int64_t* out, int n);
+
+/* Diagnostic (host arithmetic, no GPU): how scade_mlp_forward_rays_composite splits N rays of S samples over the SM pairs of a
+ * device with n_sms SMs.  *clusters = SM pairs launched (2 CTAs each).  *chain_iters = 0: 512-point steps strided over the
+ * clusters, every CTA's 256 points per step are whole rays (S in {32, 64, 128, 256}).  *chain_iters > 0: CTA c walks the
+ * contiguous points [c * chain_iters * 256, (c + 1) * chain_iters * 256), a range that starts and ends on a ray boundary. */
+int scade_mlp_composite_plan(int S, int64_t N, int n_sms, int* clusters, int* chain_iters);
 
 /* Embedder.embed (H:171-172): x [P,3] -> [P, 3 + 6*multires]. */
 int scade_embed(const float* x, int64_t P, int multires, float* out, void* stream);

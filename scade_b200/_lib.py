@@ -62,6 +62,7 @@ _SIGNATURES = {
     "scade_mlp_forward_embedded": (c_int, [POINTER(Net), c_int, _P, c_int64, _P, _P, c_size_t, c_int, _P]),
     "scade_mlp_backward": (c_int, [POINTER(Net), c_int, _P, c_int64, POINTER(c_void_p), _P, c_size_t, _P]),
     "scade_mlp_tc_stash_layout": (c_int, [POINTER(NetDesc), c_int64, POINTER(c_int64), c_int]),
+    "scade_mlp_composite_plan": (c_int, [c_int, c_int64, c_int, POINTER(c_int), POINTER(c_int)]),
     "scade_embed": (c_int, [_P, c_int64, c_int, _P, _P]),
     "scade_get_rays": (c_int, [c_int, c_int, POINTER(c_float), POINTER(c_float), c_int, c_int, _P, _P, _P]),
     "scade_make_ray_batch": (c_int, [_P, _P, c_int64, c_float, c_float, _P, _P]),

@@ -170,6 +170,15 @@ extern "C" int scade_mlp_tc_stash_layout(const scade_net_desc* desc, int64_t P, 
   return mlp_tc_stash_layout(*desc, P, out, n);
 }
 
+extern "C" int scade_mlp_composite_plan(int S, int64_t N, int n_sms, int* clusters, int* chain_iters) {
+  SCADE_CHECK_ARG(clusters && chain_iters && N >= 0 && n_sms >= 2 && mlp_tc_composite_supported(S),
+                  "mlp_composite_plan: bad arguments (S must be a multiple of 32)");
+  const MlpCompositePlan cp = mlp_tc_composite_plan(S, N * (int64_t)S, n_sms);
+  *clusters = cp.clusters;
+  *chain_iters = cp.chain_iters;
+  return SCADE_OK;
+}
+
 extern "C" int scade_embed(const float* x, int64_t P, int multires, float* out, void* stream) {
   SCADE_CHECK_ARG(x && out && P >= 0 && multires >= 0 && multires <= 16, "embed: bad arguments");
   if (P == 0) return SCADE_OK;

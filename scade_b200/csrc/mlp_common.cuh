@@ -48,6 +48,11 @@ struct MlpCompositeOut {
 inline bool mlp_tc_composite_supported(int S) { return S >= 32 && S % 32 == 0 && S <= 8192; }
 // whole rays inside a CTA's 256 points per step; any other supported S runs the kernel's chain mode
 inline bool mlp_tc_composite_strided(int S) { return S == 32 || S == 64 || S == 128 || S == 256; }
+// How the fused kernel splits P = N*S points over the SM pairs (host arithmetic only).  clusters = SM pairs launched;
+// chain_iters = 0: 512-point cluster steps strided over the clusters; > 0 (chain mode): CTA c of the 2*clusters CTAs walks
+// the contiguous points [c * chain_iters * 256, (c + 1) * chain_iters * 256), a range that starts and ends on a ray boundary.
+struct MlpCompositePlan { int clusters; int chain_iters; };
+MlpCompositePlan mlp_tc_composite_plan(int S, int64_t P, int n_sms);
 
 // entry points implemented in mlp_tc.cu (tcgen05 path)
 bool mlp_tc_supported(const scade_net_desc& d);

@@ -1334,6 +1334,21 @@ int mlp_tc_pack(const scade_net& net, void* packed_out, cudaStream_t st, bool x3
   return SCADE_OK;
 }
 
+MlpCompositePlan mlp_tc_composite_plan(int S, int64_t P, int n_sms) {
+  const int64_t cta_steps = ceil_div<int64_t>(P, tc::TILES * tc::TILE_M);           // 256-point steps in all
+  const int pairs = n_sms / 2;
+  MlpCompositePlan cp{};
+  if (mlp_tc_composite_strided(S)) {
+    cp.clusters = (int)std::min<int64_t>((cta_steps + 1) / 2, pairs);
+    return cp;
+  }
+  const int64_t period = S / std::gcd(S, tc::TILES * tc::TILE_M);                    // steps after which a range is on a ray boundary again
+  const int64_t iters = ceil_div<int64_t>(ceil_div<int64_t>(cta_steps, 2 * pairs), period) * period;
+  cp.clusters = (int)ceil_div<int64_t>(cta_steps, 2 * iters);
+  cp.chain_iters = (int)iters;
+  return cp;
+}
+
 size_t mlp_tc_workspace_bytes(const scade_net_desc& d, int64_t P, int save) {
   // without a stash: the hand-over ring of the fused compositing (one 5 KB slot per CTA; sized for any device)
   return save ? (size_t)tc::train_layout(d, P).total : (size_t)256 * tc::COMP_RING_BYTES_PER_CTA;
@@ -1421,17 +1436,12 @@ int mlp_tc_forward(const scade_net& net, const float* rays, int ray_stride, cons
     SCADE_LAUNCH_CHECK();
     return SCADE_OK;
   }
-  int64_t n_steps = (a.n_pairs + 1) / 2;
-  int clusters = (int)std::min<int64_t>(n_steps, num_sms() / 2);
-  if (comp != nullptr && !mlp_tc_composite_strided(S)) {
-    // chain mode (CompArgs): every CTA walks chain_iters consecutive 256-point steps; ranges start and end on ray boundaries
-    const int64_t cta_steps = a.n_pairs;                              // 256-point steps in all
-    const int64_t period = S / std::gcd(S, tc::TILES * tc::TILE_M);  // steps after which a range is on a ray boundary again
-    const int64_t iters = ceil_div<int64_t>(ceil_div<int64_t>(cta_steps, 2 * (num_sms() / 2)), period) * period;
-    clusters = (int)ceil_div<int64_t>(cta_steps, 2 * iters);
-    a.comp.chain_iters = (int)iters;
-    a.n_pairs = 2 * iters * clusters;                                 // every cluster runs exactly `iters` steps
-    n_steps = iters * clusters;
+  int clusters = (int)std::min<int64_t>((a.n_pairs + 1) / 2, num_sms() / 2);
+  if (comp != nullptr) {
+    const MlpCompositePlan cp = mlp_tc_composite_plan(S, a.P, num_sms());
+    clusters = cp.clusters;
+    a.comp.chain_iters = cp.chain_iters;
+    if (cp.chain_iters > 0) a.n_pairs = 2 * (int64_t)cp.chain_iters * clusters;      // every cluster runs exactly chain_iters steps
   }
   void* args[] = {&a, &plan, &tmap, &sa};
   if (comp != nullptr)

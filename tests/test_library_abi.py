@@ -26,7 +26,7 @@ def test_library_loads_and_exports_every_symbol():
     lib = _lib.load()
     for name in header_symbols():
         assert hasattr(lib, name), name
-    assert lib.scade_version() == 102
+    assert lib.scade_version() == 103
 
 
 def test_argument_validation_without_gpu():
@@ -123,3 +123,37 @@ def test_control_warps_stay_inside_their_registers():
     comp = out.split("nerf_mlp_tc_pp_kernelILb0ELb1")[1].split("_ZN5scade")[0]
     calls = [int(m) for m in re.findall(r"call target [^:]*: \d+ instructions, max R(\d+)", comp)]
     assert calls and max(calls) <= 31, out
+
+
+def _composite_plan(lib, S, N, n_sms):
+    c, it = ctypes.c_int(), ctypes.c_int()
+    assert lib.scade_mlp_composite_plan(S, N, n_sms, ctypes.byref(c), ctypes.byref(it)) == 0
+    return c.value, it.value
+
+
+@pytest.mark.parametrize("n_sms", [148, 132, 8])
+def test_fused_compositing_partition(n_sms):
+    """How the fused network + compositing kernel splits the points (scade_mlp_composite_plan, the arithmetic its launch uses):
+    never more SM pairs than the device has; every point is covered; in chain mode (rays that straddle 128-point tiles, e.g.
+    64 + 128 = 192 samples) every CTA's contiguous range starts and ends on a ray boundary, so no ray is split between two
+    compositor warps; and the padding stays below one period of steps per CTA."""
+    import math
+    lib = _lib.load()
+    rng = np.random.default_rng(5)
+    for S in (32, 64, 96, 128, 160, 192, 224, 256, 320, 384, 512, 1024, 8192):
+        for N in [1, 2, 3, 5, 37, 300, 1024, 4096, 32768, 307200] + [int(v) for v in rng.integers(1, 50000, 6)]:
+            clusters, iters = _composite_plan(lib, S, N, n_sms)
+            P = N * S
+            cta_steps = -(-P // 256)
+            assert 1 <= clusters <= n_sms // 2
+            if S in (32, 64, 128, 256):
+                assert iters == 0 and clusters == min((cta_steps + 1) // 2, n_sms // 2)
+                continue
+            period = S // math.gcd(S, 256)
+            assert iters > 0 and iters % period == 0                      # (iters * 256) % S == 0: ranges end on ray boundaries
+            assert (iters * 256) % S == 0
+            assert 2 * clusters * iters * 256 >= P                        # covered
+            assert 2 * (clusters - 1) * iters * 256 < P                   # no idle cluster
+            assert iters < -(-cta_steps // (2 * (n_sms // 2))) + period   # at most one period of padding per CTA
+    c, it = ctypes.c_int(), ctypes.c_int()
+    assert lib.scade_mlp_composite_plan(200, 10, n_sms, ctypes.byref(c), ctypes.byref(it)) != 0      # not a multiple of 32
