@@ -157,3 +157,24 @@ def test_fused_compositing_partition(n_sms):
             assert iters < -(-cta_steps // (2 * (n_sms // 2))) + period   # at most one period of padding per CTA
     c, it = ctypes.c_int(), ctypes.c_int()
     assert lib.scade_mlp_composite_plan(200, 10, n_sms, ctypes.byref(c), ctypes.byref(it)) != 0      # not a multiple of 32
+
+
+@pytest.mark.parametrize("retraw", [False, True])
+def test_composite_buffers_layout(retraw):
+    """functional.composite_buffers: one allocation for the outputs of scade_mlp_forward_rays_composite (raw first, 16-byte
+    aligned as the C entry point requires), the reference's shapes (RS:556-560), and a workspace of the size the library asks for."""
+    import torch
+    from scade_b200 import functional as F_, nerf_helpers as NH
+    net = NH.NeRF(D=8, W=256, input_ch=57, input_ch_views=3, output_ch=5, skips=[4], use_viewdirs=True, precision="tc_f16")
+    h = net.handle()
+    N, S = 37, 192
+    b = F_.composite_buffers(h, N, S, "tc_f16", retraw=retraw, device=torch.device("cpu"))
+    assert b["weights"].shape == (N, S) and b["rgb"].shape == (N, 3)
+    assert b["disp"].shape == b["acc"].shape == b["depth"].shape == (N,)
+    assert (b["raw"] is None) == (not retraw)
+    if retraw:
+        assert b["raw"].shape == (N, S, 4) and b["raw"].data_ptr() % 16 == 0
+    ptrs = sorted((t.data_ptr(), t.numel() * 4) for k, t in b.items() if k != "ws" and t is not None)
+    for (p0, n0), (p1, _) in zip(ptrs, ptrs[1:]):
+        assert p0 + n0 <= p1                                              # views of one buffer, no overlap
+    assert b["ws"].numel() == h.workspace_bytes(N * S, _lib.PREC_TC_F16, 0) >= 148 * 5120 and b["ws"].data_ptr() % 16 == 0
